@@ -1,0 +1,217 @@
+// Channel LayerNorm (modules.py:19-31) and weight-norm + operand packing (torch.nn.utils.weight_norm call
+// sites: modules.py:154-171,226-296; models.py:425-435,489-587).
+#include "evk_common.cuh"
+
+namespace evk {
+
+// one warp per row; C <= 32*MAXV
+constexpr int LN_MAXV = 32;   // up to 1024 channels
+
+__global__ void layernorm_fwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ res, int ldr,
+                                     const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                     float* __restrict__ y, int ldy, float* __restrict__ stats, long long rows, int C) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float v[LN_MAXV];
+  float s = 0.f;
+  int nv = 0;
+  for (int c = lane; c < C; c += 32, ++nv) {
+    float t = x[row * ldx + c];
+    if (res) t += res[row * ldr + c];
+    v[nv] = t;
+    s += t;
+  }
+  s = warp_sum(s);
+  const float mean = s / (float)C;
+  float q = 0.f;
+  for (int i = 0; i < nv; ++i) { float d = v[i] - mean; q += d * d; }
+  q = warp_sum(q);
+  const float rstd = rsqrtf(q / (float)C + eps);
+  nv = 0;
+  for (int c = lane; c < C; c += 32, ++nv) y[row * ldy + c] = (v[nv] - mean) * rstd * gamma[c] + beta[c];
+  if (lane == 0 && stats) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
+}
+
+// dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)); dgamma += dy*xhat; dbeta += dy
+__global__ void layernorm_bwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ res, int ldr,
+                                     const float* __restrict__ gamma, const float* __restrict__ stats,
+                                     const float* __restrict__ dy, int lddy, float* __restrict__ dx, int lddx,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C,
+                                     int rows_per_block) {
+  extern __shared__ float sm[];              // [2][C] partial dgamma/dbeta of this block
+  float* sg = sm;
+  float* sb = sm + C;
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  for (long long row = r0 + wid; row < r1; row += nw) {
+    const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
+    float xh[LN_MAXV], gd[LN_MAXV];
+    float s1 = 0.f, s2 = 0.f;
+    int nv = 0;
+    for (int c = lane; c < C; c += 32, ++nv) {
+      float t = x[row * ldx + c];
+      if (res) t += res[row * ldr + c];
+      const float h = (t - mean) * rstd;
+      const float d = dy[row * lddy + c];
+      const float g = d * gamma[c];
+      xh[nv] = h; gd[nv] = g;
+      s1 += g; s2 += g * h;
+      atomicAdd(&sg[c], d * h);
+      atomicAdd(&sb[c], d);
+    }
+    s1 = warp_sum(s1) / (float)C;
+    s2 = warp_sum(s2) / (float)C;
+    nv = 0;
+    for (int c = lane; c < C; c += 32, ++nv) dx[row * lddx + c] = rstd * (gd[nv] - s1 - xh[nv] * s2);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(&dgamma[c], sg[c]);
+    atomicAdd(&dbeta[c], sb[c]);
+  }
+}
+
+// ---- weight-norm + pack ------------------------------------------------------------------
+// block per d0: w[d0][d1][q] = v * (g[d0] / ||v[d0]||);  PA[q][d0][d1], PB[q][d1][d0]
+__global__ void weight_pack_kernel(const float* __restrict__ v, const float* __restrict__ g, int D0, int D1, int Q,
+                                   float* __restrict__ pa, int lda, float* __restrict__ pb, int ldb) {
+  __shared__ float red[33];
+  const int d0 = blockIdx.x;
+  const long long n = (long long)D1 * Q;
+  const float* vr = v + (long long)d0 * n;
+  float scale = 1.f;
+  if (g) {
+    float s = 0.f;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) s += vr[i] * vr[i];
+    s = block_sum(s, red);
+    scale = g[d0] / sqrtf(s);
+  }
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const int d1 = (int)(i / Q), q = (int)(i - (long long)d1 * Q);
+    const float w = vr[i] * scale;
+    pa[((long long)q * D0 + d0) * lda + d1] = w;
+    if (pb) pb[((long long)q * D1 + d1) * ldb + d0] = w;
+  }
+}
+
+__global__ void weight_pack_bwd_kernel(const float* __restrict__ dpa, int lda, const float* __restrict__ v,
+                                       const float* __restrict__ g, int D0, int D1, int Q, float* __restrict__ dv,
+                                       float* __restrict__ dg) {
+  __shared__ float red[33];
+  const int d0 = blockIdx.x;
+  const long long n = (long long)D1 * Q;
+  const float* vr = v + (long long)d0 * n;
+  float* dvr = dv + (long long)d0 * n;
+  if (!g) {
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+      const int d1 = (int)(i / Q), q = (int)(i - (long long)d1 * Q);
+      dvr[i] = dpa[((long long)q * D0 + d0) * lda + d1];
+    }
+    return;
+  }
+  float ss = 0.f, dot = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const int d1 = (int)(i / Q), q = (int)(i - (long long)d1 * Q);
+    const float vv = vr[i];
+    ss += vv * vv;
+    dot += dpa[((long long)q * D0 + d0) * lda + d1] * vv;
+  }
+  ss = block_sum(ss, red);
+  dot = block_sum(dot, red);
+  const float nrm = sqrtf(ss), gg = g[d0];
+  if (threadIdx.x == 0) dg[d0] = dot / nrm;
+  const float sc = gg / nrm, k = dot / ss;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const int d1 = (int)(i / Q), q = (int)(i - (long long)d1 * Q);
+    dvr[i] = sc * (dpa[((long long)q * D0 + d0) * lda + d1] - vr[i] * k);
+  }
+}
+
+__global__ void colsum_kernel(const float* __restrict__ x, long long rows, int n, int ld, float* __restrict__ out,
+                              int rows_per_block) {
+  // blockDim = (32, 8): 32 columns x 8 row-lanes
+  __shared__ float part[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const long long r0 = (long long)blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+  float acc = 0.f;
+  if (c < n)
+    for (long long r = r0 + threadIdx.y; r < r1; r += 8) acc += x[r * ld + c];
+  part[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < n) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += part[k][threadIdx.x];
+    atomicAdd(&out[c], s);
+  }
+}
+
+__global__ void zero_kernel(float* p, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.f;
+}
+
+}  // namespace evk
+using namespace evk;
+#define ST ((cudaStream_t)stream)
+
+extern "C" int evk_layernorm_fwd(const float* x, int32_t ldx, const float* res, int32_t ldr, const float* gamma,
+                                 const float* beta, float eps, float* y, int32_t ldy, float* stats, int64_t rows,
+                                 int32_t C, evk_stream_t stream) {
+  EVK_REQUIRE(x && gamma && beta && y, EVK_ERR_ARG, "layernorm_fwd: null tensor");
+  EVK_REQUIRE(C >= 1 && C <= 32 * LN_MAXV, EVK_ERR_UNSUPPORTED, "layernorm_fwd: C=%d unsupported", C);
+  if (rows == 0) return EVK_OK;
+  layernorm_fwd_kernel<<<cdiv(rows, 8), 256, 0, ST>>>(x, ldx, res, ldr, gamma, beta, eps, y, ldy, stats, rows, C);
+  return check_launch("layernorm_fwd");
+}
+
+extern "C" int evk_layernorm_bwd(const float* x, int32_t ldx, const float* res, int32_t ldr, const float* gamma,
+                                 const float* stats, const float* dy, int32_t lddy, float* dx, int32_t lddx,
+                                 float* dgamma, float* dbeta, int64_t rows, int32_t C, evk_stream_t stream) {
+  EVK_REQUIRE(x && gamma && stats && dy && dx && dgamma && dbeta, EVK_ERR_ARG, "layernorm_bwd: null tensor");
+  EVK_REQUIRE(C >= 1 && C <= 32 * LN_MAXV, EVK_ERR_UNSUPPORTED, "layernorm_bwd: C=%d unsupported", C);
+  if (rows == 0) return EVK_OK;
+  int rpb = (int)((rows + 148 * 4 - 1) / (148 * 4));
+  if (rpb < 8) rpb = 8;
+  layernorm_bwd_kernel<<<cdiv(rows, rpb), 256, 2 * C * sizeof(float), ST>>>(x, ldx, res, ldr, gamma, stats, dy, lddy, dx,
+                                                                            lddx, dgamma, dbeta, rows, C, rpb);
+  return check_launch("layernorm_bwd");
+}
+
+extern "C" int evk_weight_pack(const float* v, const float* g, int32_t D0, int32_t D1, int32_t Q, float* pa,
+                               int32_t lda, float* pb, int32_t ldb, evk_stream_t stream) {
+  EVK_REQUIRE(v && pa && D0 >= 1 && D1 >= 1 && Q >= 1 && lda >= D1 && (!pb || ldb >= D0), EVK_ERR_ARG,
+              "weight_pack: bad arguments");
+  weight_pack_kernel<<<D0, 256, 0, ST>>>(v, g, D0, D1, Q, pa, lda, pb, ldb);
+  return check_launch("weight_pack");
+}
+
+extern "C" int evk_weight_pack_bwd(const float* dpa, int32_t lda, const float* v, const float* g, int32_t D0,
+                                   int32_t D1, int32_t Q, float* dv, float* dg, evk_stream_t stream) {
+  EVK_REQUIRE(dpa && v && dv && (!g || dg), EVK_ERR_ARG, "weight_pack_bwd: null tensor");
+  weight_pack_bwd_kernel<<<D0, 256, 0, ST>>>(dpa, lda, v, g, D0, D1, Q, dv, dg);
+  return check_launch("weight_pack_bwd");
+}
+
+extern "C" int evk_colsum(const float* x, int64_t rows, int32_t n, int32_t ld, float* out, int32_t accumulate,
+                          evk_stream_t stream) {
+  EVK_REQUIRE(x && out && n >= 1, EVK_ERR_ARG, "colsum: bad arguments");
+  if (!accumulate) {
+    zero_kernel<<<cdiv(n, 256), 256, 0, ST>>>(out, n);
+    int rc = check_launch("colsum_zero");
+    if (rc) return rc;
+  }
+  if (rows == 0) return EVK_OK;
+  int nb = cdiv(n, 32);
+  long long want = (148LL * 8 + nb - 1) / nb;
+  int rpb = (int)((rows + want - 1) / want);
+  if (rpb < 64) rpb = 64;
+  dim3 grid(nb, cdiv(rows, rpb)), block(32, 8);
+  EVK_REQUIRE(grid.y <= 65535, EVK_ERR_ARG, "colsum: grid too large");
+  colsum_kernel<<<grid, block, 0, ST>>>(x, rows, n, ld, out, rpb);
+  return check_launch("colsum");
+}

@@ -1,0 +1,1166 @@
+"""Autograd operators over channels-last tensors, each a thin wrapper around libevk_sm100 kernels.
+
+Layout: an activation is [B, T, C] fp32 with unit channel stride (row pitch = stride(-2)); column slices of a
+contiguous tensor are valid operands (no copies).  Discriminator "period" views are [B, H*P, C] with the inner
+width P passed explicitly.  Lengths are int32 device tensors [B].
+
+Nothing here falls back to torch math: if the library or the GPU is missing, `lib.init()` raises.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import lib as L
+
+ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH = 0, 1, 2, 3
+UN_SCALE, UN_LRELU, UN_TANH, UN_MISH, UN_RELU, UN_TANH_FROM_OUT = 0, 1, 2, 3, 4, 5
+
+_launches = 0          # number of libevk kernel-launching calls (bench.py reports it)
+
+
+def launches():
+    return _launches
+
+
+def _lib():
+    return L.init()
+
+
+def _st():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _call(name, *args):
+    global _launches
+    _launches += 1
+    L.check(getattr(_lib(), name)(*args, _st()))
+
+
+def _rows(t):
+    """-> (rows, C, ld) of a channels-last tensor viewed as a row matrix."""
+    assert t.dtype == torch.float32 and t.is_cuda, (t.dtype, t.device)
+    if t.dim() == 1:
+        return 1, t.shape[0], t.shape[0]
+    C = t.shape[-1]
+    assert C == 1 or t.stride(-1) == 1, f"channel stride must be 1, got {t.stride()}"
+    if t.dim() == 2:
+        return t.shape[0], C, (t.stride(0) if t.shape[0] > 1 else max(C, t.stride(0)))
+    assert t.dim() == 3
+    B, T, _ = t.shape
+    if T == 1:
+        ld = t.stride(0) if B > 1 else C
+    else:
+        ld = t.stride(1)
+        assert B == 1 or t.stride(0) == T * ld, f"batch stride {t.stride(0)} != T*ld {T * ld}"
+    return B * T, C, ld
+
+
+def _c(t):
+    """contiguous channels-last (copies only when needed)."""
+    return t if (t.stride(-1) == 1 or t.shape[-1] == 1) and t.is_contiguous() else t.contiguous()
+
+
+def _ok_rows(t):
+    try:
+        _rows(t)
+        return True
+    except AssertionError:
+        return False
+
+
+def _cl(t):
+    return t if _ok_rows(t) else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------
+# RNG state (device resident => CUDA-graph replay safe)
+# ------------------------------------------------------------------------------------------------
+_rng = {}
+
+
+def rng_state(device=None):
+    device = device or torch.device("cuda", torch.cuda.current_device())
+    key = str(device)
+    if key not in _rng:
+        _rng[key] = torch.tensor([1234, 0], dtype=torch.int64, device=device)
+    return _rng[key]
+
+
+def manual_seed(seed, device=None):
+    st = rng_state(device)
+    st.copy_(torch.tensor([seed, 0], dtype=torch.int64))
+
+
+def advance_rng(inc=1 << 32):
+    _call("evk_advance_rng", _p(rng_state()), ctypes.c_uint64(inc))
+
+
+_stream_ids = {}
+
+
+def stream_id(tag):
+    """stable small integer per call-site tag (Philox stream selector)."""
+    if tag not in _stream_ids:
+        _stream_ids[tag] = len(_stream_ids) + 1
+    return _stream_ids[tag]
+
+
+# ------------------------------------------------------------------------------------------------
+# descriptor helpers
+# ------------------------------------------------------------------------------------------------
+def _desc(**kw):
+    d = L.GconvDesc()
+    off = kw.pop("off")
+    for k, v in kw.items():
+        if k in ("x", "w", "y", "res", "bias", "in_len", "out_len"):
+            setattr(d, k, v.data_ptr() if v is not None else None)
+        else:
+            setattr(d, k, v)
+    assert len(off) <= L.MAX_TAPS
+    for i, o in enumerate(off):
+        d.off[i] = int(o)
+    if not d.H:
+        d.H = 1
+    if not d.G:
+        d.G = 1
+    return d
+
+
+def _run_desc(fn, d):
+    global _launches
+    _launches += 1
+    L.check(getattr(_lib(), fn)(ctypes.byref(d), _st()))
+
+
+def _aligned(t, ld):
+    return (ld % 4 == 0) and (t.data_ptr() % 16 == 0)
+
+
+class PackedW:
+    """Operand-packed weight: pa [Q, D0, lda] (differentiable), pb [Q, D1, ldb] (derived copy)."""
+    __slots__ = ("pa", "pb", "D0", "D1", "Q")
+
+    def __init__(self, pa, pb, D0, D1, Q):
+        self.pa, self.pb, self.D0, self.D1, self.Q = pa, pb, D0, D1, Q
+
+
+def _pad4(n):
+    return n if n < 4 else (n + 3) // 4 * 4
+
+
+class _PackFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, v, g, need_pb):
+        D0 = v.shape[0]
+        D1 = v.shape[1]
+        Q = v.numel() // (D0 * D1)
+        lda, ldb = _pad4(D1), _pad4(D0)
+        pa = (torch.zeros if lda != D1 else torch.empty)((Q, D0, lda), device=v.device, dtype=torch.float32)
+        pb = None
+        if need_pb:
+            pb = (torch.zeros if ldb != D0 else torch.empty)((Q, D1, ldb), device=v.device, dtype=torch.float32)
+        vc = v.contiguous()
+        gc = g.contiguous() if g is not None else None
+        _call("evk_weight_pack", _p(vc), _p(gc), D0, D1, Q, _p(pa), lda, _p(pb), ldb)
+        ctx.save_for_backward(vc, gc)
+        ctx.dims = (D0, D1, Q, lda, tuple(v.shape), tuple(g.shape) if g is not None else None)
+        if pb is None:
+            pb = torch.empty(0, device=v.device)
+        ctx.mark_non_differentiable(pb)
+        return pa, pb
+
+    @staticmethod
+    def backward(ctx, dpa, _dpb):
+        v, g = ctx.saved_tensors
+        D0, D1, Q, lda, vshape, gshape = ctx.dims
+        dpa = dpa.contiguous()
+        dv = torch.empty(vshape, device=v.device, dtype=torch.float32)
+        dg = torch.empty(gshape, device=v.device, dtype=torch.float32) if g is not None else None
+        _call("evk_weight_pack_bwd", _p(dpa), lda, _p(v), _p(g), D0, D1, Q, _p(dv), _p(dg))
+        return dv, dg, None
+
+
+def pack_weight(v, g=None, need_pb=True):
+    """weight-norm (if g) + pack.  v: torch-layout weight [D0, D1, Q(,1)]."""
+    pa, pb = _PackFn.apply(v, g, need_pb)
+    D0, D1 = v.shape[0], v.shape[1]
+    return PackedW(pa, pb if need_pb else None, D0, D1, v.numel() // (D0 * D1))
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution family
+# ------------------------------------------------------------------------------------------------
+def _conv_out_len(Tin, Q, stride, pad, dil):
+    return (Tin + 2 * pad - dil * (Q - 1) - 1) // stride + 1
+
+
+def _fwd_like(x, Tin, w, wq0, wqstep, nq, ldw, w_sq, C, N, y, *, J, P, is_, os_, o0, Tout, off, bias=None, res=None,
+              act=0, slope=0.0, in_len=None, out_len=None, G=1):
+    """one launch of the generalised conv (tensor-core kernel when alignment allows, else direct)."""
+    B = x.shape[0]
+    _, _, ldx = _rows(x)
+    _, _, ldy = _rows(y)
+    ldr = _rows(res)[2] if res is not None else 0
+    wbase = w.data_ptr() + 4 * wq0 * w_sq
+    d = _desc(x=x, w=None, y=y, res=res, bias=bias, in_len=in_len, out_len=out_len,
+              x_sb=Tin * P * ldx, x_sh=0, w_sb=0, w_sh=0, w_sq=wqstep * w_sq, y_sb=Tout * P * ldy, y_sh=0,
+              r_sb=Tout * P * ldr, r_sh=0, ldx=ldx, ldw=ldw, ldy=ldy, ldr=ldr, Z=B, H=1, C=C, N=N, Q=nq, G=G,
+              Tin=Tin, J=J, P=P, is_=is_, os_=os_, o0=o0, Tout=Tout, act=act, slope=float(slope), off=off)
+    d.w = wbase
+    mma = G == 1 and _aligned(x, ldx) and ldw % 4 == 0 and (wbase % 16 == 0) and (d.w_sq % 4 == 0)
+    _run_desc("evk_gconv_fwd" if mma else "evk_conv_direct_fwd", d)
+
+
+def _dgrad_phases(dy, Jy, pb, ldb, C, N, Q, dx, Tin, P, stride, pad, dil):
+    """dX[u] = sum_q sum_n dY[(u+pad-q*dil)/stride][n] * PB[q][c][n] as one F launch per stride phase."""
+    assert stride == 1 or dil == 1, "strided convs must have dilation 1"
+    w_sq = pb.shape[1] * ldb
+    for rho in range(stride):
+        taps = list(range(rho, Q, stride))
+        u0 = (rho - pad) % stride
+        if u0 >= Tin:
+            continue
+        Ju = (Tin - u0 + stride - 1) // stride
+        if not taps:
+            continue
+        if stride == 1:
+            off = [pad - q * dil for q in taps]
+        else:
+            off = [(u0 + pad - q) // stride for q in taps]
+        _fwd_like(dy, Jy, pb, taps[0], stride, len(taps), ldb, w_sq, N, C, dx, J=Ju, P=P, is_=1, os_=stride, o0=u0,
+                  Tout=Tin, off=off)
+
+
+class _ConvFn(torch.autograd.Function):
+    """y = act(conv(x, W) + bias + res) * mask ; W packed (pa = [Q][N][C/G], pb = [Q][C][N])."""
+
+    @staticmethod
+    def forward(ctx, x, pa, pb, bias, res, cfg):
+        Q, stride, pad, dil, P, G, act, slope, in_len, out_len = cfg
+        x = _cl(x)
+        B, R, C = x.shape
+        assert R % P == 0
+        Tin = R // P
+        N, lda = pa.shape[1], pa.shape[2]
+        J = _conv_out_len(Tin, Q, stride, pad, dil)
+        y = torch.empty((B, J * P, N), device=x.device, dtype=torch.float32)
+        if res is not None:
+            res = _cl(res)
+        off = [q * dil - pad for q in range(Q)]
+        _fwd_like(x, Tin, pa, 0, 1, Q, lda, N * lda, C, N, y, J=J, P=P, is_=stride, os_=1, o0=0, Tout=J, off=off,
+                  bias=bias, res=res, act=act, slope=slope, in_len=in_len, out_len=out_len, G=G)
+        ctx.cfg = cfg
+        ctx.dims = (B, Tin, C, N, J, lda)
+        ctx.has = (bias is not None, res is not None)
+        ctx.save_for_backward(x, pa, pb, y if act else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        Q, stride, pad, dil, P, G, act, slope, in_len, out_len = ctx.cfg
+        B, Tin, C, N, J, lda = ctx.dims
+        x, pa, pb, y = ctx.saved_tensors
+        has_bias, has_res = ctx.has
+        dy = dy.contiguous()
+        if act:
+            dpre = torch.empty_like(dy)
+            op = {ACT_LRELU: UN_LRELU, ACT_RELU: UN_RELU, ACT_TANH: UN_TANH_FROM_OUT}[act]
+            _call("evk_unary_bwd", op, ctypes.c_float(slope), _p(y), N, _p(dy), N, _p(dpre), N, B * J * P, N)
+            dy = dpre
+        if out_len is not None:
+            dm = torch.empty_like(dy)
+            _call("evk_rowmask", _p(dy), N, _p(dm), N, B, J * P, N, _p(out_len))   # P == 1 whenever masks are used
+            dy = dm
+        dx = dpa = dbias = dres = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((B, Tin * P, C), device=dy.device, dtype=torch.float32)
+            use_mma = G == 1 and pb is not None and pb.numel() > 0 and _aligned(dy, N) and pb.shape[2] % 4 == 0
+            if use_mma:
+                if Q < stride:
+                    dx.zero_()
+                _dgrad_phases(dy, J, pb, pb.shape[2], C, N, Q, dx, Tin, P, stride, pad, dil)
+            else:
+                d = _desc(x=dx, w=pa, y=dy, res=None, bias=None, in_len=None, out_len=None,
+                          x_sb=Tin * P * C, x_sh=0, w_sb=0, w_sh=0, w_sq=N * lda, y_sb=J * P * N, y_sh=0, r_sb=0, r_sh=0,
+                          ldx=C, ldw=lda, ldy=N, ldr=0, Z=B, H=1, C=C, N=N, Q=Q, G=G, Tin=Tin, J=J, P=P, is_=stride,
+                          os_=1, o0=0, Tout=J, act=0, slope=0.0, off=[q * dil - pad for q in range(Q)])
+                _run_desc("evk_conv_direct_dgrad", d)
+            if in_len is not None:
+                dxm = torch.empty_like(dx)
+                _call("evk_rowmask", _p(dx), C, _p(dxm), C, B, Tin * P, C, _p(in_len))
+                dx = dxm
+        if ctx.needs_input_grad[1]:
+            dpa = torch.zeros_like(pa)
+            _, _, ldx = _rows(x)
+            d = _desc(x=x, w=dpa, y=dy, res=None, bias=None, in_len=in_len, out_len=None,
+                      x_sb=Tin * P * ldx, x_sh=0, w_sb=0, w_sh=0, w_sq=N * lda, y_sb=J * P * N, y_sh=0, r_sb=0, r_sh=0,
+                      ldx=ldx, ldw=lda, ldy=N, ldr=0, Z=B, H=1, C=C, N=N, Q=Q, G=G, Tin=Tin, J=J, P=P, is_=stride,
+                      os_=1, o0=0, Tout=J, act=0, slope=0.0, off=[q * dil - pad for q in range(Q)])
+            mma = G == 1 and _aligned(x, ldx) and _aligned(dy, N)
+            _run_desc("evk_gconv_wgrad" if mma else "evk_conv_direct_wgrad", d)
+        if has_bias and ctx.needs_input_grad[3]:
+            dbias = torch.empty(N, device=dy.device, dtype=torch.float32)
+            _call("evk_colsum", _p(dy), B * J * P, N, N, _p(dbias), 0)
+        if has_res and ctx.needs_input_grad[4]:
+            dres = dy
+        return dx, dpa, None, dbias, dres, None
+
+
+def conv(x, w: PackedW, bias=None, *, stride=1, pad=0, dil=1, P=1, groups=1, act=ACT_NONE, slope=0.0, res=None,
+         in_len=None, out_len=None):
+    """Conv1d (P == 1) / Conv2d with (k,1) kernels over a period-folded view (P == period)."""
+    cfg = (w.Q, stride, pad, dil, P, groups, act, slope, in_len, out_len)
+    return _ConvFn.apply(x, w.pa, w.pb, bias, res, cfg)
+
+
+def linear(x, w: PackedW, bias=None, act=ACT_NONE, slope=0.0, out_len=None, in_len=None, res=None):
+    """nn.Linear / 1x1 conv on [B, T, C] or [rows, C]."""
+    if x.dim() == 2:
+        return conv(x.unsqueeze(0), w, bias, act=act, slope=slope, res=res.unsqueeze(0) if res is not None else None).squeeze(0)
+    return conv(x, w, bias, act=act, slope=slope, out_len=out_len, in_len=in_len, res=res)
+
+
+class _ConvTFn(torch.autograd.Function):
+    """ConvTranspose1d: v [Cin][Cout][Q] packed as pa = [Q][Cin][Cout], pb = [Q][Cout][Cin]."""
+
+    @staticmethod
+    def forward(ctx, x, pa, pb, bias, cfg):
+        Q, stride, pad = cfg
+        x = _cl(x)
+        B, Tin, Cin = x.shape
+        Cout, ldb = pb.shape[1], pb.shape[2]
+        Tout = (Tin - 1) * stride - 2 * pad + Q
+        y = (torch.zeros if Q < stride else torch.empty)((B, Tout, Cout), device=x.device, dtype=torch.float32)
+        w_sq = Cout * ldb
+        for rho in range(stride):
+            taps = list(range(rho, Q, stride))
+            u0 = (rho - pad) % stride
+            if u0 >= Tout or not taps:
+                continue
+            Ju = (Tout - u0 + stride - 1) // stride
+            off = [(u0 + pad - q) // stride for q in taps]
+            _fwd_like(x, Tin, pb, taps[0], stride, len(taps), ldb, w_sq, Cin, Cout, y, J=Ju, P=1, is_=1, os_=stride,
+                      o0=u0, Tout=Tout, off=off, bias=bias)
+        ctx.cfg = cfg
+        ctx.dims = (B, Tin, Cin, Cout, Tout)
+        ctx.save_for_backward(x, pa)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        Q, stride, pad = ctx.cfg
+        B, Tin, Cin, Cout, Tout = ctx.dims
+        x, pa = ctx.saved_tensors
+        dy = dy.contiguous()
+        lda = pa.shape[2]
+        off = [q - pad for q in range(Q)]
+        dx = dpa = dbias = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((B, Tin, Cin), device=dy.device, dtype=torch.float32)
+            _fwd_like(dy, Tout, pa, 0, 1, Q, lda, Cin * lda, Cout, Cin, dx, J=Tin, P=1, is_=stride, os_=1, o0=0,
+                      Tout=Tin, off=off)
+        if ctx.needs_input_grad[1]:
+            dpa = torch.zeros_like(pa)
+            _, _, ldx = _rows(x)
+            # dPA[q][ci][co] += sum_t X[t][ci] * dY[t*stride - pad + q][co]: "x" role = dY (shifted), "y" role = X
+            d = _desc(x=dy, w=dpa, y=x, res=None, bias=None, in_len=None, out_len=None,
+                      x_sb=Tout * Cout, x_sh=0, w_sb=0, w_sh=0, w_sq=Cin * lda, y_sb=Tin * ldx, y_sh=0, r_sb=0, r_sh=0,
+                      ldx=Cout, ldw=lda, ldy=ldx, ldr=0, Z=B, H=1, C=Cout, N=Cin, Q=Q, G=1, Tin=Tout, J=Tin, P=1,
+                      is_=stride, os_=1, o0=0, Tout=Tin, act=0, slope=0.0, off=off)
+            mma = _aligned(dy, Cout) and _aligned(x, ldx)
+            _run_desc("evk_gconv_wgrad" if mma else "evk_conv_direct_wgrad", d)
+        if ctx.needs_input_grad[3]:
+            dbias = torch.empty(Cout, device=dy.device, dtype=torch.float32)
+            _call("evk_colsum", _p(dy), B * Tout, Cout, Cout, _p(dbias), 0)
+        return dx, dpa, None, dbias, None
+
+
+def conv_transpose(x, w: PackedW, bias, *, stride, pad):
+    return _ConvTFn.apply(x, w.pa, w.pb, bias, (w.Q, stride, pad))
+
+
+# ------------------------------------------------------------------------------------------------
+# element-wise family
+# ------------------------------------------------------------------------------------------------
+class _UnaryFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, op, alpha):
+        x = _cl(x)
+        rows, C, ld = _rows(x)
+        y = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+        _call("evk_unary", op, ctypes.c_float(alpha), _p(x), ld, _p(y), C, rows, C)
+        ctx.save_for_backward(x)
+        ctx.op, ctx.alpha = op, alpha
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        rows, C, ld = _rows(x)
+        dy = dy.contiguous()
+        dx = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+        _call("evk_unary_bwd", ctx.op, ctypes.c_float(ctx.alpha), _p(x), ld, _p(dy), C, _p(dx), C, rows, C)
+        return dx, None, None
+
+
+def lrelu(x, slope):
+    return _UnaryFn.apply(x, UN_LRELU, slope)
+
+
+def tanh(x):
+    return _UnaryFn.apply(x, UN_TANH, 0.0)
+
+
+def mish(x):
+    return _UnaryFn.apply(x, UN_MISH, 0.0)
+
+
+def scale(x, alpha):
+    return _UnaryFn.apply(x, UN_SCALE, alpha)
+
+
+def _axpby_raw(a, alpha, b=None, beta=0.0, c=None, gamma=0.0, length=None, T=0):
+    a = _cl(a)
+    rows, C, lda = _rows(a)
+    y = torch.empty(a.shape, device=a.device, dtype=torch.float32)
+    ldb = ldc = 0
+    if b is not None:
+        b = _cl(b)
+        ldb = _rows(b)[2]
+    if c is not None:
+        c = _cl(c)
+        ldc = _rows(c)[2]
+    _call("evk_axpby", _p(a), lda, ctypes.c_float(alpha), _p(b), ldb, ctypes.c_float(beta), _p(c), ldc,
+          ctypes.c_float(gamma), _p(y), C, rows, C, _p(length), T)
+    return y
+
+
+class _AxpbyFn(torch.autograd.Function):
+    """y = mask(alpha*a + beta*b + gamma*c)"""
+
+    @staticmethod
+    def forward(ctx, a, b, c, alpha, beta, gamma, length):
+        T = a.shape[1] if a.dim() == 3 else 0
+        ctx.k = (alpha, beta, gamma, length, T)
+        return _axpby_raw(a, alpha, b, beta, c, gamma, length, T)
+
+    @staticmethod
+    def backward(ctx, dy):
+        alpha, beta, gamma, length, T = ctx.k
+        need = ctx.needs_input_grad
+        if length is None and alpha == 1.0 and beta == 1.0 and gamma in (0.0, 1.0):
+            return (dy if need[0] else None, dy if need[1] else None, dy if need[2] else None, None, None, None, None)
+        dy = dy.contiguous()
+        base = _axpby_raw(dy, 1.0, length=length, T=T) if length is not None else dy
+        outs = []
+        for k, coef in enumerate((alpha, beta, gamma)):
+            if not need[k]:
+                outs.append(None)
+            elif coef == 1.0:
+                outs.append(base)
+            else:
+                outs.append(_axpby_raw(base, coef))
+        return (*outs, None, None, None, None)
+
+
+def add(a, b, alpha=1.0, beta=1.0, length=None):
+    return _AxpbyFn.apply(a, b, None, alpha, beta, 0.0, length)
+
+
+def add3(a, b, c, alpha=1.0, beta=1.0, gamma=1.0):
+    return _AxpbyFn.apply(a, b, c, alpha, beta, gamma, None)
+
+
+def rowmask(x, length):
+    return _AxpbyFn.apply(x, None, None, 1.0, 0.0, 0.0, length)
+
+
+class _AddBvecFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, v):
+        x = _cl(x)
+        B, T, C = x.shape
+        _, _, ldx = _rows(x)
+        v2 = v.reshape(B, C).contiguous()
+        y = torch.empty((B, T, C), device=x.device, dtype=torch.float32)
+        _call("evk_add_bvec", _p(x), ldx, _p(v2), C, _p(y), C, B, T, C)
+        ctx.dims = (B, T, C, tuple(v.shape))
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, T, C, vshape = ctx.dims
+        dv = None
+        if ctx.needs_input_grad[1]:
+            dy = dy.contiguous()
+            dv = torch.empty((B, C), device=dy.device, dtype=torch.float32)
+            _call("evk_masked_mean", _p(dy), C, _p(dv), C, B, T, C, None, 0)
+            dv = _axpby_raw(dv, float(T)).reshape(vshape)
+        return dy, dv
+
+
+def add_bvec(x, v):
+    """x [B,T,C] + v [B,1,C] (broadcast over time)."""
+    return _AddBvecFn.apply(x, v)
+
+
+class _WnGateFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, g):
+        a = _cl(a)
+        B, T, H2 = a.shape
+        H = H2 // 2
+        _, _, lda = _rows(a)
+        ldg = 0
+        if g is not None:
+            g = _cl(g)
+            ldg = _rows(g)[2]
+        y = torch.empty((B, T, H), device=a.device, dtype=torch.float32)
+        _call("evk_wn_gate", _p(a), lda, _p(g), ldg, _p(y), H, B, T, H)
+        ctx.save_for_backward(a, g)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        a, g = ctx.saved_tensors
+        B, T, H2 = a.shape
+        H = H2 // 2
+        _, _, lda = _rows(a)
+        ldg = _rows(g)[2] if g is not None else 0
+        dy = dy.contiguous()
+        da = torch.empty((B, T, H2), device=a.device, dtype=torch.float32)
+        _call("evk_wn_gate_bwd", _p(a), lda, _p(g), ldg, _p(dy), H, _p(da), H2, B, T, H)
+        dg = None
+        if g is not None and ctx.needs_input_grad[1]:
+            dg = torch.empty((B, H2), device=a.device, dtype=torch.float32)
+            _call("evk_masked_mean", _p(da), H2, _p(dg), H2, B, T, H2, None, 0)
+            dg = _axpby_raw(dg, float(T)).reshape(g.shape)
+        return da, dg
+
+
+def wn_gate(a, g):
+    """tanh(a[..., :H] + g[..., :H]) * sigmoid(a[..., H:] + g[..., H:]); g is [B, 1, 2H] (broadcast over time)."""
+    return _WnGateFn.apply(a, g)
+
+
+class _GluResFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, h):
+        h = _cl(h)
+        rows, C2, ldh = _rows(h)
+        C = C2 // 2
+        ldx = 0
+        if x is not None:
+            x = _cl(x)
+            ldx = _rows(x)[2]
+        y = torch.empty((*h.shape[:-1], C), device=h.device, dtype=torch.float32)
+        _call("evk_glu_res", _p(x), ldx, _p(h), ldh, _p(y), C, rows, C)
+        ctx.save_for_backward(h)
+        ctx.has_x = x is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (h,) = ctx.saved_tensors
+        rows, C2, ldh = _rows(h)
+        C = C2 // 2
+        dy = dy.contiguous()
+        dh = torch.empty(h.shape, device=h.device, dtype=torch.float32)
+        _call("evk_glu_res_bwd", _p(h), ldh, _p(dy), C, _p(dh), C2, rows, C)
+        return (dy if ctx.has_x else None), dh
+
+
+def glu_res(x, h):
+    """x + h[..., :C] * sigmoid(h[..., C:])   (x may be None)."""
+    return _GluResFn.apply(x, h)
+
+
+class _CatFlipFn(torch.autograd.Function):
+    """flip_channels(cat([x0, x1], -1)) -- the coupling layer's cat + Flip (modules.py:376-383,452-454) in one pass."""
+
+    @staticmethod
+    def forward(ctx, x0, x1):
+        x0, x1 = _cl(x0), _cl(x1)
+        rows, C0, ld0 = _rows(x0)
+        _, C1, ld1 = _rows(x1)
+        y = torch.empty((*x0.shape[:-1], C0 + C1), device=x0.device, dtype=torch.float32)
+        _call("evk_flip_channels", _p(x1), ld1, _p(y), C0 + C1, rows, C1)
+        _call("evk_flip_channels", _p(x0), ld0, _p(y[..., C1:]), C0 + C1, rows, C0)
+        ctx.k = (C0, C1)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        C0, C1 = ctx.k
+        dy = dy.contiguous()
+        rows = dy.numel() // (C0 + C1)
+        d0 = torch.empty((*dy.shape[:-1], C0), device=dy.device, dtype=torch.float32)
+        d1 = torch.empty((*dy.shape[:-1], C1), device=dy.device, dtype=torch.float32)
+        _call("evk_flip_channels", _p(dy), C0 + C1, _p(d1), C1, rows, C1)
+        _call("evk_flip_channels", _p(dy[..., C1:]), C0 + C1, _p(d0), C0, rows, C0)
+        return d0, d1
+
+
+def cat_flip(x0, x1):
+    return _CatFlipFn.apply(x0, x1)
+
+
+class _CatBatchFn(torch.autograd.Function):
+    """cat([a, b], dim=0) with a copy kernel (discriminators run real and generated audio as one 2B batch)."""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous(), b.contiguous()
+        y = torch.empty((a.shape[0] + b.shape[0], *a.shape[1:]), device=a.device, dtype=torch.float32)
+        na, nb = a.numel(), b.numel()
+        one, zero = ctypes.c_float(1.0), ctypes.c_float(0.0)
+        _call("evk_axpby", _p(a), na, one, None, 0, zero, None, 0, zero, _p(y), na, 1, na, None, 0)
+        _call("evk_axpby", _p(b), nb, one, None, 0, zero, None, 0, zero, _p(y[a.shape[0]:]), nb, 1, nb, None, 0)
+        ctx.na = a.shape[0]
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        na = ctx.na
+        return (dy[:na] if ctx.needs_input_grad[0] else None), (dy[na:] if ctx.needs_input_grad[1] else None)
+
+
+def cat_batch(a, b):
+    return _CatBatchFn.apply(a, b)
+
+
+class _ReparamFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, stats, noise, length):
+        stats, noise = _cl(stats), _cl(noise)
+        B, T, C2 = stats.shape
+        C = C2 // 2
+        z = torch.empty((B, T, C), device=stats.device, dtype=torch.float32)
+        _call("evk_reparam", _p(stats), _rows(stats)[2], _p(noise), _rows(noise)[2], _p(z), C, B, T, C, _p(length))
+        ctx.save_for_backward(stats, noise)
+        ctx.length = length
+        return z
+
+    @staticmethod
+    def backward(ctx, dz):
+        stats, noise = ctx.saved_tensors
+        B, T, C2 = stats.shape
+        C = C2 // 2
+        dz = dz.contiguous()
+        ds = torch.empty((B, T, C2), device=stats.device, dtype=torch.float32)
+        _call("evk_reparam_bwd", _p(stats), _rows(stats)[2], _p(noise), _rows(noise)[2], _p(dz), C, _p(ds), C2, B, T, C,
+              _p(ctx.length))
+        return ds, None, None
+
+
+def reparam(stats, noise, length):
+    """z = (m + noise * exp(logs)) * mask with stats = [m | logs]."""
+    return _ReparamFn.apply(stats, noise, length)
+
+
+class _FlipFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _cl(x)
+        rows, C, ld = _rows(x)
+        y = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+        _call("evk_flip_channels", _p(x), ld, _p(y), C, rows, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = dy.contiguous()
+        rows, C, ld = _rows(dy)
+        dx = torch.empty_like(dy)
+        _call("evk_flip_channels", _p(dy), ld, _p(dx), C, rows, C)
+        return dx
+
+
+def flip_channels(x):
+    return _FlipFn.apply(x)
+
+
+class _SliceFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ids, mul, seg):
+        x = _cl(x)
+        B, T, C = x.shape
+        _, _, ld = _rows(x)
+        y = torch.empty((B, seg, C), device=x.device, dtype=torch.float32)
+        _call("evk_slice_rows", _p(x), ld, T, _p(ids), mul, _p(y), C, B, seg, C, 0)
+        ctx.k = (ids, mul, seg, B, T, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        ids, mul, seg, B, T, C = ctx.k
+        dy = dy.contiguous()
+        dx = torch.zeros((B, T, C), device=dy.device, dtype=torch.float32)
+        _call("evk_slice_rows", _p(dx), C, T, _p(ids), mul, _p(dy), C, B, seg, C, 1)
+        return dx, None, None, None
+
+
+def slice_rows(x, ids, seg, mul=1):
+    """commons.slice_segments on a channels-last tensor; ids int64 device [B]."""
+    return _SliceFn.apply(x, ids, mul, seg)
+
+
+class _ReflectPadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, Tp):
+        x = x.contiguous()
+        B, T, _ = x.shape
+        y = torch.empty((B, Tp, 1), device=x.device, dtype=torch.float32)
+        _call("evk_reflect_pad_right", _p(x), T, _p(y), Tp, B, 0)
+        ctx.k = (B, T, Tp)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, T, Tp = ctx.k
+        dy = dy.contiguous()
+        dx = torch.empty((B, T, 1), device=dy.device, dtype=torch.float32)
+        _call("evk_reflect_pad_right", _p(dx), T, _p(dy), Tp, B, 1)
+        return dx, None
+
+
+def reflect_pad_right(x, Tp):
+    return x if Tp == x.shape[1] else _ReflectPadFn.apply(x, Tp)
+
+
+def to_channels_last(x, pad_to=None):
+    """[B, C, T] -> [B, T, C] (new memory; pitch rounded up to `pad_to` channels, returned as a view)."""
+    x = x.contiguous()
+    B, C, T = x.shape
+    ld = C if pad_to is None else (C + pad_to - 1) // pad_to * pad_to
+    buf = torch.empty((B, T, ld), device=x.device, dtype=torch.float32)
+    _call("evk_transpose_bct_btc", _p(x), _p(buf), B, C, T, ld, 1)
+    return buf[:, :, :C] if ld != C else buf
+
+
+def to_channels_first(x):
+    """[B, T, C] -> [B, C, T]"""
+    x = _cl(x)
+    B, T, C = x.shape
+    _, _, ld = _rows(x)
+    y = torch.empty((B, C, T), device=x.device, dtype=torch.float32)
+    _call("evk_transpose_bct_btc", _p(x), _p(y), B, C, T, ld, 0)
+    return y
+
+
+class _EmbFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, table, idx, rep):
+        table = table.contiguous()
+        rows = idx.numel() * rep
+        C = table.shape[1]
+        y = torch.empty((*idx.shape[:-1], idx.shape[-1] * rep, C), device=table.device, dtype=torch.float32)
+        idx = idx.contiguous()
+        _call("evk_embedding", _p(table), C, _p(idx), rows, rep, _p(y), C, C)
+        ctx.save_for_backward(idx)
+        ctx.k = (tuple(table.shape), rep)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        shape, rep = ctx.k
+        assert rep == 1
+        dy = dy.contiguous()
+        dt = torch.zeros(shape, device=dy.device, dtype=torch.float32)
+        _call("evk_embedding_bwd", _p(dy), shape[1], _p(idx), idx.numel(), _p(dt), shape[1], shape[1])
+        return dt, None, None
+
+
+def embedding(table, idx, rep=1):
+    """idx int64 [B, T] -> [B, T*rep, C] (rep = nearest-neighbour upsample factor along time)."""
+    return _EmbFn.apply(table, idx, rep)
+
+
+class _MaskedMeanFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, length):
+        x = _cl(x)
+        B, T, C = x.shape
+        y = torch.empty((B, C), device=x.device, dtype=torch.float32)
+        _call("evk_masked_mean", _p(x), _rows(x)[2], _p(y), C, B, T, C, _p(length), 0)
+        ctx.k = (B, T, C, length)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, T, C, length = ctx.k
+        dy = dy.contiguous()
+        dx = torch.empty((B, T, C), device=dy.device, dtype=torch.float32)
+        _call("evk_masked_mean", _p(dx), C, _p(dy), C, B, T, C, _p(length), 1)
+        return dx, None
+
+
+def masked_mean(x, length):
+    return _MaskedMeanFn.apply(x, length)
+
+
+class _DropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p, sid):
+        x = x.contiguous()
+        y = torch.empty_like(x)
+        _call("evk_dropout", _p(x), _p(y), x.numel(), ctypes.c_float(p), _p(rng_state(x.device)), ctypes.c_uint64(sid))
+        ctx.k = (p, sid)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        p, sid = ctx.k
+        dy = dy.contiguous()
+        dx = torch.empty_like(dy)
+        _call("evk_dropout", _p(dy), _p(dx), dy.numel(), ctypes.c_float(p), _p(rng_state(dy.device)), ctypes.c_uint64(sid))
+        return dx, None, None
+
+
+def dropout(x, p, tag):
+    """inverted dropout; the mask is regenerated (not stored) in backward from (seed, offset, stream id)."""
+    if p <= 0.0:
+        return x
+    return _DropoutFn.apply(x, p, stream_id(tag))
+
+
+def randn(shape, tag, device=None):
+    y = torch.empty(shape, device=device or "cuda", dtype=torch.float32)
+    _call("evk_randn", _p(y), y.numel(), _p(rng_state(y.device)), ctypes.c_uint64(stream_id(tag)))
+    return y
+
+
+def rand_slice_ids(length, seg, tag="slice"):
+    ids = torch.empty(length.shape[0], device=length.device, dtype=torch.int64)
+    _call("evk_rand_slice_ids", _p(ids), _p(length), length.shape[0], seg, _p(rng_state(length.device)),
+          ctypes.c_uint64(stream_id(tag)))
+    return ids
+
+
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, eps):
+        x = _cl(x)
+        rows, C, ldx = _rows(x)
+        ldr = 0
+        if res is not None:
+            res = _cl(res)
+            ldr = _rows(res)[2]
+        y = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+        stats = torch.empty((rows, 2), device=x.device, dtype=torch.float32)
+        _call("evk_layernorm_fwd", _p(x), ldx, _p(res), ldr, _p(gamma), _p(beta), ctypes.c_float(eps), _p(y), C, _p(stats),
+              rows, C)
+        ctx.save_for_backward(x, res, gamma, stats)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, res, gamma, stats = ctx.saved_tensors
+        rows, C, ldx = _rows(x)
+        ldr = _rows(res)[2] if res is not None else 0
+        dy = dy.contiguous()
+        dx = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+        dgb = torch.zeros((2, C), device=x.device, dtype=torch.float32)
+        _call("evk_layernorm_bwd", _p(x), ldx, _p(res), ldr, _p(gamma), _p(stats), _p(dy), C, _p(dx), C, _p(dgb[0]),
+              _p(dgb[1]), rows, C)
+        return dx, (dx if res is not None else None), dgb[0], dgb[1], None
+
+
+def layernorm(x, gamma, beta, res=None, eps=1e-5):
+    """LayerNorm over channels of (x + res)."""
+    return _LayerNormFn.apply(x, res, gamma, beta, eps)
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+def _transpose_cl(x, ldT):
+    """[B, T, C] -> [B, C, ldT] (time-contiguous copy used as the K-major operand of P.V and dS.K)."""
+    x = _cl(x)
+    B, T, C = x.shape
+    _, _, ld = _rows(x)
+    y = torch.empty((B, C, ldT), device=x.device, dtype=torch.float32)
+    # evk_transpose (to_btc=0) reads [B][T][ld] and writes [B][C][T]; write with row pitch ldT via per-batch view
+    if ldT == T:
+        _call("evk_transpose_bct_btc", _p(x), _p(y), B, C, T, ld, 0)
+    else:
+        tmp = torch.empty((B, C, T), device=x.device, dtype=torch.float32)
+        _call("evk_transpose_bct_btc", _p(x), _p(tmp), B, C, T, ld, 0)
+        y.zero_()
+        _call("evk_axpby", _p(tmp), T, ctypes.c_float(1.0), None, 0, ctypes.c_float(0.0), None, 0, ctypes.c_float(0.0),
+              _p(y), ldT, B * C, T, None, 0)
+    return y
+
+
+def _bgemm(fn, x, x_sb, x_sh, ldx, w, w_sb, w_sh, ldw, y, y_sb, y_sh, ldy, Z, H, C, N, rows):
+    d = _desc(x=x, w=w, y=y, res=None, bias=None, in_len=None, out_len=None, x_sb=x_sb, x_sh=x_sh, w_sb=w_sb, w_sh=w_sh,
+              w_sq=0, y_sb=y_sb, y_sh=y_sh, r_sb=0, r_sh=0, ldx=ldx, ldw=ldw, ldy=ldy, ldr=0, Z=Z, H=H, C=C, N=N, Q=1,
+              G=1, Tin=rows, J=rows, P=1, is_=1, os_=1, o0=0, Tout=rows, act=0, slope=0.0, off=[0])
+    _run_desc(fn, d)
+
+
+class _AttnFn(torch.autograd.Function):
+    """softmax((q k^T + q Ek^T) * scale, masked) (dropout) (v + Ev band) -- attentions.py:243-292."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, Ek, Ev, cfg):
+        H, win, scale_, fill, qlen, klen, p_drop, sid = cfg
+        q, k, v = _cl(q), _cl(k), _cl(v)
+        B, Tq, C = q.shape
+        Tk = k.shape[1]
+        dk = C // H
+        Z = B * H
+        ldq, ldk, ldv = _rows(q)[2], _rows(k)[2], _rows(v)[2]
+        ldS = (Tk + 3) // 4 * 4
+        S = torch.empty((Z, Tq, ldS), device=q.device, dtype=torch.float32)
+        # S[z][i][j] = q_i . k_j
+        _bgemm("evk_gconv_fwd", q, Tq * ldq, dk, ldq, k, Tk * ldk, dk, ldk, S, H * Tq * ldS, Tq * ldS, ldS, Z, H, dk, Tk, Tq)
+        rel = None
+        if win is not None:
+            Ekc = Ek.reshape(2 * win + 1, dk).contiguous()
+            rel = torch.empty((Z, Tq, 2 * win + 1), device=q.device, dtype=torch.float32)
+            _call("evk_relk_logits", _p(q), ldq, _p(Ekc), B, H, Tq, dk, win, _p(rel))
+        _call("evk_attn_softmax", _p(S), ldS, Z, H, Tq, Tk, ctypes.c_float(scale_), _p(rel), win or 0, _p(qlen), _p(klen),
+              ctypes.c_float(fill))
+        P = S
+        Pd = P
+        if p_drop > 0.0:
+            Pd = torch.empty_like(P)
+            _call("evk_dropout", _p(P), _p(Pd), P.numel(), ctypes.c_float(p_drop), _p(rng_state(q.device)),
+                  ctypes.c_uint64(sid))
+        ldT = ldS
+        Vt = _transpose_cl(v, ldT)                                   # [B, C, ldT]
+        out = torch.empty((B, Tq, C), device=q.device, dtype=torch.float32)
+        _bgemm("evk_gconv_fwd", Pd, H * Tq * ldS, Tq * ldS, ldS, Vt, C * ldT, dk * ldT, ldT, out, Tq * C, dk, C, Z, H, Tk,
+               dk, Tq)
+        band = None
+        if win is not None:
+            Evc = Ev.reshape(2 * win + 1, dk).contiguous()
+            band = torch.empty((Z, Tq, 2 * win + 1), device=q.device, dtype=torch.float32)
+            _call("evk_attn_band", _p(Pd), ldS, _p(band), Z, Tq, Tk, win, 1)
+            _call("evk_relv_out", _p(band), _p(Evc), B, H, Tq, dk, win, _p(out), C)
+        ctx.cfg = cfg
+        ctx.save_for_backward(q, k, v, P, Pd if p_drop > 0.0 else None, band, Ek, Ev)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        H, win, scale_, fill, qlen, klen, p_drop, sid = ctx.cfg
+        q, k, v, P, Pd, band, Ek, Ev = ctx.saved_tensors
+        if Pd is None:
+            Pd = P
+        B, Tq, C = q.shape
+        Tk = k.shape[1]
+        dk = C // H
+        Z = B * H
+        ldq, ldk, ldv = _rows(q)[2], _rows(k)[2], _rows(v)[2]
+        ldS = P.shape[2]
+        dout = dout.contiguous()
+        dev = q.device
+        W = 2 * win + 1 if win is not None else 0
+        # dPd = dO V^T
+        dP = torch.empty((Z, Tq, ldS), device=dev, dtype=torch.float32)
+        _bgemm("evk_gconv_fwd", dout, Tq * C, dk, C, v, Tk * ldv, dk, ldv, dP, H * Tq * ldS, Tq * ldS, ldS, Z, H, dk, Tk, Tq)
+        dEk = dEv = None
+        if win is not None:
+            Evc = Ev.reshape(W, dk).contiguous()
+            dband = torch.empty((Z, Tq, W), device=dev, dtype=torch.float32)
+            dEv = torch.zeros((W, dk), device=dev, dtype=torch.float32)
+            _call("evk_relv_bwd", _p(band), _p(dout), C, _p(Evc), B, H, Tq, dk, win, _p(dband), _p(dEv))
+            _call("evk_attn_band", _p(dP), ldS, _p(dband), Z, Tq, Tk, win, 0)
+        # dV[b][j][h*dk+d] = sum_i Pd[z][i][j] dO[b][i][h*dk+d]
+        dv = torch.zeros((B, Tk, C), device=dev, dtype=torch.float32)
+        _bgemm("evk_gconv_wgrad", dout, Tq * C, dk, C, dv, Tk * C, dk, C, Pd, H * Tq * ldS, Tq * ldS, ldS, Z, H, dk, Tk, Tq)
+        if p_drop > 0.0:
+            dPn = torch.empty_like(dP)
+            _call("evk_dropout", _p(dP), _p(dPn), dP.numel(), ctypes.c_float(p_drop), _p(rng_state(dev)), ctypes.c_uint64(sid))
+            dP = dPn
+        drel = torch.empty((Z, Tq, W), device=dev, dtype=torch.float32) if win is not None else None
+        _call("evk_attn_softmax_bwd", _p(P), _p(dP), ldS, Z, Tq, Tk, ctypes.c_float(scale_), _p(drel), win or 0)
+        dS = dP
+        # dQ = dS K  (K^T as the K-major operand)
+        Kt = _transpose_cl(k, ldS)
+        dq = torch.empty((B, Tq, C), device=dev, dtype=torch.float32)
+        _bgemm("evk_gconv_fwd", dS, H * Tq * ldS, Tq * ldS, ldS, Kt, C * ldS, dk * ldS, ldS, dq, Tq * C, dk, C, Z, H, Tk, dk, Tq)
+        # dK[b][j][h*dk+d] = sum_i dS[z][i][j] q[b][i][h*dk+d]
+        dkk = torch.zeros((B, Tk, C), device=dev, dtype=torch.float32)
+        _bgemm("evk_gconv_wgrad", q, Tq * ldq, dk, ldq, dkk, Tk * C, dk, C, dS, H * Tq * ldS, Tq * ldS, ldS, Z, H, dk, Tk, Tq)
+        if win is not None:
+            Ekc = Ek.reshape(W, dk).contiguous()
+            dEk = torch.zeros((W, dk), device=dev, dtype=torch.float32)
+            _call("evk_relk_bwd", _p(drel), _p(q), ldq, _p(Ekc), B, H, Tq, dk, win, _p(dq), C, _p(dEk))
+            dEk = dEk.reshape(Ek.shape)
+            dEv = dEv.reshape(Ev.shape)
+        return dq, dkk, dv, dEk, dEv, None
+
+
+def attention(q, k, v, *, heads, scale, Ek=None, Ev=None, window=None, fill=-1e4, qlen=None, klen=None, p_drop=0.0,
+              tag="attn"):
+    cfg = (heads, window, float(scale), float(fill), qlen, klen, float(p_drop), stream_id(tag))
+    return _AttnFn.apply(q, k, v, Ek, Ev, cfg)
+
+
+# ------------------------------------------------------------------------------------------------
+# VQ, losses, mel
+# ------------------------------------------------------------------------------------------------
+def vq_nearest(x, embed):
+    """x [B, T, D] channels-last, embed [K, D] -> codes int64 [B, T] (no gradient: frozen quantizer)."""
+    x = _cl(x.detach())
+    rows, D, ldx = _rows(x)
+    embed = embed.detach().contiguous()
+    K = embed.shape[0]
+    dots = torch.empty((rows, K), device=x.device, dtype=torch.float32)
+    _call("evk_sgemm_nt_f32", _p(x), ldx, _p(embed), D, _p(dots), K, rows, K, D)
+    codes = torch.empty(x.shape[:-1], device=x.device, dtype=torch.int64)
+    scratch = torch.empty(K, device=x.device, dtype=torch.float32)
+    _call("evk_vq_argmax", _p(dots), K, _p(x), ldx, _p(embed), D, rows, K, D, _p(codes), _p(scratch))
+    return codes
+
+
+class _ReduceLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, kind, scale_):
+        a = a.contiguous()
+        b = b.contiguous() if b is not None else None
+        out = torch.zeros(1, device=a.device, dtype=torch.float32)
+        _call("evk_reduce_loss", kind, _p(a), _p(b), a.numel(), ctypes.c_float(scale_), _p(out))
+        ctx.save_for_backward(a, b)
+        ctx.k = (kind, scale_)
+        return out[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        kind, scale_ = ctx.k
+        g = g.reshape(1).contiguous()
+        da = torch.empty_like(a)
+        _call("evk_reduce_loss_bwd", kind, _p(a), _p(b), a.numel(), ctypes.c_float(scale_), _p(g), _p(da))
+        return da, None, None, None
+
+
+def mean_sq_one_minus(a):
+    """mean((1 - a)^2)"""
+    return _ReduceLossFn.apply(a, None, 0, 1.0 / a.numel())
+
+
+def mean_sq(a):
+    return _ReduceLossFn.apply(a, None, 1, 1.0 / a.numel())
+
+
+def mean_abs_diff(a, b):
+    """mean(|a - b|), gradient wrt a only (b is the detached target)."""
+    return _ReduceLossFn.apply(a, b.detach(), 2, 1.0 / a.numel())
+
+
+class _KlFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, z_p, logs_q, m_p, logs_p, length, inv_norm):
+        ts = [_cl(t) for t in (z_p, logs_q, m_p, logs_p)]
+        B, T, C = ts[0].shape
+        out = torch.zeros(1, device=ts[0].device, dtype=torch.float32)
+        _call("evk_kl_loss", _p(ts[0]), _rows(ts[0])[2], _p(ts[1]), _rows(ts[1])[2], _p(ts[2]), _rows(ts[2])[2], _p(ts[3]),
+              _rows(ts[3])[2], B, T, C, _p(length), _p(out))
+        ctx.save_for_backward(*ts, inv_norm)
+        ctx.length = length
+        return out[0] * inv_norm
+
+    @staticmethod
+    def backward(ctx, g):
+        z_p, logs_q, m_p, logs_p, inv_norm = ctx.saved_tensors
+        B, T, C = z_p.shape
+        gg = (g * inv_norm).reshape(1).contiguous()
+        outs = [torch.empty((B, T, C), device=z_p.device, dtype=torch.float32) for _ in range(4)]
+        _call("evk_kl_loss_bwd", _p(z_p), _rows(z_p)[2], _p(logs_q), _rows(logs_q)[2], _p(m_p), _rows(m_p)[2], _p(logs_p),
+              _rows(logs_p)[2], B, T, C, _p(ctx.length), _p(gg), ctypes.c_float(1.0), _p(outs[0]), _p(outs[1]), _p(outs[2]),
+              _p(outs[3]), C)
+        return outs[0], outs[1], outs[2], outs[3], None, None
+
+
+def kl_loss(z_p, logs_q, m_p, logs_p, length):
+    """losses.py:46-61 on channels-last tensors; length int32 [B] (mask = t < length)."""
+    C = z_p.shape[-1]
+    inv_norm = 1.0 / (length.sum().to(torch.float32))        # sum(z_mask) over [B,1,T]
+    return _KlFn.apply(z_p, logs_q, m_p, logs_p, length, inv_norm)
+
+
+# ---- mel ---------------------------------------------------------------------------------------
+class MelBank:
+    """Slaney filterbank (librosa.filters.mel restated; see mel_processing.slaney_filterbank) in CSR-by-mel form."""
+    _cache = {}
+
+    def __init__(self, fb, device):
+        import numpy as np
+        n_mels, n_bins = fb.shape
+        ptr, idx, val = [0], [], []
+        for m in range(n_mels):
+            nz = np.nonzero(fb[m])[0]
+            idx.extend(nz.tolist())
+            val.extend(fb[m, nz].tolist())
+            ptr.append(len(idx))
+        self.n_mels, self.n_bins = n_mels, n_bins
+        self.ptr = torch.tensor(ptr, dtype=torch.int32, device=device)
+        self.idx = torch.tensor(idx, dtype=torch.int32, device=device)
+        self.val = torch.tensor(val, dtype=torch.float32, device=device)
+
+
+class _MelFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, wav, bank, hop, want_spec, want_mel):
+        wav = wav.contiguous()
+        B, Lw = wav.shape
+        n_fft = 2 * (bank.n_bins - 1)
+        T = (Lw + 2 * ((n_fft - hop) // 2) - n_fft) // hop + 1
+        need_grad = ctx.needs_input_grad[0]
+        ld_spec = (bank.n_bins + 3) // 4 * 4          # 16-byte row pitch so |X| can feed the tensor-core GEMMs directly
+        spec = torch.empty((B, T, ld_spec), device=wav.device, dtype=torch.float32) if want_spec else None
+        mel = torch.empty((B, T, bank.n_mels), device=wav.device, dtype=torch.float32) if want_mel else None
+        cplx = torch.empty((B, T, bank.n_bins, 2), device=wav.device, dtype=torch.float32) if need_grad else None
+        _call("evk_mel_fwd", _p(wav), B, Lw, Lw, hop, bank.n_mels, _p(bank.ptr), _p(bank.idx), _p(bank.val), _p(spec),
+              ld_spec, _p(mel), bank.n_mels, _p(cplx))
+        ctx.k = (bank, hop, B, Lw)
+        ctx.save_for_backward(cplx, mel)
+        if spec is None:
+            spec = torch.empty(0, device=wav.device)
+        else:
+            spec = spec[:, :, :bank.n_bins]
+        if mel is None:
+            mel = torch.empty(0, device=wav.device)
+        ctx.mark_non_differentiable(spec)
+        return spec, mel
+
+    @staticmethod
+    def backward(ctx, _dspec, dmel):
+        bank, hop, B, Lw = ctx.k
+        cplx, mel = ctx.saved_tensors
+        dmel = dmel.contiguous()
+        dwav = torch.zeros((B, Lw), device=dmel.device, dtype=torch.float32)
+        _call("evk_mel_bwd", _p(dmel), bank.n_mels, _p(cplx), _p(mel), bank.n_mels, B, Lw, Lw, hop, bank.n_mels, _p(bank.ptr),
+              _p(bank.idx), _p(bank.val), _p(dwav))
+        return dwav, None, None, None, None
+
+
+def mel_frontend(wav, bank, hop, want_spec=False, want_mel=True):
+    """wav [B, L] -> (spec [B,T,1025] or None, log-mel [B,T,128] or None), channels-last; differentiable wrt wav via mel."""
+    spec, mel = _MelFn.apply(wav, bank, hop, want_spec, want_mel)
+    return (spec if want_spec else None), (mel if want_mel else None)
+
+
+def spec_to_mel(spec, bank):
+    """|X| [B, T, 1025] channels-last -> log-mel [B, T, 128] (no gradient: applied to ground-truth features)."""
+    spec = _cl(spec.detach())
+    rows, F, ld = _rows(spec)
+    mel = torch.empty((*spec.shape[:-1], bank.n_mels), device=spec.device, dtype=torch.float32)
+    _call("evk_spec_to_mel", _p(spec), rows, ld, bank.n_mels, _p(bank.ptr), _p(bank.idx), _p(bank.val), _p(mel), bank.n_mels)
+    return mel
+
+
+# ---- optimiser -----------------------------------------------------------------------------------
+def adamw_flat(p, g, m, v, hyper, betas, eps, wd, grad_scale=1.0, gnorm_sq=None):
+    _call("evk_adamw_flat", _p(p), _p(g), _p(m), _p(v), p.numel(), _p(hyper), ctypes.c_float(betas[0]),
+          ctypes.c_float(betas[1]), ctypes.c_float(eps), ctypes.c_float(wd), ctypes.c_float(grad_scale), _p(gnorm_sq))

@@ -1,0 +1,8 @@
+"""Import shim: the product package lives in ``easevoice-trainer_b200/`` (a directory name Python cannot
+import directly); this package re-roots itself there so ``import easevoice_trainer_b200.xyz`` works."""
+import os as _os
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "easevoice-trainer_b200")
+__path__ = [_real]
+with open(_os.path.join(_real, "__init__.py")) as _f:
+    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))

@@ -1,0 +1,244 @@
+/* libevk_sm100.so -- C ABI of the B200-native EaseVoice stage-2 hot path.
+ *
+ * The reference (megaease/easevoice-trainer) is pure Python on stock PyTorch: it has NO operator /
+ * FFI interface.  Every entry point below therefore replaces a *call site* of the reference that
+ * lowers to a library kernel; the citation after each declaration is that call site
+ * (paths relative to /root/reference/src/easevoice/module unless noted).  INTEGRATION.md shows the
+ * ctypes binding a reference maintainer would add.
+ *
+ * Conventions
+ *  - All pointers are raw DEVICE pointers owned by the caller (PyTorch); the library never
+ *    allocates, frees or retains them.  Sizes/strides are explicit, in ELEMENTS.
+ *  - Activations are channels-last: a [B, T, C] tensor is B*T rows of C floats with row pitch `ld`.
+ *  - All work is enqueued on `stream`; no hidden synchronisation, no default-stream use; every
+ *    entry point is CUDA-graph capturable.  Returns 0 or a negative evk_status;
+ *    evk_last_error() gives the thread-local message.  Never throws, never exits.
+ *  - sm_100a only: evk_init() fails on any other device.  There is no CPU fallback.
+ */
+#ifndef EVK_H_
+#define EVK_H_
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* evk_stream_t;
+
+enum evk_status { EVK_OK = 0, EVK_ERR_ARG = -1, EVK_ERR_CUDA = -2, EVK_ERR_ARCH = -3, EVK_ERR_UNSUPPORTED = -4 };
+enum evk_act { EVK_ACT_NONE = 0, EVK_ACT_LRELU = 1, EVK_ACT_RELU = 2, EVK_ACT_TANH = 3 };
+
+#define EVK_MAX_TAPS 48
+
+int evk_init(void);                    /* checks compute capability 10.x, raises smem limits */
+int evk_version(void);
+const char* evk_last_error(void);
+int evk_sync_check(evk_stream_t stream); /* cudaStreamSynchronize + error fetch (tests only) */
+
+/* ------------------------------------------------------------------------------------------
+ * Generalised 1-D convolution as a tap-sum of GEMMs (tensor cores, TF32 in / FP32 accumulate)
+ *
+ *   Y[z][(o0 + j*os)*P + w][n] = epi( sum_{q<Q} sum_{c<C} X[z][(j*is + off[q])*P + w][c] * W[z][q][n][c] )
+ *
+ * for j in [0,J), w in [0,P); input rows outside [0, Tin*P) (or >= in_len[b]*P) read as zero.
+ * z = b*H + h addresses a two-level batch (X + b*x_sb + h*x_sh, same for W/Y/R; w_sb = w_sh = 0
+ * shares one weight).  epi(v) = mask(act(v + bias[n] + R[...][n])) with mask = (row/P < out_len[b]).
+ * Covers: Conv1d / Conv2d(k,1) forward (models.py:452-471,538-587; modules.py:187-212,298-311;
+ * attentions.py:408-416), their data gradients (one call per stride phase), ConvTranspose1d
+ * (models.py:460), nn.Linear / 1x1 convs, and the attention GEMMs (attentions.py:243-292).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct evk_gconv_desc {
+  const float* x; float* w; float* y; const float* res; const float* bias;
+  const int32_t* in_len; const int32_t* out_len;
+  int64_t x_sb, x_sh, w_sb, w_sh, w_sq, y_sb, y_sh, r_sb, r_sh;
+  int32_t ldx, ldw, ldy, ldr;
+  int32_t Z, H;          /* batch count and inner (head) count: b = z / H, h = z % H */
+  int32_t C, N, Q, G;    /* in-channels, out-channels, taps, groups (G>1: direct kernels only) */
+  int32_t Tin, J, P;     /* input positions per batch, output positions computed, inner width */
+  int32_t is, os, o0;    /* input stride, output stride, output origin (in positions) */
+  int32_t Tout;          /* output positions per batch (bounds for (o0 + j*os)) */
+  int32_t act; float slope;
+  int32_t off[EVK_MAX_TAPS];
+} evk_gconv_desc;
+
+int evk_gconv_fwd(const evk_gconv_desc* d, evk_stream_t stream);
+/* 0 (default): one TF32 product per MAC.  1: 3xTF32 error-compensated products (~fp32 accuracy, 3x tensor work);
+ * the parity tests use it to separate indexing errors from TF32 operand rounding. Process-wide. */
+int evk_set_precise(int32_t on);
+/* Weight gradient of the same operator:  W[z][q][n][c] += sum_{j,w} Yg[z][orow][n] * X[z][irow][c]
+ * (d->y is read as the output gradient, d->w is accumulated with atomics; when w_sb == w_sh == 0 the
+ * sum also runs over z).  Replaces autograd's conv weight-gradient kernels for the call sites above. */
+int evk_gconv_wgrad(const evk_gconv_desc* d, evk_stream_t stream);
+/* Direct (CUDA-core) variants for skinny layers: C/G < 8 (1-channel inputs, grouped k=41 convs of
+ * DiscriminatorS, models.py:563-575).  Same descriptor; W is [Q][N][C/G]. */
+int evk_conv_direct_fwd(const evk_gconv_desc* d, evk_stream_t stream);
+int evk_conv_direct_dgrad(const evk_gconv_desc* d, evk_stream_t stream);  /* d->x is WRITTEN (dX), d->y read */
+int evk_conv_direct_wgrad(const evk_gconv_desc* d, evk_stream_t stream);
+
+/* out[n] (+)= sum_rows x[row][n]  -- bias gradients */
+int evk_colsum(const float* x, int64_t rows, int32_t n, int32_t ld, float* out, int32_t accumulate, evk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Weight preparation: torch.nn.utils.weight_norm (modules.py:154-171, models.py:425-435,489-587)
+ * folded into the operand-packing pass.  v is [D0][D1][Q] (torch layout), g is [D0] or NULL
+ * (plain weight).  Produces PA[q][d0][d1] (pitch lda) and optionally PB[q][d1][d0] (pitch ldb).
+ * ------------------------------------------------------------------------------------------ */
+int evk_weight_pack(const float* v, const float* g, int32_t D0, int32_t D1, int32_t Q, float* pa, int32_t lda,
+                    float* pb, int32_t ldb, evk_stream_t stream);
+/* given dPA (gradient in PA layout) -> dv [D0][D1][Q] (written), dg [D0] (written) (g may be NULL) */
+int evk_weight_pack_bwd(const float* dpa, int32_t lda, const float* v, const float* g, int32_t D0, int32_t D1,
+                        int32_t Q, float* dv, float* dg, evk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused mel front end (mel_processing.py:40-142): reflect-pad -> Hann -> rFFT(2048) ->
+ * sqrt(re^2+im^2+1e-6) -> sparse Slaney filterbank -> log(clamp 1e-5).
+ * wav [B][L] (pitch ldw); outputs channels-last: spec [B*T][n_fft/2+1] (pitch ld_spec, nullable),
+ * mel [B*T][n_mels] (pitch ld_mel, nullable), cplx [B*T][n_fft/2+1][2] (nullable, saved for bwd).
+ * Filterbank is CSR by mel row: fb_ptr[n_mels+1], fb_idx[nnz], fb_val[nnz].
+ * ------------------------------------------------------------------------------------------ */
+int evk_mel_fwd(const float* wav, int32_t B, int32_t L, int32_t ldw, int32_t hop, int32_t n_mels,
+                const int32_t* fb_ptr, const int32_t* fb_idx, const float* fb_val, float* spec, int32_t ld_spec,
+                float* mel, int32_t ld_mel, float* cplx, evk_stream_t stream);
+/* gradient wrt wav of sum(dmel * mel): dwav [B][L] must be zero-initialised (overlap-add). */
+int evk_mel_bwd(const float* dmel, int32_t ld_dmel, const float* cplx, const float* mel, int32_t ld_mel, int32_t B,
+                int32_t L, int32_t ldw, int32_t hop, int32_t n_mels, const int32_t* fb_ptr, const int32_t* fb_idx,
+                const float* fb_val, float* dwav, evk_stream_t stream);
+/* spec_to_mel_torch (mel_processing.py:77-90): spec [rows][F] -> log-mel [rows][n_mels] */
+int evk_spec_to_mel(const float* spec, int64_t rows, int32_t ld_spec, int32_t n_mels, const int32_t* fb_ptr,
+                    const int32_t* fb_idx, const float* fb_val, float* mel, int32_t ld_mel, evk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Element-wise / row-wise kernels (all tensors are [rows][C] views with explicit pitches)
+ * ------------------------------------------------------------------------------------------ */
+/* generic unary map y = f(x); op: 0 copy*alpha, 1 lrelu(alpha), 2 tanh, 3 mish, 4 relu.  bwd: dx = dy*f'(x) */
+int evk_unary(int32_t op, float alpha, const float* x, int32_t ldx, float* y, int32_t ldy, int64_t rows, int32_t C,
+              evk_stream_t stream);
+int evk_unary_bwd(int32_t op, float alpha, const float* x, int32_t ldx, const float* dy, int32_t lddy, float* dx,
+                  int32_t lddx, int64_t rows, int32_t C, evk_stream_t stream);
+/* y = alpha*a + beta*b (+ gamma*c), optional row mask (t < len[b], T rows per batch); b,c nullable */
+int evk_axpby(const float* a, int32_t lda, float alpha, const float* b, int32_t ldb, float beta, const float* c,
+              int32_t ldc, float gamma, float* y, int32_t ldy, int64_t rows, int32_t C, const int32_t* len,
+              int32_t T, evk_stream_t stream);
+/* y[b][t][:] = x[b][t][:] + v[b][:]   (models.py:454 `x + self.cond(g)`) */
+int evk_add_bvec(const float* x, int32_t ldx, const float* v, int32_t ldv, float* y, int32_t ldy, int32_t B,
+                 int32_t T, int32_t C, evk_stream_t stream);
+/* WaveNet gate (commons.py:94-101): acts = tanh(a[:, :H] + g[b][:H]) * sigmoid(a[:, H:] + g[b][H:]) */
+int evk_wn_gate(const float* a, int32_t lda, const float* g, int32_t ldg, float* acts, int32_t ldo, int32_t B,
+                int32_t T, int32_t Hc, evk_stream_t stream);
+int evk_wn_gate_bwd(const float* a, int32_t lda, const float* g, int32_t ldg, const float* dacts, int32_t lddo,
+                    float* da, int32_t ldda, int32_t B, int32_t T, int32_t Hc, evk_stream_t stream);
+/* GLU with residual (modules.py:553-559): y = x + h[:, :C] * sigmoid(h[:, C:])  (x nullable => plain GLU) */
+int evk_glu_res(const float* x, int32_t ldx, const float* h, int32_t ldh, float* y, int32_t ldy, int64_t rows,
+                int32_t C, evk_stream_t stream);
+int evk_glu_res_bwd(const float* h, int32_t ldh, const float* dy, int32_t lddy, float* dh, int32_t lddh, int64_t rows,
+                    int32_t C, evk_stream_t stream);
+/* posterior reparameterisation (models.py:357-358): z = (m + noise*exp(logs)) * mask */
+int evk_reparam(const float* stats, int32_t lds, const float* noise, int32_t ldn, float* z, int32_t ldz, int32_t B,
+                int32_t T, int32_t C, const int32_t* len, evk_stream_t stream);
+int evk_reparam_bwd(const float* stats, int32_t lds, const float* noise, int32_t ldn, const float* dz, int32_t lddz,
+                    float* dstats, int32_t ldds, int32_t B, int32_t T, int32_t C, const int32_t* len,
+                    evk_stream_t stream);
+/* row mask: y = x * (t < len[b]) */
+int evk_rowmask(const float* x, int32_t ldx, float* y, int32_t ldy, int32_t B, int32_t T, int32_t C,
+                const int32_t* len, evk_stream_t stream);
+/* channel reversal (modules.py:376-383 Flip): y[r][c] = x[r][C-1-c] */
+int evk_flip_channels(const float* x, int32_t ldx, float* y, int32_t ldy, int64_t rows, int32_t C,
+                      evk_stream_t stream);
+/* segment gather (commons.py:42-48): y[b][j][:] = x[b][ids[b]*mul + j][:]; bwd scatters into zeroed dx */
+int evk_slice_rows(const float* x, int32_t ldx, int32_t Tin, const int64_t* ids, int32_t mul, float* y, int32_t ldy,
+                   int32_t B, int32_t seg, int32_t C, int32_t scatter, evk_stream_t stream);
+/* right reflect pad of a [B][T] 1-channel signal to Tp (models.py:543-546); bwd folds */
+int evk_reflect_pad_right(const float* x, int32_t T, float* y, int32_t Tp, int32_t B, int32_t bwd,
+                          evk_stream_t stream);
+/* layout change at the API boundary: [B][C][T] <-> [B][T][C(ld)] */
+int evk_transpose_bct_btc(const float* x, float* y, int32_t B, int32_t C, int32_t T, int32_t ld, int32_t to_btc,
+                          evk_stream_t stream);
+/* embedding gather y[r][:] = table[idx[r / rep]][:]  (rep=2: models.py:924-927 nearest x2) and its
+ * scatter-add gradient (rep must be 1) */
+int evk_embedding(const float* table, int32_t ldt, const int64_t* idx, int64_t rows, int32_t rep, float* y,
+                  int32_t ldy, int32_t C, evk_stream_t stream);
+int evk_embedding_bwd(const float* dy, int32_t lddy, const int64_t* idx, int64_t rows, float* dtable, int32_t ldt,
+                      int32_t C, evk_stream_t stream);
+/* masked temporal mean (modules.py:729-737): y[b][:] = sum_{t<len[b]} x[b][t][:] / len[b]; bwd broadcast */
+int evk_masked_mean(const float* x, int32_t ldx, float* y, int32_t ldy, int32_t B, int32_t T, int32_t C,
+                    const int32_t* len, int32_t bwd, evk_stream_t stream);
+/* inverted dropout with a Philox stream; seed/offset live in device memory (graph replay safe) */
+int evk_dropout(const float* x, float* y, int64_t n, float p, const uint64_t* seed_offset, uint64_t stream_id,
+                evk_stream_t stream);
+/* standard normal noise (models.py:358 randn_like) and uniform slice ids (commons.py:51-58) */
+int evk_randn(float* y, int64_t n, const uint64_t* seed_offset, uint64_t stream_id, evk_stream_t stream);
+int evk_rand_slice_ids(int64_t* ids, const int32_t* len, int32_t B, int32_t seg, const uint64_t* seed_offset,
+                       uint64_t stream_id, evk_stream_t stream);
+int evk_advance_rng(uint64_t* seed_offset, uint64_t inc, evk_stream_t stream);
+
+/* channel LayerNorm (modules.py:28-31) over the C floats of each row; saves mean/rstd [rows][2] */
+int evk_layernorm_fwd(const float* x, int32_t ldx, const float* res, int32_t ldr, const float* gamma,
+                      const float* beta, float eps, float* y, int32_t ldy, float* stats, int64_t rows, int32_t C,
+                      evk_stream_t stream);
+int evk_layernorm_bwd(const float* x, int32_t ldx, const float* res, int32_t ldr, const float* gamma,
+                      const float* stats, const float* dy, int32_t lddy, float* dx, int32_t lddx, float* dgamma,
+                      float* dbeta, int64_t rows, int32_t C, evk_stream_t stream);
+
+/* attention softmax (attentions.py:243-279, modules.py:669-682): in place on S [Z][Tq][Tk] (row pitch lds)
+ *   s = (S + relk[z][i][j-i+win]) * scale (|j-i|<=win, relk nullable [Z][Tq][2win+1], both unscaled);
+ *   key j >= klen[b] or query i >= qlen[b] -> fill (finite -1e4 or -inf); softmax over j.  */
+int evk_attn_softmax(float* S, int32_t lds, int32_t Z, int32_t H, int32_t Tq, int32_t Tk, float scale, const float* relk,
+                     int32_t win, const int32_t* qlen, const int32_t* klen, float fill, evk_stream_t stream);
+/* dS = P * (dP - sum_j dP*P) * scale, in place on dP; also emits drelk[z][i][r] = dS[i][i+r-win] (nullable) */
+int evk_attn_softmax_bwd(const float* P, float* dP, int32_t lds, int32_t Z, int32_t Tq, int32_t Tk, float scale, float* drelk,
+                         int32_t win, evk_stream_t stream);
+/* Windowed relative-position terms (attentions.py:254-288; skew helpers :312-365 replaced by band indexing).
+ * E is [2*win+1][dk] (shared across heads); heads live in the channel dim: q[b][t][h*dk + d].
+ *   relk_logits: rel[z][i][r] = q_i . E[r]                        (consumed by evk_attn_softmax)
+ *   relk_bwd:    dq_i += sum_r drel[z][i][r] E[r];  dE[r] += sum_{z,i} drel[z][i][r] q_i
+ *   attn_band:   band[z][i][r] = P[z][i][i+r-win] (to_band=1) / P[z][i][i+r-win] += band (to_band=0)
+ *   relv_out:    out_i += sum_r band[z][i][r] E[r]
+ *   relv_bwd:    dband[z][i][r] = dout_i . E[r];  dE[r] += sum_{z,i} band[z][i][r] dout_i            */
+int evk_relk_logits(const float* q, int32_t ldq, const float* E, int32_t B, int32_t H, int32_t T, int32_t dk,
+                    int32_t win, float* rel, evk_stream_t stream);
+int evk_relk_bwd(const float* drel, const float* q, int32_t ldq, const float* E, int32_t B, int32_t H, int32_t T,
+                 int32_t dk, int32_t win, float* dq, int32_t lddq, float* dE, evk_stream_t stream);
+int evk_attn_band(float* P, int32_t lds, float* band, int32_t Z, int32_t Tq, int32_t Tk, int32_t win, int32_t to_band,
+                  evk_stream_t stream);
+int evk_relv_out(const float* band, const float* E, int32_t B, int32_t H, int32_t T, int32_t dk, int32_t win,
+                 float* out, int32_t ldo, evk_stream_t stream);
+int evk_relv_bwd(const float* band, const float* dout, int32_t lddo, const float* E, int32_t B, int32_t H, int32_t T,
+                 int32_t dk, int32_t win, float* dband, float* dE, evk_stream_t stream);
+
+/* nearest-codeword search (core_vq.py:172-180): codes[r] = argmax_k -((|x|^2 - 2 x.e_k) + |e_k|^2), lowest
+ * index on ties.  The x.E^T products come from evk_sgemm_nt_f32 (exact fp32 FMA, NOT the TF32 tensor path:
+ * token indices must not depend on operand rounding).  enorm_scratch: [K] floats. */
+int evk_sgemm_nt_f32(const float* A, int32_t lda, const float* B, int32_t ldb, float* C, int32_t ldc, int32_t M,
+                     int32_t N, int32_t K, evk_stream_t stream);
+int evk_vq_argmax(const float* dots, int32_t ldd, const float* x, int32_t ldx, const float* embed, int32_t lde,
+                  int64_t rows, int32_t K, int32_t D, int64_t* codes, float* enorm_scratch, evk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Loss reductions (losses.py:7-61, sovits.py:513): out[slot] += scale * sum(f(a,b))
+ *   kind 0: (1-a)^2   1: a^2   2: |a-b|   ; bwd kinds write da (scaled by *gscale device scalar * scale)
+ * ------------------------------------------------------------------------------------------ */
+int evk_reduce_loss(int32_t kind, const float* a, const float* b, int64_t n, float scale, float* out,
+                    evk_stream_t stream);
+int evk_reduce_loss_bwd(int32_t kind, const float* a, const float* b, int64_t n, float scale, const float* gout,
+                        float* da, evk_stream_t stream);
+/* masked KL (losses.py:46-61): out += sum((logs_p-logs_q-0.5+0.5(z_p-m_p)^2 exp(-2logs_p))*mask); and grads */
+int evk_kl_loss(const float* z_p, int32_t ldz, const float* logs_q, int32_t ldq, const float* m_p, int32_t ldm,
+                const float* logs_p, int32_t ldp, int32_t B, int32_t T, int32_t C, const int32_t* len, float* out,
+                evk_stream_t stream);
+int evk_kl_loss_bwd(const float* z_p, int32_t ldz, const float* logs_q, int32_t ldq, const float* m_p, int32_t ldm,
+                    const float* logs_p, int32_t ldp, int32_t B, int32_t T, int32_t C, const int32_t* len,
+                    const float* gout, float gscale, float* dz_p, float* dlogs_q, float* dm_p, float* dlogs_p,
+                    int32_t ldg, evk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Optimiser (sovits.py:286-319,503-525): one fused AdamW pass over a flat fp32 arena (one call per
+ * lr group); also accumulates sum(g^2) (commons.py:140-155 grad-norm probe, without its 883 host syncs).
+ * ------------------------------------------------------------------------------------------ */
+int evk_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper /* device [lr, bc1, bc2] */,
+                   float beta1, float beta2, float eps, float wd, float grad_scale, float* gnorm_sq /* nullable, += */,
+                   evk_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EVK_H_ */

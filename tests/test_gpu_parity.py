@@ -1,0 +1,36 @@
+"""GPU parity tests proper (`pytest -m gpu`): CUDA path (through the C ABI) vs the CPU oracle + reference goldens."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GROUPS = ["conv", "conv_transpose", "elementwise", "attention", "vq_losses_optim", "mel", "s2_small", "s2_ragged", "api"]
+
+
+@pytest.fixture(scope="module")
+def evk():
+    from easevoice_trainer_b200 import lib
+    L = lib.init()          # raises loudly if libevk_sm100.so or the B200 is missing: there is no fallback path
+    L.evk_set_precise(0)
+    return L
+
+
+@pytest.mark.parametrize("idx", range(len(GROUPS)), ids=GROUPS)
+def test_group(evk, idx):
+    from tests import checks
+    rows = checks.ALL[idx]()
+    torch.cuda.synchronize()
+    bad = [(n, e, t) for n, e, t in rows if not (e == e and e <= t)]
+    assert not bad, "\n".join(f"{n}: err={e:.3e} > tol={t:.1e}" for n, e, t in bad)
+
+
+def test_precise_mode_tightens_conv(evk):
+    """3xTF32 mode must agree with the fp32 oracle ~100x tighter than plain TF32 (proves the error is rounding, not indexing)."""
+    from tests import checks
+    evk.evk_set_precise(1)
+    try:
+        rows = checks.check_conv() + checks.check_conv_transpose()
+    finally:
+        evk.evk_set_precise(0)
+    bad = [(n, e) for n, e, t in rows if not (e == e and e <= 1e-4)]
+    assert not bad, "\n".join(f"{n}: err={e:.3e}" for n, e in bad)
