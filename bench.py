@@ -1,0 +1,332 @@
+#!/usr/bin/env python
+"""Benchmark of the stage-2 (SoVITS + HiFi-GAN) train step -- BASELINE.json's metric.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path (N>1: launched by torchrun)
+  python bench.py --impl reference --steps K --warmup W    # the reference's algorithm on the host CPU cores (oracle port)
+
+One "step" = everything in /root/reference/src/train/sovits.py:438-525 for one batch of 16 x 10 s utterances:
+G forward, mel features + slicing, D forward/backward/AdamW, D forward again, G backward/AdamW.
+`value` is device-timed with the batch resident in HBM; `e2e` adds, every step, the pinned-host -> device copy of the
+step's inputs (wav, ssl features, phonemes, lengths), the on-GPU |X| feature extraction the reference does in CPU
+DataLoader workers, and a device -> host read of the step's losses.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "s2 SoVITS+HiFiGAN train-step audio-seconds/sec"
+UNIT = "audio-s/s"
+B_PER_GPU, UTT_SECONDS, TEXT_LEN, HOP = 16, 10.0, 120, 640
+
+
+def frames_for(sr_label):
+    T = int(UTT_SECONDS * sr_label) // HOP
+    return 2 * (T // 2 + 1)                    # TextAudioSpeakerCollate pads to 2*(Tmax//2+1) (data_utils.py:185-188)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d["hbm_gbs"], d["bf16_tflops"], d.get("bf16_tflops_sustained", d["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, 1400.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons every 200 ms during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        time.sleep(0.05)
+        sm = sorted(int(float(r[1])) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        mx = max((int(float(r[2])) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()), default=None)
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+# --------------------------------------------------------------------------------------------------
+def cpu_threads():
+    """Threads for the CPU arm: torch's intra-op pool stops scaling (and then degrades badly) on these small conv
+    shapes well before 128 threads -- measured 550 s/step with 128 threads vs ~7 s with 8 -- so use at most 16."""
+    return max(1, min(os.cpu_count() or 1, 16))
+
+
+def cpu_reference_step(Bc, T, threads, steps, warmup):
+    """The reference's algorithm (oracle port, torch fp32, CPU) for one bounded sample: fwd + both backwards."""
+    import torch
+    from oracle import s2_oracle, mel_oracle
+    torch.set_num_threads(threads)
+    PG = s2_oracle.init_params(s2_oracle.generator_param_spec(), 1234)
+    PD = s2_oracle.init_params(s2_oracle.discriminator_param_spec(), 4321)
+    for k, v in PG.items():
+        if k not in s2_oracle.GEN_BUFFERS:
+            v.requires_grad_(True)
+    for v in PD.values():
+        v.requires_grad_(True)
+    wav, ssl, text, spec_len, text_len = s2_oracle.synthetic_batch(Bc, T, TEXT_LEN, 1234)
+    spec = mel_oracle.spectrogram(wav.squeeze(1), 2048, HOP, 2048)
+    g = torch.Generator().manual_seed(1)
+    times = []
+    gp = [v for k, v in PG.items() if k not in s2_oracle.GEN_BUFFERS]
+    for it in range(warmup + steps):
+        noise = torch.randn(Bc, 192, T, generator=g)
+        ids = (torch.rand(Bc, generator=g) * (spec_len - 32 + 1)).long()
+        t0 = time.perf_counter()
+        o = s2_oracle.s2_losses(PG, PD, (ssl, spec, spec_len, wav, text, text_len), noise, ids)
+        torch.autograd.grad(o["loss_disc"], list(PD.values()), retain_graph=True)
+        torch.autograd.grad(o["loss_gen_all"], gp, allow_unused=True)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return sum(times) / len(times)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    threads = cpu_threads()
+    T = frames_for(args.sr_label)
+    Bc = args.cpu_batch
+    sec = cpu_reference_step(Bc, T, threads, args.steps, args.warmup)
+    val = Bc * UTT_SECONDS / sec
+    sample = f"oracle port of sovits.py:459-525 (fwd + D bwd + G bwd, fp32, no optimiser), B={Bc} x {UTT_SECONDS:.0f} s (T={T}), {threads} threads"
+    line = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                impl="reference",
+                config=dict(workload=f"s2_step_B{B_PER_GPU}x{UTT_SECONDS:.0f}s_sr{args.sr_label}_T{T}", cpu_sample_batch=Bc),
+                cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind="port", sample=sample),
+                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+    return 0
+
+
+# --------------------------------------------------------------------------------------------------
+def graph_time(fn):
+    """Device time (ms) of `fn`'s launches with the host taken out of the loop: capture once, time a graph replay."""
+    import torch
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    g.replay()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    g.replay()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def kernel_table(ops, dev):
+    """Heaviest conv layers of the step (Appendix A of SURVEY.md), forward launch of each timed in isolation.
+    count = how many times a launch of that shape/flop count runs per step (fwd + dgrad of G and of the 2B-batched D)."""
+    import torch
+    B = B_PER_GPU
+    rows = []
+    #        name, batch, T, C, N, k, dil, P, stride, launches/step
+    layers = [("dec stage1 resblock k11 128ch", B, 2560, 128, 128, 11, 1, 1, 1, 12), ("dec stage1 resblock k7 128ch", B, 2560, 128, 128, 7, 1, 1, 1, 12),
+              ("dec stage0 resblock k11 256ch", B, 320, 256, 256, 11, 1, 1, 1, 12), ("dec stage2 resblock k11 64ch", B, 5120, 64, 64, 11, 1, 1, 1, 12),
+              ("dec stage3 resblock k11 32ch", B, 10240, 32, 32, 11, 1, 1, 1, 12), ("dec stage4 resblock k11 16ch", B, 20480, 16, 16, 11, 1, 1, 1, 12),
+              ("discP 1024->1024 k5 p=2", 2 * B, 127, 1024, 1024, 5, 1, 2, 1, 4), ("discP 512->1024 k5 s3 p=2", 2 * B, 380, 512, 1024, 5, 1, 2, 3, 4),
+              ("discS 1024->1024 k5", 2 * B, 80, 1024, 1024, 5, 1, 1, 1, 4), ("enc_q WN in_layer 192->384 k5", B, 346, 192, 384, 5, 1, 1, 1, 32),
+              ("enc_p FFN 192->768 k3", B, 346, 192, 768, 3, 1, 1, 1, 12)]
+    for name, b, T, C, N, k, dil, P, stride, count in layers:
+        nset = 6
+        xs = [torch.randn(b, T * P, C, device=dev) for _ in range(nset)]
+        v = torch.randn(N, C, k, device=dev) * 0.02
+        w = ops.pack_weight(v, None)
+        bias = torch.zeros(N, device=dev)
+        pad = (k * dil - dil) // 2
+        def burst():
+            for _ in range(4):
+                for x in xs:
+                    yy = ops.conv(x, w, bias, stride=stride, pad=pad, dil=dil, P=P)
+            return yy
+        with torch.no_grad():
+            y = burst()
+            ms = graph_time(burst) / (4 * nset)
+        J = y.shape[1]
+        flops = 2.0 * b * J * N * C * k
+        rows.append(dict(layer=name, ms=ms, flops=flops, tflops=flops / (ms * 1e-3) / 1e12, count=count))
+        del xs
+    return rows
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from easevoice_trainer_b200 import lib, ops, models
+    from easevoice_trainer_b200.train import s2_step
+    from easevoice_trainer_b200 import configs
+    lib.init()
+    hps = configs.load_s2_config()
+    torch.manual_seed(hps["train"]["seed"])
+    net_g = models.SynthesizerTrn(hps["data"]["filter_length"] // 2 + 1, hps["train"]["segment_size"] // hps["data"]["hop_length"],
+                                  n_speakers=hps["data"]["n_speakers"], **hps["model"]).to(dev).train()
+    net_d = models.MultiPeriodDiscriminator(hps["model"]["use_spectral_norm"]).to(dev).train()
+    st = s2_step.S2Step(net_g, net_d, hps["train"], hps["data"], world_size=world)
+    ops.manual_seed(hps["train"]["seed"] + rank)
+    T = frames_for(args.sr_label)
+    host = s2_step.synthetic_batch(B_PER_GPU, T, TEXT_LEN, dev, seed=1234 + rank)
+    host = {k: v.pin_memory() for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+
+    batch = s2_step.to_device_batch(host, dev, st.bank)
+    last = {}
+
+    run = st.step if args.no_graph else st.graph_step
+
+    def step_resident():
+        last.update(run(batch))
+
+    def step_e2e():
+        b = s2_step.to_device_batch(host, dev, st.bank)
+        out = run(b)
+        last["host"] = torch.stack([out["loss_gen_all"], out["loss_disc"]]).cpu()     # D2H read of the step's losses
+
+    l0 = ops.launches()
+    st.step(batch)                                   # one eager step: counts the library launches a step consists of
+    launches = ops.launches() - l0
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    ms = timed(step_resident, args.steps)
+    clocks = sampler.stop() if sampler else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    audio_s = world * B_PER_GPU * UTT_SECONDS
+    losses = {k: float(v) for k, v in last.items() if k != "host"}
+
+    extra = {}
+    if rank == 0:
+        hbm, tf_burst, tf_sus, src = peaks()
+        # ---- dominant kernel: the tensor-core implicit-GEMM conv, timed per layer shape with back-to-back launches
+        table = kernel_table(ops, dev)
+        fl = sum(r["flops"] * r["count"] for r in table)
+        tm = sum(r["ms"] * r["count"] for r in table)
+        ach = fl / (tm * 1e-3) / 1e12
+        extra["roofline"] = dict(bound="tensor", kernel="gconv_f_kernel (TF32 mma.sync implicit-GEMM conv, fwd + dgrad launches)",
+                                 achieved=ach, peak=tf_sus, unit="TFLOP/s", frac=ach / tf_sus, traffic=None,
+                                 peak_source=f"{src} cuBLAS bf16 sustained; the kernel computes in TF32 whose nominal peak is half of bf16",
+                                 how="flops-weighted over the heaviest layer shapes of the step, each 20 back-to-back launches "
+                                     "between CUDA events on rotating (> L2) buffers",
+                                 layers=[{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in table])
+        # ---- fused mel kernel standalone: 16 x 10 s at the label rate, |X| + log-mel emitted
+        Lw = batch["wav"].shape[1]
+        nset, reps = 6, 3                                        # 6 x (wav 14 MB + |X| 23 MB + mel 3 MB) = 240 MB > L2
+        wavs = [torch.rand(B_PER_GPU, Lw, device=dev) - 0.5 for _ in range(nset)]
+        frames = B_PER_GPU * (Lw // HOP)
+        def mel_burst():
+            for _ in range(reps):
+                for w in wavs:
+                    ops.mel_frontend(w, st.bank, HOP, want_spec=True, want_mel=True)
+        mel_burst()
+        mel_ms = graph_time(mel_burst) / (nset * reps)
+        alg_bytes = 4.0 * B_PER_GPU * Lw + frames * (1025 + 128) * 4.0     # 7172 B/frame with |X| emitted
+        gbs = alg_bytes / (mel_ms * 1e-3) / 1e9
+        extra["mel_roofline"] = dict(bound="hbm", kernel="mel_fwd_kernel (|X| + log-mel emitted)", achieved=gbs, peak=hbm,
+                                     unit="GB/s", frac=gbs / hbm, frames=frames, ms=mel_ms, peak_source=src, traffic=None,
+                                     how=f"{nset * reps} back-to-back launches over {nset} rotating buffer sets (> L2)")
+        # ---- CPU baseline on this box's host cores (bounded sample)
+        threads = cpu_threads()
+        if not args.no_cpu_baseline:
+            sec = cpu_reference_step(args.cpu_batch, T, threads, 1, 0)
+            v = args.cpu_batch * UTT_SECONDS / sec
+            extra["cpu_baseline"] = dict(value=v, unit=UNIT, cores=threads, kind="port",
+                                         sample=f"oracle port of sovits.py:459-525 (fwd + both backwards, fp32), B={args.cpu_batch} x 10 s, "
+                                                f"T={T}, 1 cold step, {sec:.1f} s")
+        line = dict(metric=METRIC, value=audio_s / (ms * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="tf32", data="synthetic",
+                    config=dict(workload=f"s2_step_B{B_PER_GPU}x{UTT_SECONDS:.0f}s_sr{args.sr_label}_T{T}", global_batch=world * B_PER_GPU,
+                                frames=T, segment=hps["train"]["segment_size"], text_len=TEXT_LEN,
+                                parallelism=f"dp{world}", weights="random-init seed 1234",
+                                l2="params+optimizer state+activations touched per step (>2 GB) far exceed the 126 MB L2; no explicit flush"),
+                    e2e=dict(value=audio_s / (ms_e2e * 1e-3), unit=UNIT, ms_per_step=ms_e2e, h2d_bytes_per_step=h2d,
+                             d2h_bytes_per_step=8),
+                    gpu_launches=launches, cuda_graph=not args.no_graph, clocks=clocks, losses=losses)
+        line.update(extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sr-label", type=int, default=22050, help="BASELINE.json quotes 10 s @ 22.05 kHz; 32000 = native s2.json rate")
+    ap.add_argument("--cpu-batch", type=int, default=2, help="utterances in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

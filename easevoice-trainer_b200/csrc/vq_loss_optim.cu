@@ -153,12 +153,15 @@ __global__ void kl_loss_bwd_kernel(const float* __restrict__ zp, int ldz, const 
 }
 
 // ---- fused AdamW over a flat arena -----------------------------------------------------------
-// hyper (device): [lr, bias_correction1, bias_correction2]
+// hyper (device): [lr, step]  -- step is the 1-based AdamW step counter kept on the device (graph-replay safe);
+// bias corrections 1 - beta^step are derived here in double precision.
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                             long long n, const float* __restrict__ hyper, float beta1, float beta2, float eps, float wd,
-                             float grad_scale, float* __restrict__ gnorm_sq) {
+                             long long n, const float* __restrict__ hyper, float lr_scale, float beta1, float beta2, float eps,
+                             float wd, float grad_scale, float* __restrict__ gnorm_sq) {
   __shared__ float red[33];
-  const float lr = hyper[0], bc1 = hyper[1], bc2 = hyper[2];
+  const float lr = hyper[0] * lr_scale;
+  const double stepd = (double)hyper[1];
+  const float bc1 = (float)(1.0 - pow((double)beta1, stepd)), bc2 = (float)(1.0 - pow((double)beta2, stepd));
   const float step = lr / bc1, isq = rsqrtf(bc2);
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -243,11 +246,19 @@ extern "C" int evk_kl_loss_bwd(const float* z_p, int32_t ldz, const float* logs_
                                                    gscale, dz_p, dlogs_q, dm_p, dlogs_p, ldg);
   return check_launch("kl_loss_bwd");
 }
-extern "C" int evk_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, float beta1,
-                              float beta2, float eps, float wd, float grad_scale, float* gnorm_sq,
+__global__ void scalar_add_kernel(float* x, float v) { x[0] += v; }
+
+extern "C" int evk_scalar_add(float* x, float v, evk_stream_t stream) {
+  EVK_REQUIRE(x, EVK_ERR_ARG, "scalar_add: null");
+  scalar_add_kernel<<<1, 1, 0, ST>>>(x, v);
+  return check_launch("scalar_add");
+}
+
+extern "C" int evk_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, float lr_scale,
+                              float beta1, float beta2, float eps, float wd, float grad_scale, float* gnorm_sq,
                               evk_stream_t stream) {
   EVK_REQUIRE(p && g && m && v && hyper, EVK_ERR_ARG, "adamw_flat: null tensor");
   if (n == 0) return EVK_OK;
-  adamw_kernel<<<g1(n), 256, 0, ST>>>(p, g, m, v, n, hyper, beta1, beta2, eps, wd, grad_scale, gnorm_sq);
+  adamw_kernel<<<g1(n), 256, 0, ST>>>(p, g, m, v, n, hyper, lr_scale, beta1, beta2, eps, wd, grad_scale, gnorm_sq);
   return check_launch("adamw_flat");
 }

@@ -35,10 +35,46 @@ def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
 
+# ---- optional per-call device timing (bench.py roofline / breakdown; off by default) -------------------------
+_prof = None
+
+
+def profile_begin():
+    """Start recording (name, CUDA-event pair, algorithmic flops, algorithmic bytes) for every library call."""
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """-> {family: dict(calls, ms, flops, bytes)}; synchronises once at the end (never inside the step)."""
+    global _prof
+    rec, _prof = _prof, None
+    torch.cuda.synchronize()
+    agg = {}
+    for name, e0, e1, fl, by in rec:
+        a = agg.setdefault(name, dict(calls=0, ms=0.0, flops=0.0, bytes=0.0))
+        a["calls"] += 1
+        a["ms"] += e0.elapsed_time(e1)
+        a["flops"] += fl
+        a["bytes"] += by
+    return agg
+
+
+def _timed(name, fn, flops=0.0, nbytes=0.0):
+    if _prof is None:
+        return fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    r = fn()
+    e1.record()
+    _prof.append((name, e0, e1, flops, nbytes))
+    return r
+
+
 def _call(name, *args):
     global _launches
     _launches += 1
-    L.check(getattr(_lib(), name)(*args, _st()))
+    _timed(name, lambda: L.check(getattr(_lib(), name)(*args, _st())))
 
 
 def _rows(t):
@@ -134,7 +170,8 @@ def _desc(**kw):
 def _run_desc(fn, d):
     global _launches
     _launches += 1
-    L.check(getattr(_lib(), fn)(ctypes.byref(d), _st()))
+    flops = 2.0 * d.Z * d.J * d.P * d.N * (d.C // max(d.G, 1)) * d.Q
+    _timed(fn, lambda: L.check(getattr(_lib(), fn)(ctypes.byref(d), _st())), flops)
 
 
 def _aligned(t, ld):
@@ -1161,6 +1198,12 @@ def spec_to_mel(spec, bank):
 
 
 # ---- optimiser -----------------------------------------------------------------------------------
-def adamw_flat(p, g, m, v, hyper, betas, eps, wd, grad_scale=1.0, gnorm_sq=None):
-    _call("evk_adamw_flat", _p(p), _p(g), _p(m), _p(v), p.numel(), _p(hyper), ctypes.c_float(betas[0]),
-          ctypes.c_float(betas[1]), ctypes.c_float(eps), ctypes.c_float(wd), ctypes.c_float(grad_scale), _p(gnorm_sq))
+def adamw_flat(p, g, m, v, hyper, lr_scale, betas, eps, wd, grad_scale=1.0, gnorm_sq=None):
+    """hyper: device float32 [lr, step] (step already incremented for this update)."""
+    _call("evk_adamw_flat", _p(p), _p(g), _p(m), _p(v), p.numel(), _p(hyper), ctypes.c_float(lr_scale),
+          ctypes.c_float(betas[0]), ctypes.c_float(betas[1]), ctypes.c_float(eps), ctypes.c_float(wd),
+          ctypes.c_float(grad_scale), _p(gnorm_sq))
+
+
+def scalar_add(x, v):
+    _call("evk_scalar_add", _p(x), ctypes.c_float(v))

@@ -49,12 +49,19 @@ class FlatAdamW:
                 p.data = self.flat_p[off:off + k].view_as(p)
                 self.slots[n] = (off, k)
                 off += k
-            self.groups.append(dict(lr_scale=lr_scale, beg=beg, end=off, names=list(names),
-                                    hyper=torch.zeros(3, device=dev, dtype=torch.float32)))
+            self.groups.append(dict(lr_scale=lr_scale, beg=beg, end=off, names=list(names)))
         self.params = [named[n] for _, names in groups for n in names]
         self.names = [n for _, names in groups for n in names]
-        self.step_count = 0
+        self.hyper = torch.zeros(2, device=dev, dtype=torch.float32)        # [lr, step] lives on the device
         self.gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
+
+    @property
+    def step_count(self):
+        return int(self.hyper[1].item())
+
+    def set_lr(self, lr):
+        """host-side (outside any captured graph): the lr only changes at epoch boundaries (ExponentialLR)."""
+        self.hyper[0] = float(lr)
 
     def set_grads(self, grads):
         """copy autograd's per-parameter gradients into the flat buffer (unused parameters get zeros)."""
@@ -68,24 +75,23 @@ class FlatAdamW:
                 srcs.append(g)
         torch._foreach_copy_(views, srcs)
 
-    def step(self, lr, grad_scale=1.0):
-        self.step_count += 1
-        b1, b2 = self.betas
-        bc1, bc2 = 1.0 - b1 ** self.step_count, 1.0 - b2 ** self.step_count
+    def step(self, grad_scale=1.0):
+        """graph-capturable: step counter, bias corrections and lr are read from device memory."""
+        ops.scalar_add(self.hyper[1:], 1.0)
         self.gnorm_sq.zero_()
         for g in self.groups:
-            g["hyper"].copy_(torch.tensor([lr * g["lr_scale"], bc1, bc2], dtype=torch.float32), non_blocking=True)
             s, e = g["beg"], g["end"]
-            ops.adamw_flat(self.flat_p[s:e], self.flat_g[s:e], self.flat_m[s:e], self.flat_v[s:e], g["hyper"], self.betas,
-                           self.eps, self.wd, grad_scale, self.gnorm_sq)
+            ops.adamw_flat(self.flat_p[s:e], self.flat_g[s:e], self.flat_m[s:e], self.flat_v[s:e], self.hyper, g["lr_scale"],
+                           self.betas, self.eps, self.wd, grad_scale, self.gnorm_sq)
 
     # torch.optim-compatible state for checkpoints (ckpt.py:78-93 stores optimizer.state_dict())
     def state_dict(self):
         state = {}
+        sc = self.step_count
         for i, n in enumerate(self.names):
             off, k = self.slots[n]
             shape = self.params[i].shape
-            state[i] = dict(step=torch.tensor(float(self.step_count)), exp_avg=self.flat_m[off:off + k].view(shape).clone(),
+            state[i] = dict(step=torch.tensor(float(sc)), exp_avg=self.flat_m[off:off + k].view(shape).clone(),
                             exp_avg_sq=self.flat_v[off:off + k].view(shape).clone())
         pg, idx = [], 0
         for g in self.groups:
@@ -102,7 +108,7 @@ class FlatAdamW:
                 st = sd["state"][i]
                 self.flat_m[off:off + k].copy_(st["exp_avg"].reshape(-1))
                 self.flat_v[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
-                self.step_count = int(st["step"])
+                self.hyper[1] = float(st["step"])
 
 
 def g_param_groups(net_g, text_low_lr_rate):
@@ -134,9 +140,12 @@ class S2Step:
         self.opt_d = FlatAdamW(net_d.named_parameters(), [(1.0, [n for n, _ in net_d.named_parameters()])], betas,
                                hps_train["eps"])
         self.lr = hps_train["learning_rate"]
+        self.opt_g.set_lr(self.lr)
+        self.opt_d.set_lr(self.lr)
         dev = next(net_g.parameters()).device
         self.bank = get_bank(hps_data["sampling_rate"], hps_data["filter_length"], hps_data["n_mel_channels"],
                              hps_data["mel_fmin"], hps_data["mel_fmax"], dev)
+        self._graphs = {}
 
     def losses(self, batch, noise=None, ids_slice=None):
         """Forward + both losses (no optimiser).  batch: dict of channels-last device tensors:
@@ -181,25 +190,73 @@ class S2Step:
             dist.all_reduce(opt.flat_g)
 
     def step(self, batch, noise=None, ids_slice=None):
+        """Eager step (every kernel launched from Python).  No host synchronisation anywhere."""
         r = self.losses(batch, noise, ids_slice)
         loss_d = self.d_loss(r)
         gd = torch.autograd.grad(loss_d, self.opt_d.params, allow_unused=True)
         self.opt_d.set_grads(gd)
         self._allreduce(self.opt_d)
-        self.opt_d.step(self.lr, 1.0 / self.world)
+        self.opt_d.step(1.0 / self.world)
         loss_g, parts = self.g_loss(r)
         gg = torch.autograd.grad(loss_g, self.opt_g.params, allow_unused=True)
         self.opt_g.set_grads(gg)
         self._allreduce(self.opt_g)
-        self.opt_g.step(self.lr, 1.0 / self.world)
+        self.opt_g.step(1.0 / self.world)
         ops.advance_rng()
         out = dict(loss_disc=loss_d.detach(), loss_gen_all=loss_g.detach(), grad_norm_d=self.opt_d.gnorm_sq,
                    grad_norm_g=self.opt_g.gnorm_sq)
         out.update({k: v.detach() for k, v in parts.items()})
         return out
 
+    # ---- CUDA-graph path: the ~3000 launches of one step are captured once per batch shape and replayed --------
+    def graph_step(self, batch):
+        """Copy `batch` into the static input buffers of the graph captured for its shape, replay, return the static
+        loss tensors.  Shapes are bucketed by the sampler (sovits.py:233-252), so a handful of graphs covers a run."""
+        key = (tuple(batch["ssl"].shape), tuple(batch["text"].shape))
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._capture(batch)
+            self._graphs[key] = g
+        graph, static, out = g
+        for k in static:
+            if static[k] is not batch[k]:
+                static[k].copy_(batch[k], non_blocking=True)
+        graph.replay()
+        return out
+
+    def _capture(self, batch):
+        static = {k: (v.clone() if k != "spec" else v) for k, v in batch.items()}
+        # `spec` keeps its padded row pitch (a view of a wider buffer): clone the parent storage explicitly
+        sp = batch["spec"]
+        wide = torch.empty((sp.shape[0], sp.shape[1], sp.stride(1)), device=sp.device, dtype=sp.dtype)
+        static["spec"] = wide[:, :, :sp.shape[2]]
+        static["spec"].copy_(sp)
+        # warm-up (allocator, smem attributes, NCCL) must not count as training: snapshot and restore all mutable state
+        snap = [t.clone() for t in (self.opt_g.flat_p, self.opt_g.flat_m, self.opt_g.flat_v, self.opt_g.hyper,
+                                    self.opt_d.flat_p, self.opt_d.flat_m, self.opt_d.flat_v, self.opt_d.hyper,
+                                    ops.rng_state(sp.device))]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.step(static)
+        torch.cuda.current_stream().wait_stream(side)
+        for dst, src in zip((self.opt_g.flat_p, self.opt_g.flat_m, self.opt_g.flat_v, self.opt_g.hyper, self.opt_d.flat_p,
+                             self.opt_d.flat_m, self.opt_d.flat_v, self.opt_d.hyper, ops.rng_state(sp.device)), snap):
+            dst.copy_(src)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.step(static)
+        return graph, static, out
+
+    def set_lr(self, lr):
+        self.lr = lr
+        self.opt_g.set_lr(lr)
+        self.opt_d.set_lr(lr)
+
     def decay_lr(self):
-        self.lr *= self.t["lr_decay"]
+        self.set_lr(self.lr * self.t["lr_decay"])
 
 
 def synthetic_batch(B, T, X, device, seed=1234, hop=640, bank=None, ragged=False):

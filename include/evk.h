@@ -234,9 +234,11 @@ int evk_kl_loss_bwd(const float* z_p, int32_t ldz, const float* logs_q, int32_t 
  * Optimiser (sovits.py:286-319,503-525): one fused AdamW pass over a flat fp32 arena (one call per
  * lr group); also accumulates sum(g^2) (commons.py:140-155 grad-norm probe, without its 883 host syncs).
  * ------------------------------------------------------------------------------------------ */
-int evk_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper /* device [lr, bc1, bc2] */,
-                   float beta1, float beta2, float eps, float wd, float grad_scale, float* gnorm_sq /* nullable, += */,
-                   evk_stream_t stream);
+int evk_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n,
+                   const float* hyper /* device [lr, step]; bias corrections derived on the device (graph-replay safe) */,
+                   float lr_scale, float beta1, float beta2, float eps, float wd, float grad_scale,
+                   float* gnorm_sq /* nullable, += */, evk_stream_t stream);
+int evk_scalar_add(float* x, float v, evk_stream_t stream);   /* x[0] += v (device-side step counters) */
 
 #ifdef __cplusplus
 }
