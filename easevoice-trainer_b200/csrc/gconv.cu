@@ -20,7 +20,7 @@ struct GP {
   const float* x; float* w; float* y; const float* res; const float* bias;
   const int* in_len; const int* out_len;
   long long x_sb, x_sh, w_sb, w_sh, w_sq, y_sb, y_sh, r_sb, r_sh;
-  int ldx, ldw, ldy, ldr;
+  int ldx, ldw, ldy, ldr, b_sh;
   int Z, H, C, N, Q, Tin, J, P, is, os, o0, Tout, act;
   float slope;
   int off_min, off_max;
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(NT) gconv_f_kernel(const __grid_constant__ GP 
         for (int e = 0; e < 2; ++e) {
           if (n + e < p.N) {
             float v = acc[mf][nf][hf * 2 + e];
-            if (p.bias) v += p.bias[n + e];
+            if (p.bias) v += p.bias[h * p.b_sh + n + e];
             if (R) v += R[orow * p.ldr + n + e];
             v = apply_act(v, p.act, p.slope);
             Y[orow * p.ldy + n + e] = live ? v : 0.f;
@@ -212,6 +212,8 @@ __global__ void __launch_bounds__(NT) gconv_f_kernel(const __grid_constant__ GP 
 
 // ============================================================================================
 // W kernel (weight gradient): dW[q][n][c] += sum_pos Yg[orow][n] * X[irow(pos,q)][c]
+// GEMM view: M = n (out channels), N = (q, c) columns (taps folded into the column space so that skinny layers
+// fill the tile), K = positions (split over CTAs, merged with fp32 atomics).
 // ============================================================================================
 template <int TN, int TC, int WARPS_N, int WARPS_C, int WARPS_K, bool PRECISE>
 __global__ void __launch_bounds__(NT) gconv_w_kernel(const __grid_constant__ GP p) {
@@ -220,27 +222,28 @@ __global__ void __launch_bounds__(NT) gconv_w_kernel(const __grid_constant__ GP 
   static_assert(MF >= 1 && NF >= 1, "tile");
   constexpr int RK = (WARPS_K * 8 > 32) ? WARPS_K * 8 : 32;   // positions per pipeline stage
   constexpr int LDA = TN + 8, LDB = TC + 8;    // == 8 (mod 32) -> conflict-free fragment reads
-  __shared__ __align__(16) float As[2][RK][LDA];
-  __shared__ __align__(16) float Bs[2][RK][LDB];
+  extern __shared__ __align__(16) float wsm[];
+  float (*As)[RK][LDA] = reinterpret_cast<float (*)[RK][LDA]>(wsm);                     // [2][RK][LDA]
+  float (*Bs)[RK][LDB] = reinterpret_cast<float (*)[RK][LDB]>(wsm + 2 * RK * LDA);      // [2][RK][LDB]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int gid = lane >> 2, t4 = lane & 3;
   const int wk = warp % WARPS_K, wc = (warp / WARPS_K) % WARPS_C, wnn = warp / (WARPS_K * WARPS_C);
-  const int zq = blockIdx.z, z = zq / p.Q, q = zq - z * p.Q;
+  const int z = blockIdx.z;
   const int b = z / p.H, h = z - b * p.H;
-  const int tiles_c = (p.C + TC - 1) / TC;
+  const int Cq = (p.C + 3) & ~3;                      // per-tap column pitch (16-byte pieces never straddle taps)
+  const int ncols = p.Q * Cq;
+  const int tiles_c = (ncols + TC - 1) / TC;
   const int tn = blockIdx.y / tiles_c, tc = blockIdx.y - tn * tiles_c;
-  const int n0 = tn * TN, c0 = tc * TC;
+  const int n0 = tn * TN, col0 = tc * TC;
   const float* X = p.x + b * p.x_sb + h * p.x_sh;
   const float* Yg = p.y + b * p.y_sb + h * p.y_sh;
   const int npos = p.J * p.P;
   const int pbeg = blockIdx.x * p.rch, pend = min(npos, pbeg + p.rch);
   int lim = p.Tin;
   if (p.in_len) lim = min(lim, p.in_len[b]);
-  const int offq = p.off[q];
 
   auto load_stage = [&](int r0, int buf) {
-    // A: Yg rows
     constexpr int PA = TN / 4, PB = TC / 4;
     for (int i = tid; i < RK * PA; i += NT) {
       int rr = i / PA, pc = i - rr * PA;
@@ -256,12 +259,13 @@ __global__ void __launch_bounds__(NT) gconv_w_kernel(const __grid_constant__ GP 
     }
     for (int i = tid; i < RK * PB; i += NT) {
       int rr = i / PB, pc = i - rr * PB;
-      int pos = r0 + rr, c = c0 + pc * 4;
-      bool ok = (pos < pend) && (c < p.C);
+      int pos = r0 + rr, col = col0 + pc * 4;
+      int q = col / Cq, c = col - q * Cq;
+      bool ok = (pos < pend) && (q < p.Q) && (c < p.C);
       const float* src = X;
       if (ok) {
         int j = pos / p.P, w = pos - j * p.P;
-        int ij = j * p.is + offq;
+        int ij = j * p.is + p.off[q];
         ok = (ij >= 0) && (ij < lim);
         if (ok) src = X + ((long long)ij * p.P + w) * p.ldx + c;
       }
@@ -327,19 +331,21 @@ __global__ void __launch_bounds__(NT) gconv_w_kernel(const __grid_constant__ GP 
     __syncthreads();
   }
 
-  float* Wd = p.w + b * p.w_sb + h * p.w_sh + (long long)q * p.w_sq;
+  float* Wd = p.w + b * p.w_sb + h * p.w_sh;
 #pragma unroll
-  for (int mf = 0; mf < MF; ++mf)
+  for (int nf = 0; nf < NF; ++nf)
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      const int n = n0 + wnn * MF * 16 + mf * 16 + hf * 8 + gid;
-      if (n >= p.N) continue;
+    for (int e = 0; e < 2; ++e) {
+      const int col = col0 + wc * NF * 8 + nf * 8 + 2 * t4 + e;
+      const int q = col / Cq, c = col - q * Cq;
+      if (q >= p.Q || c >= p.C) continue;
+      float* wq = Wd + (long long)q * p.w_sq + c;
 #pragma unroll
-      for (int nf = 0; nf < NF; ++nf)
+      for (int mf = 0; mf < MF; ++mf)
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int c = c0 + wc * NF * 8 + nf * 8 + 2 * t4 + e;
-          if (c < p.C) atomicAdd(Wd + (long long)n * p.ldw + c, acc[mf][nf][hf * 2 + e]);
+        for (int hf = 0; hf < 2; ++hf) {
+          const int n = n0 + wnn * MF * 16 + mf * 16 + hf * 8 + gid;
+          if (n < p.N) atomicAdd(wq + (long long)n * p.ldw, acc[mf][nf][hf * 2 + e]);
         }
     }
 }
@@ -359,7 +365,7 @@ static int fill_gp(const evk_gconv_desc* d, GP& p) {
   p.in_len = d->in_len; p.out_len = d->out_len;
   p.x_sb = d->x_sb; p.x_sh = d->x_sh; p.w_sb = d->w_sb; p.w_sh = d->w_sh; p.w_sq = d->w_sq;
   p.y_sb = d->y_sb; p.y_sh = d->y_sh; p.r_sb = d->r_sb; p.r_sh = d->r_sh;
-  p.ldx = d->ldx; p.ldw = d->ldw; p.ldy = d->ldy; p.ldr = d->ldr;
+  p.ldx = d->ldx; p.ldw = d->ldw; p.ldy = d->ldy; p.ldr = d->ldr; p.b_sh = d->b_sh;
   p.Z = d->Z; p.H = d->H; p.C = d->C; p.N = d->N; p.Q = d->Q; p.Tin = d->Tin; p.J = d->J; p.P = d->P;
   p.is = d->is; p.os = d->os; p.o0 = d->o0; p.Tout = d->Tout; p.act = d->act; p.slope = d->slope;
   int mn = d->off[0], mx = d->off[0];
@@ -375,7 +381,7 @@ static int fill_gp(const evk_gconv_desc* d, GP& p) {
 }
 
 static int check_mma_alignment(const evk_gconv_desc* d, const char* who) {
-  EVK_REQUIRE(d->G <= 1, EVK_ERR_UNSUPPORTED, "%s: grouped convolutions use evk_conv_direct_*", who);
+  EVK_REQUIRE(d->G <= 1, EVK_ERR_UNSUPPORTED, "%s: pass groups as the inner batch (H = groups), not G", who);
   EVK_REQUIRE((d->ldx % 4) == 0 && (d->ldw % 4) == 0 && (d->w_sq % 4) == 0, EVK_ERR_ARG,
               "%s: ldx, ldw, w_sq must be multiples of 4 (ldx=%d ldw=%d)", who, d->ldx, d->ldw);
   EVK_REQUIRE((d->x_sb % 4) == 0 && (d->x_sh % 4) == 0 && (d->w_sb % 4) == 0 && (d->w_sh % 4) == 0, EVK_ERR_ARG,
@@ -459,19 +465,28 @@ extern "C" int evk_gconv_fwd(const evk_gconv_desc* d, evk_stream_t stream) {
 
 template <int TN, int TC, int WN, int WC, int WK, bool PRECISE>
 static int launch_w(GP& p, cudaStream_t st) {
+  constexpr int RK = (WK * 8 > 32) ? WK * 8 : 32;
+  constexpr size_t smem = (size_t)2 * RK * ((TN + 8) + (TC + 8)) * sizeof(float);
   const long long npos = (long long)p.J * p.P;
-  const int tiles = cdiv(p.N, TN) * cdiv(p.C, TC);
+  const int Cq = (p.C + 3) & ~3;
+  const int tiles = cdiv(p.N, TN) * cdiv((long long)p.Q * Cq, TC);
   // aim for >= ~4 waves of 148 SMs, but keep >= 256 positions per CTA
-  long long ctas_fixed = (long long)tiles * p.Z * p.Q;
+  long long ctas_fixed = (long long)tiles * p.Z;
   long long want = (148LL * 8 + ctas_fixed - 1) / ctas_fixed;
   long long rch = (npos + want - 1) / want;
   rch = ((rch + 31) / 32) * 32;
   if (rch < 256) rch = 256;
   p.rch = (int)rch;
-  dim3 grid(cdiv(npos, rch), tiles, p.Z * p.Q);
+  dim3 grid(cdiv(npos, rch), tiles, p.Z);
   if (grid.x == 0) return EVK_OK;
   EVK_REQUIRE(grid.y <= 65535 && grid.z <= 65535, EVK_ERR_ARG, "gconv_wgrad: grid too large");
-  gconv_w_kernel<TN, TC, WN, WC, WK, PRECISE><<<grid, NT, 0, st>>>(p);
+  auto kern = gconv_w_kernel<TN, TC, WN, WC, WK, PRECISE>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_set = true;
+  }
+  kern<<<grid, NT, smem, st>>>(p);
   return check_launch("gconv_w_kernel");
 }
 
@@ -479,7 +494,7 @@ extern "C" int evk_gconv_wgrad(const evk_gconv_desc* d, evk_stream_t stream) {
   GP p;
   int rc = fill_gp(d, p);
   if (rc) return rc;
-  EVK_REQUIRE(d->G <= 1, EVK_ERR_UNSUPPORTED, "gconv_wgrad: grouped convolutions use evk_conv_direct_wgrad");
+  EVK_REQUIRE(d->G <= 1, EVK_ERR_UNSUPPORTED, "gconv_wgrad: pass groups as the inner batch (H = groups), not G");
   EVK_REQUIRE((d->ldx % 4) == 0 && (d->ldy % 4) == 0, EVK_ERR_ARG,
               "gconv_wgrad: ldx, ldy must be multiples of 4 (ldx=%d ldy=%d)", d->ldx, d->ldy);
   EVK_REQUIRE(((uintptr_t)d->x % 16) == 0 && ((uintptr_t)d->y % 16) == 0, EVK_ERR_ARG, "gconv_wgrad: x/y must be 16-byte aligned");
@@ -487,14 +502,15 @@ extern "C" int evk_gconv_wgrad(const evk_gconv_desc* d, evk_stream_t stream) {
               "gconv_wgrad: batch strides must be multiples of 4");
   EVK_REQUIRE(d->y != nullptr && d->x != nullptr && d->w != nullptr, EVK_ERR_ARG, "gconv_wgrad: null tensor");
   cudaStream_t st = (cudaStream_t)stream;
-  const int mx = max(p.N, p.C), mnv = min(p.N, p.C);
+  const long long ncols = (long long)p.Q * ((p.C + 3) & ~3);
 #define EVK_W(...) (g_precise ? launch_w<__VA_ARGS__, true>(p, st) : launch_w<__VA_ARGS__, false>(p, st))
-  if (mnv <= 16) {
-    if (p.N <= 16 && p.C <= 16) return EVK_W(16, 16, 1, 1, 8);
-    if (p.N <= 16) return EVK_W(16, 64, 1, 4, 2);
-    return EVK_W(64, 16, 4, 1, 2);
+  if (p.N <= 16) {
+    if (ncols <= 16) return EVK_W(16, 16, 1, 1, 8);
+    return EVK_W(16, 64, 1, 4, 2);
   }
-  if (mx <= 32) return EVK_W(32, 32, 2, 2, 2);
+  if (ncols <= 16) return EVK_W(64, 16, 4, 1, 2);
+  if (p.N <= 32) return EVK_W(32, 64, 2, 4, 1);
+  if (p.N >= 128 && ncols >= 128) return EVK_W(128, 128, 2, 4, 1);
   return EVK_W(64, 64, 2, 4, 1);
 #undef EVK_W
 }

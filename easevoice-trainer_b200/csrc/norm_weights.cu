@@ -78,7 +78,7 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ x, int ldx, const
 // ---- weight-norm + pack ------------------------------------------------------------------
 // block per d0: w[d0][d1][q] = v * (g[d0] / ||v[d0]||);  PA[q][d0][d1], PB[q][d1][d0]
 __global__ void weight_pack_kernel(const float* __restrict__ v, const float* __restrict__ g, int D0, int D1, int Q,
-                                   float* __restrict__ pa, int lda, float* __restrict__ pb, int ldb) {
+                                   float* __restrict__ pa, int lda, int D0p, float* __restrict__ pb, int ldb, int D1p) {
   __shared__ float red[33];
   const int d0 = blockIdx.x;
   const long long n = (long long)D1 * Q;
@@ -93,12 +93,12 @@ __global__ void weight_pack_kernel(const float* __restrict__ v, const float* __r
   for (long long i = threadIdx.x; i < n; i += blockDim.x) {
     const int d1 = (int)(i / Q), q = (int)(i - (long long)d1 * Q);
     const float w = vr[i] * scale;
-    pa[((long long)q * D0 + d0) * lda + d1] = w;
-    if (pb) pb[((long long)q * D1 + d1) * ldb + d0] = w;
+    pa[((long long)q * D0p + d0) * lda + d1] = w;
+    if (pb) pb[((long long)q * D1p + d1) * ldb + d0] = w;
   }
 }
 
-__global__ void weight_pack_bwd_kernel(const float* __restrict__ dpa, int lda, const float* __restrict__ v,
+__global__ void weight_pack_bwd_kernel(const float* __restrict__ dpa, int lda, int D0p, const float* __restrict__ v,
                                        const float* __restrict__ g, int D0, int D1, int Q, float* __restrict__ dv,
                                        float* __restrict__ dg) {
   __shared__ float red[33];
@@ -109,7 +109,7 @@ __global__ void weight_pack_bwd_kernel(const float* __restrict__ dpa, int lda, c
   if (!g) {
     for (long long i = threadIdx.x; i < n; i += blockDim.x) {
       const int d1 = (int)(i / Q), q = (int)(i - (long long)d1 * Q);
-      dvr[i] = dpa[((long long)q * D0 + d0) * lda + d1];
+      dvr[i] = dpa[((long long)q * D0p + d0) * lda + d1];
     }
     return;
   }
@@ -118,7 +118,7 @@ __global__ void weight_pack_bwd_kernel(const float* __restrict__ dpa, int lda, c
     const int d1 = (int)(i / Q), q = (int)(i - (long long)d1 * Q);
     const float vv = vr[i];
     ss += vv * vv;
-    dot += dpa[((long long)q * D0 + d0) * lda + d1] * vv;
+    dot += dpa[((long long)q * D0p + d0) * lda + d1] * vv;
   }
   ss = block_sum(ss, red);
   dot = block_sum(dot, red);
@@ -127,7 +127,7 @@ __global__ void weight_pack_bwd_kernel(const float* __restrict__ dpa, int lda, c
   const float sc = gg / nrm, k = dot / ss;
   for (long long i = threadIdx.x; i < n; i += blockDim.x) {
     const int d1 = (int)(i / Q), q = (int)(i - (long long)d1 * Q);
-    dvr[i] = sc * (dpa[((long long)q * D0 + d0) * lda + d1] - vr[i] * k);
+    dvr[i] = sc * (dpa[((long long)q * D0p + d0) * lda + d1] - vr[i] * k);
   }
 }
 
@@ -186,15 +186,30 @@ extern "C" int evk_weight_pack(const float* v, const float* g, int32_t D0, int32
                                int32_t lda, float* pb, int32_t ldb, evk_stream_t stream) {
   EVK_REQUIRE(v && pa && D0 >= 1 && D1 >= 1 && Q >= 1 && lda >= D1 && (!pb || ldb >= D0), EVK_ERR_ARG,
               "weight_pack: bad arguments");
-  weight_pack_kernel<<<D0, 256, 0, ST>>>(v, g, D0, D1, Q, pa, lda, pb, ldb);
+  weight_pack_kernel<<<D0, 256, 0, ST>>>(v, g, D0, D1, Q, pa, lda, D0, pb, ldb, D1);
   return check_launch("weight_pack");
+}
+
+extern "C" int evk_weight_pack_p(const float* v, const float* g, int32_t D0, int32_t D1, int32_t Q, float* pa,
+                                 int32_t lda, int32_t D0p, float* pb, int32_t ldb, int32_t D1p, evk_stream_t stream) {
+  EVK_REQUIRE(v && pa && D0 >= 1 && D1 >= 1 && Q >= 1 && D0p >= D0 && D1p >= D1 && lda >= D1 && (!pb || ldb >= D0),
+              EVK_ERR_ARG, "weight_pack_p: bad arguments");
+  weight_pack_kernel<<<D0, 256, 0, ST>>>(v, g, D0, D1, Q, pa, lda, D0p, pb, ldb, D1p);
+  return check_launch("weight_pack_p");
 }
 
 extern "C" int evk_weight_pack_bwd(const float* dpa, int32_t lda, const float* v, const float* g, int32_t D0,
                                    int32_t D1, int32_t Q, float* dv, float* dg, evk_stream_t stream) {
   EVK_REQUIRE(dpa && v && dv && (!g || dg), EVK_ERR_ARG, "weight_pack_bwd: null tensor");
-  weight_pack_bwd_kernel<<<D0, 256, 0, ST>>>(dpa, lda, v, g, D0, D1, Q, dv, dg);
+  weight_pack_bwd_kernel<<<D0, 256, 0, ST>>>(dpa, lda, D0, v, g, D0, D1, Q, dv, dg);
   return check_launch("weight_pack_bwd");
+}
+
+extern "C" int evk_weight_pack_bwd_p(const float* dpa, int32_t lda, int32_t D0p, const float* v, const float* g,
+                                     int32_t D0, int32_t D1, int32_t Q, float* dv, float* dg, evk_stream_t stream) {
+  EVK_REQUIRE(dpa && v && dv && (!g || dg) && D0p >= D0, EVK_ERR_ARG, "weight_pack_bwd_p: bad arguments");
+  weight_pack_bwd_kernel<<<D0, 256, 0, ST>>>(dpa, lda, D0p, v, g, D0, D1, Q, dv, dg);
+  return check_launch("weight_pack_bwd_p");
 }
 
 extern "C" int evk_colsum(const float* x, int64_t rows, int32_t n, int32_t ld, float* out, int32_t accumulate,

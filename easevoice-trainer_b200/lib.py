@@ -15,7 +15,7 @@ class GconvDesc(ctypes.Structure):
     _fields_ = (
         [(n, ctypes.c_void_p) for n in ("x", "w", "y", "res", "bias", "in_len", "out_len")]
         + [(n, ctypes.c_int64) for n in ("x_sb", "x_sh", "w_sb", "w_sh", "w_sq", "y_sb", "y_sh", "r_sb", "r_sh")]
-        + [(n, ctypes.c_int32) for n in ("ldx", "ldw", "ldy", "ldr", "Z", "H", "C", "N", "Q", "G", "Tin", "J", "P",
+        + [(n, ctypes.c_int32) for n in ("ldx", "ldw", "ldy", "ldr", "b_sh", "Z", "H", "C", "N", "Q", "G", "Tin", "J", "P",
                                          "is_", "os_", "o0", "Tout", "act")]
         + [("slope", ctypes.c_float), ("off", ctypes.c_int32 * MAX_TAPS)]
     )

@@ -55,13 +55,23 @@ class ParamTree(nn.Module):
         return True
 
     # ---- packed-weight helpers (weight-norm folded into the packing pass) --------------------
-    def w(self, pfx, need_pb=True):
-        if self.has(pfx + ".weight_v"):
-            return ops.pack_weight(self.P(pfx + ".weight_v"), self.P(pfx + ".weight_g"), need_pb)
-        return ops.pack_weight(self.P(pfx + ".weight"), None, need_pb)
+    _frozen = False            # True: weights enter the graph as constants (no weight gradients are computed)
 
-    def b(self, pfx):
-        return self.P(pfx + ".bias") if self.has(pfx + ".bias") else None
+    def w(self, pfx, need_pb=True, pad0=0, pad1=0):
+        fz = (lambda t: t.detach()) if self._frozen else (lambda t: t)
+        if self.has(pfx + ".weight_v"):
+            return ops.pack_weight(fz(self.P(pfx + ".weight_v")), fz(self.P(pfx + ".weight_g")), need_pb, pad0, pad1)
+        return ops.pack_weight(fz(self.P(pfx + ".weight")), None, need_pb, pad0, pad1)
+
+    def b(self, pfx, pad=0):
+        if not self.has(pfx + ".bias"):
+            return None
+        b = self.P(pfx + ".bias")
+        if self._frozen:
+            b = b.detach()
+        if pad > b.shape[0]:
+            b = torch.nn.functional.pad(b, (0, pad - b.shape[0]))
+        return b
 
 
 def _kaiming_uniform_(t, fan_in, gen):
@@ -342,7 +352,9 @@ class SynthesizerTrn(ParamTree):
                 outs.append(h)
             x = ops.add3(outs[0], outs[1], outs[2], 1.0 / nk, 1.0 / nk, 1.0 / nk)
         x = ops.lrelu(x, 0.01)                             # F.leaky_relu default slope (models.py:467)
-        return ops.conv(x, self.w("dec.conv_post"), None, pad=3, act=ops.ACT_TANH)
+        # the single output channel is padded to 4 (zero weights) so that its gradients stay on the tensor-core kernels
+        y4 = ops.conv(x, self.w("dec.conv_post", pad0=4), None, pad=3, act=ops.ACT_TANH)
+        return ops.take_channels(y4, 1)
 
     # ---------------------------------------------------------------------------------------------
     def forward_cl(self, ssl, spec, lengths, text, text_lengths, noise=None, ids_slice=None):
@@ -451,38 +463,49 @@ class MultiPeriodDiscriminator(ParamTree):
                     v = self.P(name[:-1] + "v")
                     p.copy_(v.flatten(1).norm(dim=1).view(p.shape))
 
-    def _disc_s(self, x):
+    # 1-channel tensors (the waveform, the logits) are carried with 4 channels (3 of them zero, zero weights) so that
+    # every layer -- including its data/weight gradients -- runs on the 16-byte-tiled tensor-core kernels.
+    def _disc_s(self, x4):
         fmap = []
+        x = x4
         for i, (co, cig, k, s, p, g) in enumerate(self.S_CFG):
             n = f"discriminators.0.convs.{i}"
-            x = ops.conv(x, self.w(n), self.b(n), stride=s, pad=p, groups=g, act=ops.ACT_LRELU, slope=LRELU_SLOPE)
+            x = ops.conv(x, self.w(n, pad1=4 if i == 0 else 0), self.b(n), stride=s, pad=p, groups=g, act=ops.ACT_LRELU,
+                         slope=LRELU_SLOPE)
             fmap.append(x)
         n = "discriminators.0.conv_post"
-        x = ops.conv(x, self.w(n), self.b(n), pad=1)
+        x = ops.take_channels(ops.conv(x, self.w(n, pad0=4), self.b(n, pad=4), pad=1), 1)
         fmap.append(x)
         return x, fmap
 
     def _disc_p(self, d, x, period):
         B, T, _ = x.shape
         Tp = (T + period - 1) // period * period
-        x = ops.reflect_pad_right(x, Tp)
+        x = ops.pad_channels(ops.reflect_pad_right(x, Tp), 4)
         fmap = []
         for i, s in enumerate((3, 3, 3, 3, 1)):
             n = f"discriminators.{d}.convs.{i}"
-            x = ops.conv(x, self.w(n), self.b(n), stride=s, pad=2, P=period, act=ops.ACT_LRELU, slope=LRELU_SLOPE)
+            x = ops.conv(x, self.w(n, pad1=4 if i == 0 else 0), self.b(n), stride=s, pad=2, P=period, act=ops.ACT_LRELU,
+                         slope=LRELU_SLOPE)
             fmap.append(x)
         n = f"discriminators.{d}.conv_post"
-        x = ops.conv(x, self.w(n), self.b(n), pad=1, P=period)
+        x = ops.take_channels(ops.conv(x, self.w(n, pad0=4), self.b(n, pad=4), pad=1, P=period), 1)
         fmap.append(x)
         return x, fmap
 
-    def forward_cl(self, y, y_hat):
+    def forward_cl(self, y, y_hat, weights_need_grad=True):
         """y, y_hat [B, T, 1] -> per discriminator (logits [2B, J, 1], fmaps list of [2B, J, C]); rows [:B] are the
-        real half, rows [B:] the generated half (one 2B pass instead of the reference's two sequential passes)."""
-        x = ops.cat_batch(y, y_hat)
-        outs = [self._disc_s(x)]
-        for d, period in enumerate(PERIODS, start=1):
-            outs.append(self._disc_p(d, x, period))
+        real half, rows [B:] the generated half (one 2B pass instead of the reference's two sequential passes).
+        weights_need_grad=False (generator step): D weights are constants, so no D weight gradients are computed --
+        the reference computes and then discards them (sovits.py:503,511-520)."""
+        self._frozen = not weights_need_grad
+        try:
+            x = ops.cat_batch(y, y_hat)
+            outs = [self._disc_s(ops.pad_channels(x, 4))]
+            for d, period in enumerate(PERIODS, start=1):
+                outs.append(self._disc_p(d, x, period))
+        finally:
+            self._frozen = False
         return outs
 
     def forward(self, y, y_hat):

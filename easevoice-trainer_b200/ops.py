@@ -192,20 +192,22 @@ def _pad4(n):
 
 class _PackFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, v, g, need_pb):
+    def forward(ctx, v, g, need_pb, pad0, pad1):
         D0 = v.shape[0]
         D1 = v.shape[1]
         Q = v.numel() // (D0 * D1)
-        lda, ldb = _pad4(D1), _pad4(D0)
-        pa = (torch.zeros if lda != D1 else torch.empty)((Q, D0, lda), device=v.device, dtype=torch.float32)
+        D0p, D1p = max(D0, pad0), max(D1, pad1)          # channel dims < 4 are zero-padded so every conv is 16-byte tileable
+        lda, ldb = _pad4(D1p), _pad4(D0p)
+        exact = (D0p == D0 and D1p == D1)
+        pa = (torch.zeros if (lda != D1 or not exact) else torch.empty)((Q, D0p, lda), device=v.device, dtype=torch.float32)
         pb = None
         if need_pb:
-            pb = (torch.zeros if ldb != D0 else torch.empty)((Q, D1, ldb), device=v.device, dtype=torch.float32)
+            pb = (torch.zeros if (ldb != D0 or not exact) else torch.empty)((Q, D1p, ldb), device=v.device, dtype=torch.float32)
         vc = v.contiguous()
         gc = g.contiguous() if g is not None else None
-        _call("evk_weight_pack", _p(vc), _p(gc), D0, D1, Q, _p(pa), lda, _p(pb), ldb)
+        _call("evk_weight_pack_p", _p(vc), _p(gc), D0, D1, Q, _p(pa), lda, D0p, _p(pb), ldb, D1p)
         ctx.save_for_backward(vc, gc)
-        ctx.dims = (D0, D1, Q, lda, tuple(v.shape), tuple(g.shape) if g is not None else None)
+        ctx.dims = (D0, D1, Q, lda, D0p, tuple(v.shape), tuple(g.shape) if g is not None else None)
         if pb is None:
             pb = torch.empty(0, device=v.device)
         ctx.mark_non_differentiable(pb)
@@ -214,19 +216,19 @@ class _PackFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dpa, _dpb):
         v, g = ctx.saved_tensors
-        D0, D1, Q, lda, vshape, gshape = ctx.dims
+        D0, D1, Q, lda, D0p, vshape, gshape = ctx.dims
         dpa = dpa.contiguous()
         dv = torch.empty(vshape, device=v.device, dtype=torch.float32)
         dg = torch.empty(gshape, device=v.device, dtype=torch.float32) if g is not None else None
-        _call("evk_weight_pack_bwd", _p(dpa), lda, _p(v), _p(g), D0, D1, Q, _p(dv), _p(dg))
-        return dv, dg, None
+        _call("evk_weight_pack_bwd_p", _p(dpa), lda, D0p, _p(v), _p(g), D0, D1, Q, _p(dv), _p(dg))
+        return dv, dg, None, None, None
 
 
-def pack_weight(v, g=None, need_pb=True):
-    """weight-norm (if g) + pack.  v: torch-layout weight [D0, D1, Q(,1)]."""
-    pa, pb = _PackFn.apply(v, g, need_pb)
-    D0, D1 = v.shape[0], v.shape[1]
-    return PackedW(pa, pb if need_pb else None, D0, D1, v.numel() // (D0 * D1))
+def pack_weight(v, g=None, need_pb=True, pad0=0, pad1=0):
+    """weight-norm (if g) + pack.  v: torch-layout weight [D0, D1, Q(,1)]; pad0/pad1 zero-pad the channel dims."""
+    pa, pb = _PackFn.apply(v, g, need_pb, pad0, pad1)
+    D0, D1 = max(v.shape[0], pad0), max(v.shape[1], pad1)
+    return PackedW(pa, pb if need_pb else None, D0, D1, v.numel() // (v.shape[0] * v.shape[1]))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -237,24 +239,28 @@ def _conv_out_len(Tin, Q, stride, pad, dil):
 
 
 def _fwd_like(x, Tin, w, wq0, wqstep, nq, ldw, w_sq, C, N, y, *, J, P, is_, os_, o0, Tout, off, bias=None, res=None,
-              act=0, slope=0.0, in_len=None, out_len=None, G=1):
-    """one launch of the generalised conv (tensor-core kernel when alignment allows, else direct)."""
+              act=0, slope=0.0, in_len=None, out_len=None, H=1, x_sh=0, w_sh=0, y_sh=0, b_sh=0):
+    """one launch of the generalised conv on the tensor-core kernel.  Grouped convs pass H = groups with the per-group
+    channel offsets x_sh / w_sh / y_sh / b_sh (C, N are then per-group sizes)."""
     B = x.shape[0]
     _, _, ldx = _rows(x)
     _, _, ldy = _rows(y)
     ldr = _rows(res)[2] if res is not None else 0
     wbase = w.data_ptr() + 4 * wq0 * w_sq
     d = _desc(x=x, w=None, y=y, res=res, bias=bias, in_len=in_len, out_len=out_len,
-              x_sb=Tin * P * ldx, x_sh=0, w_sb=0, w_sh=0, w_sq=wqstep * w_sq, y_sb=Tout * P * ldy, y_sh=0,
-              r_sb=Tout * P * ldr, r_sh=0, ldx=ldx, ldw=ldw, ldy=ldy, ldr=ldr, Z=B, H=1, C=C, N=N, Q=nq, G=G,
-              Tin=Tin, J=J, P=P, is_=is_, os_=os_, o0=o0, Tout=Tout, act=act, slope=float(slope), off=off)
+              x_sb=Tin * P * ldx, x_sh=x_sh, w_sb=0, w_sh=w_sh, w_sq=wqstep * w_sq, y_sb=Tout * P * ldy, y_sh=y_sh,
+              r_sb=Tout * P * ldr, r_sh=y_sh, ldx=ldx, ldw=ldw, ldy=ldy, ldr=ldr, b_sh=b_sh, Z=B * H, H=H, C=C, N=N, Q=nq,
+              G=1, Tin=Tin, J=J, P=P, is_=is_, os_=os_, o0=o0, Tout=Tout, act=act, slope=float(slope), off=off)
     d.w = wbase
-    mma = G == 1 and _aligned(x, ldx) and ldw % 4 == 0 and (wbase % 16 == 0) and (d.w_sq % 4 == 0)
+    mma = _aligned(x, ldx) and ldw % 4 == 0 and (wbase % 16 == 0) and (d.w_sq % 4 == 0) and x_sh % 4 == 0 and w_sh % 4 == 0
+    if not mma:
+        assert H == 1, "grouped convs need 16-byte aligned group slices"
     _run_desc("evk_gconv_fwd" if mma else "evk_conv_direct_fwd", d)
 
 
-def _dgrad_phases(dy, Jy, pb, ldb, C, N, Q, dx, Tin, P, stride, pad, dil):
-    """dX[u] = sum_q sum_n dY[(u+pad-q*dil)/stride][n] * PB[q][c][n] as one F launch per stride phase."""
+def _dgrad_phases(dy, Jy, pb, ldb, C, N, Q, dx, Tin, P, stride, pad, dil, H=1):
+    """dX[u] = sum_q sum_n dY[(u+pad-q*dil)/stride][n] * PB[q][c][n] as one F launch per stride phase.
+    C, N are per-group sizes when H (= groups) > 1; PB is [Q][C][ldb] with the group's n-columns at offset h*N."""
     assert stride == 1 or dil == 1, "strided convs must have dilation 1"
     w_sq = pb.shape[1] * ldb
     for rho in range(stride):
@@ -270,11 +276,11 @@ def _dgrad_phases(dy, Jy, pb, ldb, C, N, Q, dx, Tin, P, stride, pad, dil):
         else:
             off = [(u0 + pad - q) // stride for q in taps]
         _fwd_like(dy, Jy, pb, taps[0], stride, len(taps), ldb, w_sq, N, C, dx, J=Ju, P=P, is_=1, os_=stride, o0=u0,
-                  Tout=Tin, off=off)
+                  Tout=Tin, off=off, H=H, x_sh=N if H > 1 else 0, w_sh=N if H > 1 else 0, y_sh=C if H > 1 else 0)
 
 
 class _ConvFn(torch.autograd.Function):
-    """y = act(conv(x, W) + bias + res) * mask ; W packed (pa = [Q][N][C/G], pb = [Q][C][N])."""
+    """y = act(conv(x, W) + bias + res) * mask ; W packed (pa = [Q][N][C/G], pb = [Q][C/G][N])."""
 
     @staticmethod
     def forward(ctx, x, pa, pb, bias, res, cfg):
@@ -284,13 +290,15 @@ class _ConvFn(torch.autograd.Function):
         assert R % P == 0
         Tin = R // P
         N, lda = pa.shape[1], pa.shape[2]
+        Cg, Ng = C // G, N // G
         J = _conv_out_len(Tin, Q, stride, pad, dil)
         y = torch.empty((B, J * P, N), device=x.device, dtype=torch.float32)
         if res is not None:
             res = _cl(res)
         off = [q * dil - pad for q in range(Q)]
-        _fwd_like(x, Tin, pa, 0, 1, Q, lda, N * lda, C, N, y, J=J, P=P, is_=stride, os_=1, o0=0, Tout=J, off=off,
-                  bias=bias, res=res, act=act, slope=slope, in_len=in_len, out_len=out_len, G=G)
+        gk = dict(H=G, x_sh=Cg, w_sh=Ng * lda, y_sh=Ng, b_sh=Ng) if G > 1 else {}
+        _fwd_like(x, Tin, pa, 0, 1, Q, lda, N * lda, Cg, Ng, y, J=J, P=P, is_=stride, os_=1, o0=0, Tout=J, off=off,
+                  bias=bias, res=res, act=act, slope=slope, in_len=in_len, out_len=out_len, **gk)
         ctx.cfg = cfg
         ctx.dims = (B, Tin, C, N, J, lda)
         ctx.has = (bias is not None, res is not None)
@@ -303,6 +311,7 @@ class _ConvFn(torch.autograd.Function):
         B, Tin, C, N, J, lda = ctx.dims
         x, pa, pb, y = ctx.saved_tensors
         has_bias, has_res = ctx.has
+        Cg, Ng = C // G, N // G
         dy = dy.contiguous()
         if act:
             dpre = torch.empty_like(dy)
@@ -314,18 +323,20 @@ class _ConvFn(torch.autograd.Function):
             _call("evk_rowmask", _p(dy), N, _p(dm), N, B, J * P, N, _p(out_len))   # P == 1 whenever masks are used
             dy = dm
         dx = dpa = dbias = dres = None
+        offs = [q * dil - pad for q in range(Q)]
         if ctx.needs_input_grad[0]:
             dx = torch.empty((B, Tin * P, C), device=dy.device, dtype=torch.float32)
-            use_mma = G == 1 and pb is not None and pb.numel() > 0 and _aligned(dy, N) and pb.shape[2] % 4 == 0
+            use_mma = (pb is not None and pb.numel() > 0 and _aligned(dy, N) and pb.shape[2] % 4 == 0
+                       and (G == 1 or (Ng % 4 == 0 and Cg % 4 == 0)))
             if use_mma:
                 if Q < stride:
                     dx.zero_()
-                _dgrad_phases(dy, J, pb, pb.shape[2], C, N, Q, dx, Tin, P, stride, pad, dil)
+                _dgrad_phases(dy, J, pb, pb.shape[2], Cg, Ng, Q, dx, Tin, P, stride, pad, dil, H=G)
             else:
                 d = _desc(x=dx, w=pa, y=dy, res=None, bias=None, in_len=None, out_len=None,
                           x_sb=Tin * P * C, x_sh=0, w_sb=0, w_sh=0, w_sq=N * lda, y_sb=J * P * N, y_sh=0, r_sb=0, r_sh=0,
-                          ldx=C, ldw=lda, ldy=N, ldr=0, Z=B, H=1, C=C, N=N, Q=Q, G=G, Tin=Tin, J=J, P=P, is_=stride,
-                          os_=1, o0=0, Tout=J, act=0, slope=0.0, off=[q * dil - pad for q in range(Q)])
+                          ldx=C, ldw=lda, ldy=N, ldr=0, b_sh=0, Z=B, H=1, C=C, N=N, Q=Q, G=G, Tin=Tin, J=J, P=P, is_=stride,
+                          os_=1, o0=0, Tout=J, act=0, slope=0.0, off=offs)
                 _run_desc("evk_conv_direct_dgrad", d)
             if in_len is not None:
                 dxm = torch.empty_like(dx)
@@ -334,12 +345,20 @@ class _ConvFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dpa = torch.zeros_like(pa)
             _, _, ldx = _rows(x)
-            d = _desc(x=x, w=dpa, y=dy, res=None, bias=None, in_len=in_len, out_len=None,
-                      x_sb=Tin * P * ldx, x_sh=0, w_sb=0, w_sh=0, w_sq=N * lda, y_sb=J * P * N, y_sh=0, r_sb=0, r_sh=0,
-                      ldx=ldx, ldw=lda, ldy=N, ldr=0, Z=B, H=1, C=C, N=N, Q=Q, G=G, Tin=Tin, J=J, P=P, is_=stride,
-                      os_=1, o0=0, Tout=J, act=0, slope=0.0, off=[q * dil - pad for q in range(Q)])
-            mma = G == 1 and _aligned(x, ldx) and _aligned(dy, N)
-            _run_desc("evk_gconv_wgrad" if mma else "evk_conv_direct_wgrad", d)
+            mma = _aligned(x, ldx) and _aligned(dy, N) and (G == 1 or (Cg % 4 == 0 and Ng % 4 == 0))
+            if mma:
+                d = _desc(x=x, w=dpa, y=dy, res=None, bias=None, in_len=in_len, out_len=None,
+                          x_sb=Tin * P * ldx, x_sh=Cg if G > 1 else 0, w_sb=0, w_sh=Ng * lda if G > 1 else 0, w_sq=N * lda,
+                          y_sb=J * P * N, y_sh=Ng if G > 1 else 0, r_sb=0, r_sh=0, ldx=ldx, ldw=lda, ldy=N, ldr=0, b_sh=0,
+                          Z=B * G, H=G, C=Cg, N=Ng, Q=Q, G=1, Tin=Tin, J=J, P=P, is_=stride, os_=1, o0=0, Tout=J, act=0,
+                          slope=0.0, off=offs)
+                _run_desc("evk_gconv_wgrad", d)
+            else:
+                d = _desc(x=x, w=dpa, y=dy, res=None, bias=None, in_len=in_len, out_len=None,
+                          x_sb=Tin * P * ldx, x_sh=0, w_sb=0, w_sh=0, w_sq=N * lda, y_sb=J * P * N, y_sh=0, r_sb=0, r_sh=0,
+                          ldx=ldx, ldw=lda, ldy=N, ldr=0, b_sh=0, Z=B, H=1, C=C, N=N, Q=Q, G=G, Tin=Tin, J=J, P=P,
+                          is_=stride, os_=1, o0=0, Tout=J, act=0, slope=0.0, off=offs)
+                _run_desc("evk_conv_direct_wgrad", d)
         if has_bias and ctx.needs_input_grad[3]:
             dbias = torch.empty(N, device=dy.device, dtype=torch.float32)
             _call("evk_colsum", _p(dy), B * J * P, N, N, _p(dbias), 0)
@@ -407,7 +426,7 @@ class _ConvTFn(torch.autograd.Function):
             # dPA[q][ci][co] += sum_t X[t][ci] * dY[t*stride - pad + q][co]: "x" role = dY (shifted), "y" role = X
             d = _desc(x=dy, w=dpa, y=x, res=None, bias=None, in_len=None, out_len=None,
                       x_sb=Tout * Cout, x_sh=0, w_sb=0, w_sh=0, w_sq=Cin * lda, y_sb=Tin * ldx, y_sh=0, r_sb=0, r_sh=0,
-                      ldx=Cout, ldw=lda, ldy=ldx, ldr=0, Z=B, H=1, C=Cout, N=Cin, Q=Q, G=1, Tin=Tout, J=Tin, P=1,
+                      ldx=Cout, ldw=lda, ldy=ldx, ldr=0, b_sh=0, Z=B, H=1, C=Cout, N=Cin, Q=Q, G=1, Tin=Tout, J=Tin, P=1,
                       is_=stride, os_=1, o0=0, Tout=Tin, act=0, slope=0.0, off=off)
             mma = _aligned(dy, Cout) and _aligned(x, ldx)
             _run_desc("evk_gconv_wgrad" if mma else "evk_conv_direct_wgrad", d)
@@ -669,6 +688,63 @@ class _CatBatchFn(torch.autograd.Function):
 
 def cat_batch(a, b):
     return _CatBatchFn.apply(a, b)
+
+
+class _PadChFn(torch.autograd.Function):
+    """[.., C] -> [.., Cp] zero-padded channels (1-channel waveforms are padded to 4 so that the first discriminator
+    layers run on the 16-byte-tiled tensor-core kernels)."""
+
+    @staticmethod
+    def forward(ctx, x, Cp):
+        x = _cl(x)
+        rows, C, ld = _rows(x)
+        y = torch.zeros((*x.shape[:-1], Cp), device=x.device, dtype=torch.float32)
+        _call("evk_axpby", _p(x), ld, ctypes.c_float(1.0), None, 0, ctypes.c_float(0.0), None, 0, ctypes.c_float(0.0), _p(y),
+              Cp, rows, C, None, 0)
+        ctx.k = (C, Cp)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        C, Cp = ctx.k
+        dy = dy.contiguous()
+        rows = dy.numel() // Cp
+        dx = torch.empty((*dy.shape[:-1], C), device=dy.device, dtype=torch.float32)
+        _call("evk_axpby", _p(dy), Cp, ctypes.c_float(1.0), None, 0, ctypes.c_float(0.0), None, 0, ctypes.c_float(0.0),
+              _p(dx), C, rows, C, None, 0)
+        return dx, None
+
+
+def pad_channels(x, Cp):
+    return x if x.shape[-1] >= Cp else _PadChFn.apply(x, Cp)
+
+
+class _TakeChFn(torch.autograd.Function):
+    """contiguous copy of the first C channels (inverse of pad_channels)."""
+
+    @staticmethod
+    def forward(ctx, x, C):
+        x = _cl(x)
+        rows, Cp, ld = _rows(x)
+        y = torch.empty((*x.shape[:-1], C), device=x.device, dtype=torch.float32)
+        _call("evk_axpby", _p(x), ld, ctypes.c_float(1.0), None, 0, ctypes.c_float(0.0), None, 0, ctypes.c_float(0.0), _p(y),
+              C, rows, C, None, 0)
+        ctx.k = (C, Cp)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        C, Cp = ctx.k
+        dy = dy.contiguous()
+        rows = dy.numel() // C
+        dx = torch.zeros((*dy.shape[:-1], Cp), device=dy.device, dtype=torch.float32)
+        _call("evk_axpby", _p(dy), C, ctypes.c_float(1.0), None, 0, ctypes.c_float(0.0), None, 0, ctypes.c_float(0.0),
+              _p(dx), Cp, rows, C, None, 0)
+        return dx, None
+
+
+def take_channels(x, C):
+    return x if x.shape[-1] == C else _TakeChFn.apply(x, C)
 
 
 class _ReparamFn(torch.autograd.Function):
@@ -937,7 +1013,7 @@ def _transpose_cl(x, ldT):
 
 def _bgemm(fn, x, x_sb, x_sh, ldx, w, w_sb, w_sh, ldw, y, y_sb, y_sh, ldy, Z, H, C, N, rows):
     d = _desc(x=x, w=w, y=y, res=None, bias=None, in_len=None, out_len=None, x_sb=x_sb, x_sh=x_sh, w_sb=w_sb, w_sh=w_sh,
-              w_sq=0, y_sb=y_sb, y_sh=y_sh, r_sb=0, r_sh=0, ldx=ldx, ldw=ldw, ldy=ldy, ldr=0, Z=Z, H=H, C=C, N=N, Q=1,
+              w_sq=0, y_sb=y_sb, y_sh=y_sh, r_sb=0, r_sh=0, ldx=ldx, ldw=ldw, ldy=ldy, ldr=0, b_sh=0, Z=Z, H=H, C=C, N=N, Q=1,
               G=1, Tin=rows, J=rows, P=1, is_=1, os_=1, o0=0, Tout=rows, act=0, slope=0.0, off=[0])
     _run_desc(fn, d)
 

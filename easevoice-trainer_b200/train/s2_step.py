@@ -173,7 +173,7 @@ class S2Step:
 
     def g_loss(self, r):
         B = r["y"].shape[0]
-        outs = self.net_d.forward_cl(r["y"], r["y_hat"])                           # sovits.py:511
+        outs = self.net_d.forward_cl(r["y"], r["y_hat"], weights_need_grad=False)  # sovits.py:511
         loss_mel = ops.mean_abs_diff(r["y_hat_mel"], r["y_mel"]) * self.t["c_mel"]
         loss_kl = ops.kl_loss(r["z_p"], r["logs_q"], r["m_p"], r["logs_p"], r["lengths"]) * self.t["c_kl"]
         loss_fm, loss_gen = 0, 0

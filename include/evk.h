@@ -52,6 +52,7 @@ typedef struct evk_gconv_desc {
   const int32_t* in_len; const int32_t* out_len;
   int64_t x_sb, x_sh, w_sb, w_sh, w_sq, y_sb, y_sh, r_sb, r_sh;
   int32_t ldx, ldw, ldy, ldr;
+  int32_t b_sh;          /* bias offset per inner-batch index h (grouped convs run as H = groups) */
   int32_t Z, H;          /* batch count and inner (head) count: b = z / H, h = z % H */
   int32_t C, N, Q, G;    /* in-channels, out-channels, taps, groups (G>1: direct kernels only) */
   int32_t Tin, J, P;     /* input positions per batch, output positions computed, inner width */
@@ -85,6 +86,12 @@ int evk_colsum(const float* x, int64_t rows, int32_t n, int32_t ld, float* out, 
  * ------------------------------------------------------------------------------------------ */
 int evk_weight_pack(const float* v, const float* g, int32_t D0, int32_t D1, int32_t Q, float* pa, int32_t lda,
                     float* pb, int32_t ldb, evk_stream_t stream);
+/* Same, with the channel dims zero-padded to D0p x D1p rows/cols (PA is [Q][D0p][lda], PB [Q][D1p][ldb], both
+ * pre-zeroed by the caller): 1-channel layers are padded to 4 so they run on the tensor-core kernels. */
+int evk_weight_pack_p(const float* v, const float* g, int32_t D0, int32_t D1, int32_t Q, float* pa, int32_t lda,
+                      int32_t D0p, float* pb, int32_t ldb, int32_t D1p, evk_stream_t stream);
+int evk_weight_pack_bwd_p(const float* dpa, int32_t lda, int32_t D0p, const float* v, const float* g, int32_t D0,
+                          int32_t D1, int32_t Q, float* dv, float* dg, evk_stream_t stream);
 /* given dPA (gradient in PA layout) -> dv [D0][D1][Q] (written), dg [D0] (written) (g may be NULL) */
 int evk_weight_pack_bwd(const float* dpa, int32_t lda, const float* v, const float* g, int32_t D0, int32_t D1,
                         int32_t Q, float* dv, float* dg, evk_stream_t stream);
