@@ -353,7 +353,9 @@ __global__ void __launch_bounds__(NT) gconv_w_kernel(const __grid_constant__ GP 
 // ============================================================================================
 // host side
 // ============================================================================================
-static int g_precise = 0;
+int g_precise = 0;          // 3xTF32 products on the mma.sync kernels (parity tests)
+int g_backend_tc = 1;       // use the tcgen05/TMEM kernel for eligible (stride-1) launches
+int gconv_tc_try(const evk_gconv_desc* d, cudaStream_t st);
 
 static int fill_gp(const evk_gconv_desc* d, GP& p) {
   EVK_REQUIRE(d != nullptr, EVK_ERR_ARG, "gconv: null descriptor");
@@ -433,6 +435,7 @@ static int launch_f(GP& p, cudaStream_t st) {
 using namespace evk;
 
 extern "C" int evk_set_precise(int32_t on) { g_precise = on ? 1 : 0; return EVK_OK; }
+extern "C" int evk_set_backend(int32_t tcgen05) { g_backend_tc = tcgen05 ? 1 : 0; return EVK_OK; }
 
 extern "C" int evk_gconv_fwd(const evk_gconv_desc* d, evk_stream_t stream) {
   GP p;
@@ -442,6 +445,10 @@ extern "C" int evk_gconv_fwd(const evk_gconv_desc* d, evk_stream_t stream) {
   if (rc) return rc;
   EVK_REQUIRE(d->y != nullptr && d->x != nullptr && d->w != nullptr, EVK_ERR_ARG, "gconv_fwd: null tensor");
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_backend_tc && !g_precise && (d->ldx % 4) == 0) {
+    rc = gconv_tc_try(d, st);
+    if (rc <= 0) return rc;
+  }
   // pick the N tile with the least padding (prefer wide)
   const int N = p.N;
   auto waste = [&](int bn) { return (long long)cdiv(N, bn) * bn; };

@@ -4,6 +4,8 @@
 
 namespace evk {
 
+extern int g_precise;
+
 // one warp per row; C <= 32*MAXV
 constexpr int LN_MAXV = 32;   // up to 1024 channels
 
@@ -77,8 +79,11 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ x, int ldx, const
 
 // ---- weight-norm + pack ------------------------------------------------------------------
 // block per d0: w[d0][d1][q] = v * (g[d0] / ||v[d0]||);  PA[q][d0][d1], PB[q][d1][d0]
+// round_tf32: weights are rounded to TF32 (round-to-nearest) here, once, so the tensor-core kernels can stage them
+// with cp.async and still get rounded (not truncated) operands.
 __global__ void weight_pack_kernel(const float* __restrict__ v, const float* __restrict__ g, int D0, int D1, int Q,
-                                   float* __restrict__ pa, int lda, int D0p, float* __restrict__ pb, int ldb, int D1p) {
+                                   float* __restrict__ pa, int lda, int D0p, float* __restrict__ pb, int ldb, int D1p,
+                                   int round_tf32) {
   __shared__ float red[33];
   const int d0 = blockIdx.x;
   const long long n = (long long)D1 * Q;
@@ -92,7 +97,8 @@ __global__ void weight_pack_kernel(const float* __restrict__ v, const float* __r
   }
   for (long long i = threadIdx.x; i < n; i += blockDim.x) {
     const int d1 = (int)(i / Q), q = (int)(i - (long long)d1 * Q);
-    const float w = vr[i] * scale;
+    float w = vr[i] * scale;
+    if (round_tf32) w = __uint_as_float(f2tf32(w));
     pa[((long long)q * D0p + d0) * lda + d1] = w;
     if (pb) pb[((long long)q * D1p + d1) * ldb + d0] = w;
   }
@@ -186,7 +192,7 @@ extern "C" int evk_weight_pack(const float* v, const float* g, int32_t D0, int32
                                int32_t lda, float* pb, int32_t ldb, evk_stream_t stream) {
   EVK_REQUIRE(v && pa && D0 >= 1 && D1 >= 1 && Q >= 1 && lda >= D1 && (!pb || ldb >= D0), EVK_ERR_ARG,
               "weight_pack: bad arguments");
-  weight_pack_kernel<<<D0, 256, 0, ST>>>(v, g, D0, D1, Q, pa, lda, D0, pb, ldb, D1);
+  weight_pack_kernel<<<D0, 256, 0, ST>>>(v, g, D0, D1, Q, pa, lda, D0, pb, ldb, D1, !g_precise);
   return check_launch("weight_pack");
 }
 
@@ -194,7 +200,7 @@ extern "C" int evk_weight_pack_p(const float* v, const float* g, int32_t D0, int
                                  int32_t lda, int32_t D0p, float* pb, int32_t ldb, int32_t D1p, evk_stream_t stream) {
   EVK_REQUIRE(v && pa && D0 >= 1 && D1 >= 1 && Q >= 1 && D0p >= D0 && D1p >= D1 && lda >= D1 && (!pb || ldb >= D0),
               EVK_ERR_ARG, "weight_pack_p: bad arguments");
-  weight_pack_kernel<<<D0, 256, 0, ST>>>(v, g, D0, D1, Q, pa, lda, D0p, pb, ldb, D1p);
+  weight_pack_kernel<<<D0, 256, 0, ST>>>(v, g, D0, D1, Q, pa, lda, D0p, pb, ldb, D1p, !g_precise);
   return check_launch("weight_pack_p");
 }
 

@@ -66,6 +66,8 @@ int evk_gconv_fwd(const evk_gconv_desc* d, evk_stream_t stream);
 /* 0 (default): one TF32 product per MAC.  1: 3xTF32 error-compensated products (~fp32 accuracy, 3x tensor work);
  * the parity tests use it to separate indexing errors from TF32 operand rounding. Process-wide. */
 int evk_set_precise(int32_t on);
+/* 1 (default): stride-1 launches run on the tcgen05/TMEM kernel (gconv_tc.cu); 0: mma.sync kernels only. */
+int evk_set_backend(int32_t tcgen05);
 /* Weight gradient of the same operator:  W[z][q][n][c] += sum_{j,w} Yg[z][orow][n] * X[z][irow][c]
  * (d->y is read as the output gradient, d->w is accumulated with atomics; when w_sb == w_sh == 0 the
  * sum also runs over z).  Replaces autograd's conv weight-gradient kernels for the call sites above. */
