@@ -261,22 +261,34 @@ def _fwd_like(x, Tin, w, wq0, wqstep, nq, ldw, w_sq, C, N, y, *, J, P, is_, os_,
 def _dgrad_phases(dy, Jy, pb, ldb, C, N, Q, dx, Tin, P, stride, pad, dil, H=1):
     """dX[u] = sum_q sum_n dY[(u+pad-q*dil)/stride][n] * PB[q][c][n] as one F launch per stride phase.
     C, N are per-group sizes when H (= groups) > 1; PB is [Q][C][ldb] with the group's n-columns at offset h*N."""
-    assert stride == 1 or dil == 1, "strided convs must have dilation 1"
     w_sq = pb.shape[1] * ldb
+    for u0, Ju, q0, nq, off in dgrad_phase_plan(Q, stride, pad, dil, Tin):
+        _fwd_like(dy, Jy, pb, q0, stride, nq, ldb, w_sq, N, C, dx, J=Ju, P=P, is_=1, os_=stride, o0=u0, Tout=Tin, off=off,
+                  H=H, x_sh=N if H > 1 else 0, w_sh=N if H > 1 else 0, y_sh=C if H > 1 else 0)
+
+
+def dgrad_phase_plan(Q, stride, pad, dil, Tin):
+    """Polyphase decomposition of a conv's data gradient (also of ConvTranspose1d's forward).
+
+    dX[u] = sum_q dY[(u + pad - q*dil)/stride] W[q] over the taps for which the division is exact.  For every residue
+    rho of (u + pad) mod stride this yields a stride-1 tap-sum over dY writing every stride-th u:
+        -> list of (u0, Ju, q0, nq, off):  u = u0 + stride*jj (jj < Ju) uses taps q0, q0+stride, ... (nq of them) and
+           reads dY[jj + off[k]].
+    """
+    assert stride == 1 or dil == 1, "strided convs must have dilation 1"
+    plan = []
     for rho in range(stride):
         taps = list(range(rho, Q, stride))
         u0 = (rho - pad) % stride
-        if u0 >= Tin:
+        if u0 >= Tin or not taps:
             continue
         Ju = (Tin - u0 + stride - 1) // stride
-        if not taps:
-            continue
         if stride == 1:
             off = [pad - q * dil for q in taps]
         else:
             off = [(u0 + pad - q) // stride for q in taps]
-        _fwd_like(dy, Jy, pb, taps[0], stride, len(taps), ldb, w_sq, N, C, dx, J=Ju, P=P, is_=1, os_=stride, o0=u0,
-                  Tout=Tin, off=off, H=H, x_sh=N if H > 1 else 0, w_sh=N if H > 1 else 0, y_sh=C if H > 1 else 0)
+        plan.append((u0, Ju, taps[0], len(taps), off))
+    return plan
 
 
 class _ConvFn(torch.autograd.Function):
@@ -393,15 +405,9 @@ class _ConvTFn(torch.autograd.Function):
         Tout = (Tin - 1) * stride - 2 * pad + Q
         y = (torch.zeros if Q < stride else torch.empty)((B, Tout, Cout), device=x.device, dtype=torch.float32)
         w_sq = Cout * ldb
-        for rho in range(stride):
-            taps = list(range(rho, Q, stride))
-            u0 = (rho - pad) % stride
-            if u0 >= Tout or not taps:
-                continue
-            Ju = (Tout - u0 + stride - 1) // stride
-            off = [(u0 + pad - q) // stride for q in taps]
-            _fwd_like(x, Tin, pb, taps[0], stride, len(taps), ldb, w_sq, Cin, Cout, y, J=Ju, P=1, is_=1, os_=stride,
-                      o0=u0, Tout=Tout, off=off, bias=bias)
+        for u0, Ju, q0, nq, off in dgrad_phase_plan(Q, stride, pad, 1, Tout):
+            _fwd_like(x, Tin, pb, q0, stride, nq, ldb, w_sq, Cin, Cout, y, J=Ju, P=1, is_=1, os_=stride, o0=u0, Tout=Tout,
+                      off=off, bias=bias)
         ctx.cfg = cfg
         ctx.dims = (B, Tin, Cin, Cout, Tout)
         ctx.save_for_backward(x, pa)
