@@ -182,6 +182,11 @@ def kernel_table(ops, dev):
     return rows
 
 
+def trace(msg):
+    if os.environ.get("EVK_BENCH_TRACE"):
+        print(f"[bench rank {os.environ.get('RANK', '0')} t={time.time() % 1000:.1f}] {msg}", file=sys.stderr, flush=True)
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -196,6 +201,7 @@ def run_ours(args):
     from easevoice_trainer_b200.train import s2_step
     from easevoice_trainer_b200 import configs
     lib.init()
+    trace("lib + process group up")
     hps = configs.load_s2_config()
     torch.manual_seed(hps["train"]["seed"])
     net_g = models.SynthesizerTrn(hps["data"]["filter_length"] // 2 + 1, hps["train"]["segment_size"] // hps["data"]["hop_length"],
@@ -227,6 +233,7 @@ def run_ours(args):
         return float(ms) / steps
 
     batch = s2_step.to_device_batch(host, dev, st.bank)
+    trace("batch on device")
     last = {}
 
     run = st.step if args.no_graph else st.graph_step
@@ -242,13 +249,17 @@ def run_ours(args):
     l0 = ops.launches()
     st.step(batch)                                   # one eager step: counts the library launches a step consists of
     launches = ops.launches() - l0
+    torch.cuda.synchronize()
+    trace("eager step done")
     for _ in range(args.warmup):
         step_resident()
+        trace("warm-up step done")
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.3)
     ms = timed(step_resident, args.steps)
+    trace(f"timed region done {ms:.1f} ms")
     clocks = sampler.stop() if sampler else None
     for _ in range(2):
         step_e2e()
