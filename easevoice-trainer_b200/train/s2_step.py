@@ -189,24 +189,40 @@ class S2Step:
         if self.world > 1:
             dist.all_reduce(opt.flat_g)
 
-    def step(self, batch, noise=None, ids_slice=None):
-        """Eager step (every kernel launched from Python).  No host synchronisation anywhere."""
+    # The step in three segments, split where the data-parallel gradient exchanges happen:
+    #   A: G forward, features, D forward, D backward -> flat D grads          | all-reduce(D grads)
+    #   B: D AdamW, D forward (updated weights), G backward -> flat G grads    | all-reduce(G grads)
+    #   C: G AdamW, RNG advance
+    def _seg_a(self, batch, noise=None, ids_slice=None):
         r = self.losses(batch, noise, ids_slice)
         loss_d = self.d_loss(r)
-        gd = torch.autograd.grad(loss_d, self.opt_d.params, allow_unused=True)
-        self.opt_d.set_grads(gd)
-        self._allreduce(self.opt_d)
+        self.opt_d.set_grads(torch.autograd.grad(loss_d, self.opt_d.params, allow_unused=True))
+        return r, loss_d
+
+    def _seg_b(self, r):
         self.opt_d.step(1.0 / self.world)
         loss_g, parts = self.g_loss(r)
-        gg = torch.autograd.grad(loss_g, self.opt_g.params, allow_unused=True)
-        self.opt_g.set_grads(gg)
-        self._allreduce(self.opt_g)
+        self.opt_g.set_grads(torch.autograd.grad(loss_g, self.opt_g.params, allow_unused=True))
+        return loss_g, parts
+
+    def _seg_c(self):
         self.opt_g.step(1.0 / self.world)
         ops.advance_rng()
-        out = dict(loss_disc=loss_d.detach(), loss_gen_all=loss_g.detach(), grad_norm_d=self.opt_d.gnorm_sq,
-                   grad_norm_g=self.opt_g.gnorm_sq)
+
+    @staticmethod
+    def _outputs(loss_d, loss_g, parts, opt_d, opt_g):
+        out = dict(loss_disc=loss_d.detach(), loss_gen_all=loss_g.detach(), grad_norm_d=opt_d.gnorm_sq, grad_norm_g=opt_g.gnorm_sq)
         out.update({k: v.detach() for k, v in parts.items()})
         return out
+
+    def step(self, batch, noise=None, ids_slice=None):
+        """Eager step (every kernel launched from Python).  No host synchronisation anywhere."""
+        r, loss_d = self._seg_a(batch, noise, ids_slice)
+        self._allreduce(self.opt_d)
+        loss_g, parts = self._seg_b(r)
+        self._allreduce(self.opt_g)
+        self._seg_c()
+        return self._outputs(loss_d, loss_g, parts, self.opt_d, self.opt_g)
 
     # ---- CUDA-graph path: the ~3000 launches of one step are captured once per batch shape and replayed --------
     def graph_step(self, batch):
@@ -217,11 +233,18 @@ class S2Step:
         if g is None:
             g = self._capture(batch)
             self._graphs[key] = g
-        graph, static, out = g
+        graphs, static, out = g
         for k in static:
             if static[k] is not batch[k]:
                 static[k].copy_(batch[k], non_blocking=True)
-        graph.replay()
+        if len(graphs) == 1:
+            graphs[0].replay()
+        else:                               # data parallel: NCCL all-reduces run between the captured segments
+            graphs[0].replay()
+            self._allreduce(self.opt_d)
+            graphs[1].replay()
+            self._allreduce(self.opt_g)
+            graphs[2].replay()
         return out
 
     def _capture(self, batch):
@@ -245,10 +268,21 @@ class S2Step:
                              self.opt_d.flat_m, self.opt_d.flat_v, self.opt_d.hyper, ops.rng_state(sp.device)), snap):
             dst.copy_(src)
         torch.cuda.synchronize()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            out = self.step(static)
-        return graph, static, out
+        if self.world == 1:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self.step(static)
+            return [graph], static, out
+        # world > 1: three graphs sharing one memory pool (replayed in capture order), collectives in between
+        ga, gb, gc = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(ga):
+            r, loss_d = self._seg_a(static)
+        with torch.cuda.graph(gb, pool=ga.pool()):
+            loss_g, parts = self._seg_b(r)
+        with torch.cuda.graph(gc, pool=ga.pool()):
+            self._seg_c()
+        out = self._outputs(loss_d, loss_g, parts, self.opt_d, self.opt_g)
+        return [ga, gb, gc], static, out
 
     def set_lr(self, lr):
         self.lr = lr
