@@ -25,7 +25,6 @@ struct TP {
   int off_min, off_max;
   int KCH, TG, NG;          // 16-byte K-chunks per stage (2, 4 or 8), taps per group, groups
   int slab_rows, a_pitch;   // rows staged per chunk, slab panel pitch (rows, == 4 mod 8)
-  int NSLAB;                // slab ring depth: 2, or 3 when there is one tap group per chunk (see producer loop)
   int off[EVK_MAX_TAPS];
 };
 
@@ -71,31 +70,19 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("{\n.reg .b64 st;\nmbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"(smem_u32(bar)) : "memory");
-}
-
-constexpr int NS = 4;            // weight-stage ring depth
-constexpr int NPROD = 192;       // producer threads (warps 0..5); warp 6 issues the MMAs; all 8 warps run the epilogue
-
 // BN: N tile (UMMA N, TMEM columns per M tile); MT: number of 128-position M tiles per CTA (weights reused MT times)
-//
-// Warp-specialised mainloop.  Units u = (channel chunk ch, tap group g):
-//   producers : stage the input slab of chunk ch (global -> regs -> rna(tf32) -> smem panels, double buffered) and the
-//               weight tile of unit u into ring stage u % NS with cp.async; a stage is published (fence.proxy.async +
-//               mbarrier arrive) once its cp.async group has landed, NS-1 stages later, so loads run ahead of the MMAs.
-//   MMA thread: waits full barriers, issues tcgen05.mma for every (tap, K-step, M tile), tcgen05.commit -> empty barriers.
 template <int BN, int MT>
 __global__ void __launch_bounds__(TC_THREADS, 2) gconv_tc_kernel(const __grid_constant__ TP p) {
   constexpr int B_PITCH = BN + 4;                               // weight panel pitch (rows); == 4 (mod 8)
-  constexpr int TCOLS = (BN * MT < 32) ? 32 : BN * MT;          // power of two >= 32 for BN in {16..128}, MT in {1,2}
+  constexpr int TCOLS = (BN * MT < 32) ? 32 : BN * MT;          // power of two >= 32 for BN in {16..256}, MT in {1,2}
+  static_assert(TCOLS <= 512, "TMEM has 512 columns");
   extern __shared__ __align__(128) uint8_t tsm[];
   const int KCH = p.KCH, KC = KCH * 4;
   const int slab_bytes = KCH * p.a_pitch * 16;
   const int wt_bytes = p.TG * KCH * B_PITCH * 16;
-  uint8_t* slab0 = tsm;                                         // [NSLAB][KCH][a_pitch][16 B]
-  uint8_t* wt0 = tsm + p.NSLAB * slab_bytes;                    // [NS][TG][KCH][B_PITCH][16 B]
-  __shared__ __align__(8) uint64_t full_w[NS], empty_w[NS], full_s[3], empty_s[3], acc_full;
+  uint8_t* slab0 = tsm;                                         // [2][KCH][a_pitch][16 B]
+  uint8_t* wt0 = tsm + 2 * slab_bytes;                          // [2][TG][KCH][B_PITCH][16 B]
+  __shared__ __align__(8) uint64_t mbar[2];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -114,9 +101,8 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gconv_tc_kernel(const __grid_co
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
   }
   if (tid == 32) {
-    for (int i = 0; i < NS; ++i) { mbar_init(&full_w[i], NPROD); mbar_init(&empty_w[i], 1); }
-    for (int i = 0; i < 3; ++i) { mbar_init(&full_s[i], NPROD); mbar_init(&empty_s[i], 1); }
-    mbar_init(&acc_full, 1);
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n");
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n");
@@ -125,109 +111,86 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gconv_tc_kernel(const __grid_co
   const uint32_t tmem_base = tmem_base_s;
 
   const int nchunks = (p.C + KC - 1) / KC;
-  const int NG = p.NG;
-  const int U = nchunks * NG;
+  const int U = nchunks * p.NG;
 
-  if (warp < 6) {
-    // =============================== producers ===============================
-    const int ptid = tid;
-    auto load_slab = [&](int ch, int buf) {
-      uint8_t* dst = slab0 + buf * slab_bytes;
-      const int c0 = ch * KC;
-      const int total = p.slab_rows * KCH;
-      for (int i0 = ptid; i0 < total; i0 += NPROD * 4) {
-        float4 v[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {                            // 4 independent 16-byte loads in flight per thread
-          const int i = i0 + k * NPROD;
-          v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (i < total) {
-            const int r = i / KCH, kc = i - r * KCH;
-            const int c = c0 + kc * 4, f = lo + r;
-            if (f >= 0 && f < lim_rows && c < p.C) v[k] = *reinterpret_cast<const float4*>(X + (long long)f * p.ldx + c);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int i = i0 + k * NPROD;
-          if (i < total) {
-            const int r = i / KCH, kc = i - r * KCH;
-            uint4 t = make_uint4(f2tf32(v[k].x), f2tf32(v[k].y), f2tf32(v[k].z), f2tf32(v[k].w));
-            *reinterpret_cast<uint4*>(dst + ((size_t)kc * p.a_pitch + r) * 16) = t;
-          }
-        }
-      }
-    };
-    auto load_w = [&](int ch, int g, int stage) {
-      uint8_t* dst = wt0 + stage * wt_bytes;
-      const int c0 = ch * KC;
-      const int total = p.TG * BN * KCH;
-      for (int i = ptid; i < total; i += NPROD) {
-        const int tq = i / (BN * KCH), rem = i - tq * (BN * KCH);
-        const int n = rem / KCH, kc = rem - n * KCH;
-        const int c = c0 + kc * 4, q = g * p.TG + tq;
-        const bool ok = (q < p.Q) && (n0 + n < p.N) && (c < p.C);
-        const float* src = ok ? (Wg + (long long)q * p.w_sq + (long long)(n0 + n) * p.ldw + c) : Wg;
-        cp_async16(dst + ((size_t)(tq * KCH + kc) * B_PITCH + n) * 16, src, ok ? 16 : 0);
-      }
-    };
-    for (int u = 0; u < U; ++u) {
-      const int ch = u / NG, g = u - ch * NG, st = u % NS;
-      if (g == 0) {
-        // the slab ring must be deep enough that the chunk being overwritten (ch - NSLAB) only depends on weight
-        // stages already published (publication lags NS-2 units): (NSLAB-1)*NG >= 2, guaranteed by the host
-        const int sb = ch % p.NSLAB;
-        if (ch >= p.NSLAB) mbar_wait(&empty_s[sb], ((ch / p.NSLAB) - 1) & 1);
-        load_slab(ch, sb);
-        asm volatile("fence.proxy.async.shared::cta;\n");
-        mbar_arrive(&full_s[sb]);
-      }
-      if (u >= NS) mbar_wait(&empty_w[st], ((u / NS) - 1) & 1);
-      load_w(ch, g, st);
-      cp_async_commit();
-      if (u >= NS - 2) {                                         // publish the stage issued NS-2 units ago
-        cp_async_wait<NS - 2>();
-        asm volatile("fence.proxy.async.shared::cta;\n");
-        mbar_arrive(&full_w[(u - (NS - 2)) % NS]);
-      }
+  auto load_slab = [&](int ch, int buf) {                       // global -> regs -> rna(tf32) -> smem panels
+    uint8_t* dst = slab0 + buf * slab_bytes;
+    const int c0 = ch * KC;
+    const int total = p.slab_rows * KCH;
+    for (int i = tid; i < total; i += TC_THREADS) {
+      const int r = i / KCH, kc = i - r * KCH;
+      const int c = c0 + kc * 4, f = lo + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f >= 0 && f < lim_rows && c < p.C) v = *reinterpret_cast<const float4*>(X + (long long)f * p.ldx + c);
+      uint4 t = make_uint4(f2tf32(v.x), f2tf32(v.y), f2tf32(v.z), f2tf32(v.w));
+      *reinterpret_cast<uint4*>(dst + ((size_t)kc * p.a_pitch + r) * 16) = t;
     }
-    cp_async_wait<0>();
-    asm volatile("fence.proxy.async.shared::cta;\n");
-    for (int u = max(0, U - (NS - 2)); u < U; ++u) mbar_arrive(&full_w[u % NS]);
-  } else if (warp == 6) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      const uint32_t slab_a = smem_u32(slab0), wt_a = smem_u32(wt0);
-      const uint32_t a_lbo = p.a_pitch * 16;
-      for (int u = 0; u < U; ++u) {
-        const int ch = u / NG, g = u - ch * NG, st = u % NS;
-        if (g == 0) mbar_wait(&full_s[ch % p.NSLAB], (ch / p.NSLAB) & 1);
-        mbar_wait(&full_w[st], (u / NS) & 1);
+  };
+  auto load_w = [&](int ch, int g, int buf) {                   // cp.async (weights are tf32-rounded at pack time)
+    uint8_t* dst = wt0 + buf * wt_bytes;
+    const int c0 = ch * KC;
+    const int total = p.TG * BN * KCH;
+    for (int i = tid; i < total; i += TC_THREADS) {
+      const int tq = i / (BN * KCH), rem = i - tq * (BN * KCH);
+      const int n = rem / KCH, kc = rem - n * KCH;
+      const int c = c0 + kc * 4, q = g * p.TG + tq;
+      const bool ok = (q < p.Q) && (n0 + n < p.N) && (c < p.C);
+      const float* src = ok ? (Wg + (long long)q * p.w_sq + (long long)(n0 + n) * p.ldw + c) : Wg;
+      cp_async16(dst + ((size_t)(tq * KCH + kc) * B_PITCH + n) * 16, src, ok ? 16 : 0);
+    }
+  };
+
+  // instruction descriptor: D=f32, A=B=tf32, both K-major, N = BN, M = 128
+  constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+  load_slab(0, 0);
+  load_w(0, 0, 0);
+  cp_async_commit();
+  uint32_t uses[2] = {0, 0};                                     // completed-commit count per W buffer (phase tracking)
+  for (int u = 0; u < U; ++u) {
+    const int ch = u / p.NG, g = u - ch * p.NG;
+    if (u + 1 < U) {
+      const int ch1 = (u + 1) / p.NG, g1 = (u + 1) - ch1 * p.NG;
+      const int nb = (u + 1) & 1;
+      if (u >= 1) {                                              // MMAs of unit u-1 read W buffer nb (and older slabs)
+        mbar_wait(&mbar[nb], (uses[nb] - 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;\n");
-        const uint32_t sl = slab_a + (ch % p.NSLAB) * slab_bytes;
-        const uint32_t wt = wt_a + st * wt_bytes;
-        const int ntaps = min(p.TG, p.Q - g * p.TG);
-        for (int tq = 0; tq < ntaps; ++tq) {
-          const int toff = (p.off[g * p.TG + tq] - p.off_min) * p.P;
-          for (int k2 = 0; k2 < KCH / 2; ++k2) {
-            const uint64_t bdesc = make_smem_desc(wt + ((tq * KCH + 2 * k2) * B_PITCH) * 16, B_PITCH * 16, 128);
+      }
+      if (g1 == 0) load_slab(ch1, ch1 & 1);
+      load_w(ch1, g1, nb);
+      cp_async_commit();
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    asm volatile("fence.proxy.async.shared::cta;\n");           // generic-proxy smem writes -> visible to the tensor core
+    __syncthreads();
+    if (tid == 0) {
+      asm volatile("tcgen05.fence::after_thread_sync;\n");
+      const uint32_t sl = smem_u32(slab0 + (ch & 1) * slab_bytes);
+      const uint32_t wt = smem_u32(wt0 + (u & 1) * wt_bytes);
+      const int ntaps = min(p.TG, p.Q - g * p.TG);
+      for (int tq = 0; tq < ntaps; ++tq) {
+        const int toff = (p.off[g * p.TG + tq] - p.off_min) * p.P;
+        for (int k2 = 0; k2 < KCH / 2; ++k2) {
+          const uint64_t bdesc = make_smem_desc(wt + ((tq * KCH + 2 * k2) * B_PITCH) * 16, B_PITCH * 16, 128);
 #pragma unroll
-            for (int mt = 0; mt < MT; ++mt) {
-              const uint64_t adesc = make_smem_desc(sl + ((2 * k2) * p.a_pitch + mt * 128 + toff) * 16, a_lbo, 128);
-              umma_tf32(tmem_base + mt * BN, adesc, bdesc, IDESC, (u | tq | k2) != 0 ? 1u : 0u);
-            }
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t adesc = make_smem_desc(sl + ((2 * k2) * p.a_pitch + mt * 128 + toff) * 16, p.a_pitch * 16, 128);
+            umma_tf32(tmem_base + mt * BN, adesc, bdesc, IDESC, (u | tq | k2) != 0 ? 1u : 0u);
           }
         }
-        umma_commit(&empty_w[st]);
-        if (g == NG - 1) umma_commit(&empty_s[ch % p.NSLAB]);
       }
-      umma_commit(&acc_full);
+      umma_commit(&mbar[u & 1]);
     }
+    uses[u & 1]++;
   }
-  // all warps: wait for the accumulator, then epilogue
-  mbar_wait(&acc_full, 0);
-  asm volatile("tcgen05.fence::after_thread_sync;\n");
+  // wait for the last commit (all MMAs complete), then epilogue
+  {
+    const int lb = (U - 1) & 1;
+    mbar_wait(&mbar[lb], (uses[lb] - 1) & 1);
+    asm volatile("tcgen05.fence::after_thread_sync;\n");
+  }
 
   float* Y = p.y + b * p.y_sb + h * p.y_sh;
   const float* R = p.res ? (p.res + b * p.r_sb + h * p.r_sh) : nullptr;
@@ -289,20 +252,20 @@ static int launch_tc(TP& p, cudaStream_t st) {
   // stage shape: KCH 16-byte K-chunks (KC = 4*KCH channels) and TG taps per stage
   auto plan = [&](int kch, int& tg, int& ng) {
     const long long tap_bytes = (long long)kch * B_PITCH * 16;
-    tg = (int)max(1LL, min((long long)p.Q, (17 * 1024) / tap_bytes));          // ~16 KB weight stages, NS of them
+    tg = (int)max(1LL, min((long long)p.Q, (36 * 1024) / tap_bytes));
     ng = (p.Q + tg - 1) / tg;
     tg = (p.Q + ng - 1) / ng;
-    return (long long)(ng >= 2 ? 2 : 3) * kch * pitch * 16 + (long long)NS * tg * tap_bytes;
+    return 2 * (long long)kch * pitch * 16 + 2 * (long long)tg * tap_bytes;
   };
   int KCH = p.C >= 32 ? 8 : (p.C >= 16 ? 4 : 2), TG = 1, NG = 1;
   long long smem = plan(KCH, TG, NG);
   if (smem > 110 * 1024 && KCH == 8) {                            // prefer two resident CTAs per SM
     int tg2, ng2;
     long long s2 = plan(4, tg2, ng2);
-    if (s2 <= 110 * 1024 || smem > 200 * 1024) { KCH = 4; TG = tg2; NG = ng2; smem = s2; }
+    if (s2 <= 110 * 1024) { KCH = 4; TG = tg2; NG = ng2; smem = s2; }
   }
   if (smem > 200 * 1024 || pitch > 16383) return 1;               // caller falls back to the mma.sync kernel
-  p.KCH = KCH; p.TG = TG; p.NG = NG; p.slab_rows = (int)rows; p.a_pitch = (int)pitch; p.NSLAB = NG >= 2 ? 2 : 3;
+  p.KCH = KCH; p.TG = TG; p.NG = NG; p.slab_rows = (int)rows; p.a_pitch = (int)pitch;
   auto kern = gconv_tc_kernel<BN, MT>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -335,6 +298,7 @@ int gconv_tc_try(const evk_gconv_desc* d, cudaStream_t st) {
   const long long npos = (long long)d->J * d->P;
   const bool two = npos >= 4 * 128;                              // reuse each weight tile for two M tiles when rows allow
   const int N = d->N;
+  if (N >= 256 && (N % 256) == 0) return two ? launch_tc<256, 2>(p, st) : launch_tc<256, 1>(p, st);   // higher flop/byte
   if (N > 64) return two ? launch_tc<128, 2>(p, st) : launch_tc<128, 1>(p, st);
   if (N > 32) return two ? launch_tc<64, 2>(p, st) : launch_tc<64, 1>(p, st);
   if (N > 16) return two ? launch_tc<32, 2>(p, st) : launch_tc<32, 1>(p, st);
