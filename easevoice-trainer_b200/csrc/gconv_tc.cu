@@ -298,7 +298,9 @@ int gconv_tc_try(const evk_gconv_desc* d, cudaStream_t st) {
   const long long npos = (long long)d->J * d->P;
   const bool two = npos >= 4 * 128;                              // reuse each weight tile for two M tiles when rows allow
   const int N = d->N;
-  if (N >= 256 && (N % 256) == 0) return two ? launch_tc<256, 2>(p, st) : launch_tc<256, 1>(p, st);   // higher flop/byte
+  // 256-wide N tiles double the flops per staged byte, but only pay off when the grid still fills the chip
+  const long long ctas256 = ((npos + 255) / 256) * (N / 256) * (long long)d->Z;
+  if (N >= 256 && (N % 256) == 0 && two && ctas256 >= 2 * 148) return launch_tc<256, 2>(p, st);
   if (N > 64) return two ? launch_tc<128, 2>(p, st) : launch_tc<128, 1>(p, st);
   if (N > 32) return two ? launch_tc<64, 2>(p, st) : launch_tc<64, 1>(p, st);
   if (N > 16) return two ? launch_tc<32, 2>(p, st) : launch_tc<32, 1>(p, st);
