@@ -125,7 +125,7 @@ def run_reference(args):
                 config=dict(workload=f"s2_step_B{B_PER_GPU}x{UTT_SECONDS:.0f}s_sr{args.sr_label}_T{T}", cpu_sample_batch=Bc),
                 cpu_baseline=dict(value=val, unit=UNIT, cores=threads, kind="port", sample=sample),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -315,14 +315,27 @@ def run_ours(args):
                              d2h_bytes_per_step=8),
                     gpu_launches=launches, cuda_graph=not args.no_graph, clocks=clocks, losses=losses)
         line.update(extra)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
 
 
+def emit(line):
+    """write the one JSON line to the REAL stdout (fd 1 is pointed at stderr while the benchmark runs so that library
+    banners -- e.g. NCCL's version line -- cannot pollute the result stream)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
