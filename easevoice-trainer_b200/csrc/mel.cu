@@ -14,6 +14,7 @@ constexpr int NBIN = NH + 1;      // 1025
 
 __device__ float2 g_tw[NFFT];     // e^{-2 pi i k / 2048}
 __device__ float g_hann[NFFT];    // periodic Hann
+__device__ float2 g_tw32[32 * 32]; // [k1][t] = e^{-2 pi i t k1 / 1024}: inter-stage twiddles of the 32 x 32 warp FFT
 static bool g_tables_ready = false;
 
 int mel_init_tables() {
@@ -27,6 +28,13 @@ int mel_init_tables() {
   }
   if (cudaMemcpyToSymbol(g_tw, tw, sizeof(tw)) != cudaSuccess) return EVK_ERR_CUDA;
   if (cudaMemcpyToSymbol(g_hann, hw, sizeof(hw)) != cudaSuccess) return EVK_ERR_CUDA;
+  static float2 t32[32 * 32];
+  for (int k1 = 0; k1 < 32; ++k1)
+    for (int t = 0; t < 32; ++t) {
+      double a = 2.0 * M_PI * (double)((t * k1) % 1024) / 1024.0;
+      t32[k1 * 32 + t] = make_float2((float)cos(a), (float)(-sin(a)));
+    }
+  if (cudaMemcpyToSymbol(g_tw32, t32, sizeof(t32)) != cudaSuccess) return EVK_ERR_CUDA;
   g_tables_ready = true;
   return EVK_OK;
 }
@@ -119,6 +127,126 @@ __global__ void __launch_bounds__(256) mel_fwd_kernel(const float* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Warp-per-frame variant (the fast path): the 1024-point complex FFT of the even/odd packed frame is computed as
+// 32 x 32 with all data in registers -- each lane runs a 32-point radix-2 FFT on its own registers (compile-time
+// indices, compile-time twiddles), the warp transposes through shared memory once, each lane runs a second
+// 32-point FFT.  No block-wide barrier, 8 frames per CTA, every global access coalesced.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int MEL_WPB = 8;
+constexpr int MEL_WARP_SMEM = 32 * 33 * 8 + (NBIN + 3) * 4;   // 12 560 B per warp
+
+__host__ __device__ constexpr int brev5(int k) {
+  return ((k & 1) << 4) | ((k & 2) << 2) | (k & 4) | ((k & 8) >> 2) | ((k & 16) >> 4);
+}
+
+// cos(2 pi k / 32), sin(2 pi k / 32), k = 0..15
+__device__ constexpr float C32[16] = {1.f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f,
+                                      0.70710678118654752f, 0.55557023301960218f, 0.38268343236508977f,
+                                      0.19509032201612825f, 0.f, -0.19509032201612825f, -0.38268343236508977f,
+                                      -0.55557023301960218f, -0.70710678118654752f, -0.83146961230254524f,
+                                      -0.92387953251128674f, -0.98078528040323043f};
+__device__ constexpr float S32[16] = {0.f, 0.19509032201612825f, 0.38268343236508977f, 0.55557023301960218f,
+                                      0.70710678118654752f, 0.83146961230254524f, 0.92387953251128674f,
+                                      0.98078528040323043f, 1.f, 0.98078528040323043f, 0.92387953251128674f,
+                                      0.83146961230254524f, 0.70710678118654752f, 0.55557023301960218f,
+                                      0.38268343236508977f, 0.19509032201612825f};
+
+// in-place 32-point DIF FFT on registers; X[k] ends up in element brev5(k)
+__device__ __forceinline__ void fft32_regs(float (&xr)[32], float (&xi)[32]) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+#pragma unroll
+    for (int blk = 0; blk < 32; blk += 2 * half) {
+#pragma unroll
+      for (int j = 0; j < half; ++j) {
+        const int i0 = blk + j, i1 = i0 + half;
+        const int tw = j * (16 / half);                       // exponent of W_32 (compile-time after unrolling)
+        const float ar = xr[i0], ai = xi[i0], br = xr[i1], bi = xi[i1];
+        xr[i0] = ar + br; xi[i0] = ai + bi;
+        const float dr = ar - br, di = ai - bi;
+        if (tw == 0) { xr[i1] = dr; xi[i1] = di; }
+        else if (tw == 8) { xr[i1] = di; xi[i1] = -dr; }     // * (-i)
+        else {                                                 // (dr + i di)(c - i s)
+          xr[i1] = fmaf(dr, C32[tw], di * S32[tw]);
+          xi[i1] = fmaf(di, C32[tw], -dr * S32[tw]);
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(MEL_WPB * 32, 2) mel_fwd_warp_kernel(
+    const float* __restrict__ wav, int L, int ldw, int T, long long nframes, int hop, int n_mels,
+    const int* __restrict__ fb_ptr, const int* __restrict__ fb_idx, const float* __restrict__ fb_val,
+    float* __restrict__ spec, int ld_spec, float* __restrict__ mel, int ld_mel, float* __restrict__ cplx) {
+  extern __shared__ __align__(16) uint8_t msm[];               // per warp: float2[32*33] transpose buffer + float[NBIN+3]
+  const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
+  const long long frame = (long long)blockIdx.x * MEL_WPB + w;
+  if (frame >= nframes) return;                                // warp-uniform; no block-wide barriers below
+  const int b = (int)(frame / T), f = (int)(frame - (long long)b * T);
+  const int pad = (NFFT - hop) / 2, s0 = f * hop - pad;
+  const float* wv = wav + (long long)b * ldw;
+  float xr[32], xi[32];
+  const bool interior = (s0 >= 0) && (s0 + NFFT <= L) && (((s0 & 1) == 0) && ((reinterpret_cast<uintptr_t>(wv) & 7) == 0));
+#pragma unroll
+  for (int n1 = 0; n1 < 32; ++n1) {                            // z[m] = (x[2m] w[2m], x[2m+1] w[2m+1]), m = 32 n1 + t
+    const int m = 32 * n1 + t;
+    const float2 hw = *reinterpret_cast<const float2*>(&g_hann[2 * m]);
+    float2 v;
+    if (interior) v = *reinterpret_cast<const float2*>(wv + s0 + 2 * m);
+    else v = make_float2(wv[reflect_idx(s0 + 2 * m, L)], wv[reflect_idx(s0 + 2 * m + 1, L)]);
+    xr[n1] = v.x * hw.x;
+    xi[n1] = v.y * hw.y;
+  }
+  fft32_regs(xr, xi);                                          // A[k1][n2 = t] in element brev5(k1)
+  float2* z = reinterpret_cast<float2*>(msm + (size_t)w * MEL_WARP_SMEM);
+#pragma unroll
+  for (int k1 = 0; k1 < 32; ++k1) {                            // inter-stage twiddle, then transpose through smem
+    const float2 tw = g_tw32[k1 * 32 + t];
+    const float ar = xr[brev5(k1)], ai = xi[brev5(k1)];
+    z[k1 * 33 + t] = make_float2(ar * tw.x - ai * tw.y, ar * tw.y + ai * tw.x);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int n2 = 0; n2 < 32; ++n2) {                            // lane t now owns k1 = t
+    const float2 v = z[t * 33 + n2];
+    xr[n2] = v.x; xi[n2] = v.y;
+  }
+  __syncwarp();
+  fft32_regs(xr, xi);                                          // Z[t + 32 k2] in element brev5(k2)
+#pragma unroll
+  for (int k2 = 0; k2 < 32; ++k2) z[t + 32 * k2] = make_float2(xr[brev5(k2)], xi[brev5(k2)]);
+  __syncwarp();
+  float* mg = reinterpret_cast<float*>(msm + (size_t)w * MEL_WARP_SMEM + 32 * 33 * sizeof(float2));
+  float2* cp = cplx ? reinterpret_cast<float2*>(cplx) + frame * NBIN : nullptr;
+#pragma unroll
+  for (int j = 0; j <= 32; ++j) {                              // real-FFT untangle: bins k = t + 32 j (+ bin 1024)
+    const int k = t + 32 * j;
+    if (j == 32 && t != 0) break;
+    const float2 zk = (j < 32) ? make_float2(xr[brev5(j & 31)], xi[brev5(j & 31)]) : z[0];
+    float2 zc = z[(NH - k) & (NH - 1)];
+    zc.y = -zc.y;
+    const float2 sm = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
+    const float2 dd = make_float2(0.5f * (zk.x - zc.x), 0.5f * (zk.y - zc.y));
+    const float2 tw = g_tw[k];
+    const float2 tt = cmul(tw, dd);
+    const float2 X = make_float2(sm.x + tt.y, sm.y - tt.x);
+    const float m = sqrtf(X.x * X.x + X.y * X.y + 1e-6f);
+    mg[k] = m;
+    if (spec) spec[frame * ld_spec + k] = m;
+    if (cp) cp[k] = X;
+  }
+  __syncwarp();
+  if (mel) {
+    for (int mm = t; mm < n_mels; mm += 32) {
+      float acc = 0.f;
+      for (int e = fb_ptr[mm]; e < fb_ptr[mm + 1]; ++e) acc = fmaf(fb_val[e], mg[fb_idx[e]], acc);
+      mel[frame * ld_mel + mm] = logf(fmaxf(acc, 1e-5f));
+    }
+  }
+}
+
 // adjoint: d wav from d logmel (per frame direct inverse transform; only B*32 frames per train step)
 __global__ void __launch_bounds__(256) mel_bwd_kernel(const float* __restrict__ dmel, int ld_dmel,
                                                       const float* __restrict__ cplx, const float* __restrict__ mel,
@@ -180,6 +308,9 @@ __global__ void spec_to_mel_kernel(const float* __restrict__ spec, long long row
 }  // namespace evk
 using namespace evk;
 
+static int g_mel_variant = 1;      // 1: warp-per-frame register FFT (default); 0: CTA-per-frame shared-memory FFT
+extern "C" int evk_set_mel_variant(int32_t v) { g_mel_variant = v ? 1 : 0; return EVK_OK; }
+
 static int frames_of(int L, int hop) { return (L + 2 * ((NFFT - hop) / 2) - NFFT) / hop + 1; }
 
 extern "C" int evk_mel_fwd(const float* wav, int32_t B, int32_t L, int32_t ldw, int32_t hop, int32_t n_mels,
@@ -192,9 +323,20 @@ extern "C" int evk_mel_fwd(const float* wav, int32_t B, int32_t L, int32_t ldw, 
   if (rc) { set_error("mel_fwd: table init failed"); return rc; }
   const int T = frames_of(L, hop);
   if (T <= 0) return EVK_OK;
-  mel_fwd_kernel<<<B * T, 256, 0, (cudaStream_t)stream>>>(wav, L, ldw, T, hop, n_mels, fb_ptr, fb_idx, fb_val, spec,
-                                                          ld_spec, mel, ld_mel, cplx);
-  return check_launch("mel_fwd_kernel");
+  const long long nframes = (long long)B * T;
+  if (g_mel_variant == 0) {                                      // reference variant: one 256-thread CTA per frame
+    mel_fwd_kernel<<<B * T, 256, 0, (cudaStream_t)stream>>>(wav, L, ldw, T, hop, n_mels, fb_ptr, fb_idx, fb_val, spec,
+                                                            ld_spec, mel, ld_mel, cplx);
+    return check_launch("mel_fwd_kernel");
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(mel_fwd_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MEL_WPB * MEL_WARP_SMEM);
+    attr_set = true;
+  }
+  mel_fwd_warp_kernel<<<(unsigned)((nframes + MEL_WPB - 1) / MEL_WPB), MEL_WPB * 32, MEL_WPB * MEL_WARP_SMEM, (cudaStream_t)stream>>>(
+      wav, L, ldw, T, nframes, hop, n_mels, fb_ptr, fb_idx, fb_val, spec, ld_spec, mel, ld_mel, cplx);
+  return check_launch("mel_fwd_warp_kernel");
 }
 
 extern "C" int evk_mel_bwd(const float* dmel, int32_t ld_dmel, const float* cplx, const float* mel, int32_t ld_mel,

@@ -108,6 +108,8 @@ int evk_weight_pack_bwd(const float* dpa, int32_t lda, const float* v, const flo
 int evk_mel_fwd(const float* wav, int32_t B, int32_t L, int32_t ldw, int32_t hop, int32_t n_mels,
                 const int32_t* fb_ptr, const int32_t* fb_idx, const float* fb_val, float* spec, int32_t ld_spec,
                 float* mel, int32_t ld_mel, float* cplx, evk_stream_t stream);
+/* 1 (default): warp-per-frame register FFT; 0: the first CTA-per-frame shared-memory FFT (kept for A/B parity). */
+int evk_set_mel_variant(int32_t v);
 /* gradient wrt wav of sum(dmel * mel): dwav [B][L] must be zero-initialised (overlap-add). */
 int evk_mel_bwd(const float* dmel, int32_t ld_dmel, const float* cplx, const float* mel, int32_t ld_mel, int32_t B,
                 int32_t L, int32_t ldw, int32_t hop, int32_t n_mels, const int32_t* fb_ptr, const int32_t* fb_idx,
