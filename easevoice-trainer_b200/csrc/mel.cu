@@ -133,8 +133,9 @@ __global__ void __launch_bounds__(256) mel_fwd_kernel(const float* __restrict__ 
 // indices, compile-time twiddles), the warp transposes through shared memory once, each lane runs a second
 // 32-point FFT.  No block-wide barrier, 8 frames per CTA, every global access coalesced.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int MEL_WPB = 8;
+constexpr int MEL_WPB = 6;
 constexpr int MEL_WARP_SMEM = 32 * 33 * 8 + (NBIN + 3) * 4;   // 12 560 B per warp
+constexpr int MEL_TAB_SMEM = NFFT * 4 + 32 * 32 * 8 + (NH + 8) * 8;   // Hann + inter-stage twiddles + untangle twiddles
 
 __host__ __device__ constexpr int brev5(int k) {
   return ((k & 1) << 4) | ((k & 2) << 2) | (k & 4) | ((k & 8) >> 2) | ((k & 16) >> 4);
@@ -180,10 +181,19 @@ __global__ void __launch_bounds__(MEL_WPB * 32, 2) mel_fwd_warp_kernel(
     const float* __restrict__ wav, int L, int ldw, int T, long long nframes, int hop, int n_mels,
     const int* __restrict__ fb_ptr, const int* __restrict__ fb_idx, const float* __restrict__ fb_val,
     float* __restrict__ spec, int ld_spec, float* __restrict__ mel, int ld_mel, float* __restrict__ cplx) {
-  extern __shared__ __align__(16) uint8_t msm[];               // per warp: float2[32*33] transpose buffer + float[NBIN+3]
+  // persistent CTA: the three lookup tables are staged in shared memory once (the 200 KB of per-warp buffers leave
+  // almost no L1, so table reads from global memory would otherwise go to L2 on every frame)
+  extern __shared__ __align__(16) uint8_t msm[];
+  float* s_hann = reinterpret_cast<float*>(msm);
+  float2* s_tw32 = reinterpret_cast<float2*>(msm + NFFT * 4);
+  float2* s_tw = reinterpret_cast<float2*>(msm + NFFT * 4 + 32 * 32 * 8);
+  uint8_t* wsm = msm + MEL_TAB_SMEM;                           // per warp: float2[32*33] transpose buffer + float[NBIN+3]
+  for (int i = threadIdx.x; i < NFFT; i += blockDim.x) s_hann[i] = g_hann[i];
+  for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) s_tw32[i] = g_tw32[i];
+  for (int i = threadIdx.x; i <= NH; i += blockDim.x) s_tw[i] = g_tw[i];
+  __syncthreads();
   const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
-  const long long frame = (long long)blockIdx.x * MEL_WPB + w;
-  if (frame >= nframes) return;                                // warp-uniform; no block-wide barriers below
+  for (long long frame = (long long)blockIdx.x * MEL_WPB + w; frame < nframes; frame += (long long)gridDim.x * MEL_WPB) {
   const int b = (int)(frame / T), f = (int)(frame - (long long)b * T);
   const int pad = (NFFT - hop) / 2, s0 = f * hop - pad;
   const float* wv = wav + (long long)b * ldw;
@@ -192,7 +202,7 @@ __global__ void __launch_bounds__(MEL_WPB * 32, 2) mel_fwd_warp_kernel(
 #pragma unroll
   for (int n1 = 0; n1 < 32; ++n1) {                            // z[m] = (x[2m] w[2m], x[2m+1] w[2m+1]), m = 32 n1 + t
     const int m = 32 * n1 + t;
-    const float2 hw = *reinterpret_cast<const float2*>(&g_hann[2 * m]);
+    const float2 hw = *reinterpret_cast<const float2*>(&s_hann[2 * m]);
     float2 v;
     if (interior) v = *reinterpret_cast<const float2*>(wv + s0 + 2 * m);
     else v = make_float2(wv[reflect_idx(s0 + 2 * m, L)], wv[reflect_idx(s0 + 2 * m + 1, L)]);
@@ -200,10 +210,10 @@ __global__ void __launch_bounds__(MEL_WPB * 32, 2) mel_fwd_warp_kernel(
     xi[n1] = v.y * hw.y;
   }
   fft32_regs(xr, xi);                                          // A[k1][n2 = t] in element brev5(k1)
-  float2* z = reinterpret_cast<float2*>(msm + (size_t)w * MEL_WARP_SMEM);
+  float2* z = reinterpret_cast<float2*>(wsm + (size_t)w * MEL_WARP_SMEM);
 #pragma unroll
   for (int k1 = 0; k1 < 32; ++k1) {                            // inter-stage twiddle, then transpose through smem
-    const float2 tw = g_tw32[k1 * 32 + t];
+    const float2 tw = s_tw32[k1 * 32 + t];
     const float ar = xr[brev5(k1)], ai = xi[brev5(k1)];
     z[k1 * 33 + t] = make_float2(ar * tw.x - ai * tw.y, ar * tw.y + ai * tw.x);
   }
@@ -218,7 +228,7 @@ __global__ void __launch_bounds__(MEL_WPB * 32, 2) mel_fwd_warp_kernel(
 #pragma unroll
   for (int k2 = 0; k2 < 32; ++k2) z[t + 32 * k2] = make_float2(xr[brev5(k2)], xi[brev5(k2)]);
   __syncwarp();
-  float* mg = reinterpret_cast<float*>(msm + (size_t)w * MEL_WARP_SMEM + 32 * 33 * sizeof(float2));
+  float* mg = reinterpret_cast<float*>(wsm + (size_t)w * MEL_WARP_SMEM + 32 * 33 * sizeof(float2));
   float2* cp = cplx ? reinterpret_cast<float2*>(cplx) + frame * NBIN : nullptr;
 #pragma unroll
   for (int j = 0; j <= 32; ++j) {                              // real-FFT untangle: bins k = t + 32 j (+ bin 1024)
@@ -229,7 +239,7 @@ __global__ void __launch_bounds__(MEL_WPB * 32, 2) mel_fwd_warp_kernel(
     zc.y = -zc.y;
     const float2 sm = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
     const float2 dd = make_float2(0.5f * (zk.x - zc.x), 0.5f * (zk.y - zc.y));
-    const float2 tw = g_tw[k];
+    const float2 tw = s_tw[k];
     const float2 tt = cmul(tw, dd);
     const float2 X = make_float2(sm.x + tt.y, sm.y - tt.x);
     const float m = sqrtf(X.x * X.x + X.y * X.y + 1e-6f);
@@ -244,6 +254,8 @@ __global__ void __launch_bounds__(MEL_WPB * 32, 2) mel_fwd_warp_kernel(
       for (int e = fb_ptr[mm]; e < fb_ptr[mm + 1]; ++e) acc = fmaf(fb_val[e], mg[fb_idx[e]], acc);
       mel[frame * ld_mel + mm] = logf(fmaxf(acc, 1e-5f));
     }
+  }
+  __syncwarp();                                                // the per-warp buffers are reused by the next frame
   }
 }
 
@@ -331,10 +343,12 @@ extern "C" int evk_mel_fwd(const float* wav, int32_t B, int32_t L, int32_t ldw, 
   }
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(mel_fwd_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MEL_WPB * MEL_WARP_SMEM);
+    cudaFuncSetAttribute(mel_fwd_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MEL_TAB_SMEM + MEL_WPB * MEL_WARP_SMEM);
     attr_set = true;
   }
-  mel_fwd_warp_kernel<<<(unsigned)((nframes + MEL_WPB - 1) / MEL_WPB), MEL_WPB * 32, MEL_WPB * MEL_WARP_SMEM, (cudaStream_t)stream>>>(
+  const long long need = (nframes + MEL_WPB - 1) / MEL_WPB;
+  const unsigned grid = (unsigned)(need < 2 * 148 ? need : 2 * 148);            // persistent: two CTAs per SM
+  mel_fwd_warp_kernel<<<grid, MEL_WPB * 32, MEL_TAB_SMEM + MEL_WPB * MEL_WARP_SMEM, (cudaStream_t)stream>>>(
       wav, L, ldw, T, nframes, hop, n_mels, fb_ptr, fb_idx, fb_val, spec, ld_spec, mel, ld_mel, cplx);
   return check_launch("mel_fwd_warp_kernel");
 }
