@@ -135,7 +135,8 @@ __global__ void __launch_bounds__(256) mel_fwd_kernel(const float* __restrict__ 
 // ------------------------------------------------------------------------------------------------------------
 constexpr int MEL_WPB = 6;
 constexpr int MEL_WARP_SMEM = 32 * 33 * 8 + (NBIN + 3) * 4;   // 12 560 B per warp
-constexpr int MEL_TAB_SMEM = NFFT * 4 + 32 * 32 * 8 + (NH + 8) * 8;   // Hann + inter-stage twiddles + untangle twiddles
+constexpr int MEL_FB_MAX = 2064;                                          // filterbank non-zeros staged in smem (2 016 for 128 Slaney mels)
+constexpr int MEL_TAB_SMEM = 32 * 32 * 8 + (NH + 8) * 8 + MEL_FB_MAX * 8 + 144 * 4;   // twiddles (2 tables) + CSR val/idx/ptr
 
 __host__ __device__ constexpr int brev5(int k) {
   return ((k & 1) << 4) | ((k & 2) << 2) | (k & 4) | ((k & 8) >> 2) | ((k & 16) >> 4);
@@ -184,13 +185,19 @@ __global__ void __launch_bounds__(MEL_WPB * 32, 2) mel_fwd_warp_kernel(
   // persistent CTA: the three lookup tables are staged in shared memory once (the 200 KB of per-warp buffers leave
   // almost no L1, so table reads from global memory would otherwise go to L2 on every frame)
   extern __shared__ __align__(16) uint8_t msm[];
-  float* s_hann = reinterpret_cast<float*>(msm);
-  float2* s_tw32 = reinterpret_cast<float2*>(msm + NFFT * 4);
-  float2* s_tw = reinterpret_cast<float2*>(msm + NFFT * 4 + 32 * 32 * 8);
+  float2* s_tw32 = reinterpret_cast<float2*>(msm);
+  float2* s_tw = reinterpret_cast<float2*>(msm + 32 * 32 * 8);
+  float* s_fval = reinterpret_cast<float*>(msm + 32 * 32 * 8 + (NH + 8) * 8);
+  int* s_fidx = reinterpret_cast<int*>(s_fval + MEL_FB_MAX);
+  int* s_fptr = s_fidx + MEL_FB_MAX;
   uint8_t* wsm = msm + MEL_TAB_SMEM;                           // per warp: float2[32*33] transpose buffer + float[NBIN+3]
-  for (int i = threadIdx.x; i < NFFT; i += blockDim.x) s_hann[i] = g_hann[i];
   for (int i = threadIdx.x; i < 32 * 32; i += blockDim.x) s_tw32[i] = g_tw32[i];
   for (int i = threadIdx.x; i <= NH; i += blockDim.x) s_tw[i] = g_tw[i];
+  if (mel) {
+    const int nnz = fb_ptr[n_mels];
+    for (int i = threadIdx.x; i < nnz; i += blockDim.x) { s_fval[i] = fb_val[i]; s_fidx[i] = fb_idx[i]; }
+    for (int i = threadIdx.x; i <= n_mels; i += blockDim.x) s_fptr[i] = fb_ptr[i];
+  }
   __syncthreads();
   const int w = threadIdx.x >> 5, t = threadIdx.x & 31;
   for (long long frame = (long long)blockIdx.x * MEL_WPB + w; frame < nframes; frame += (long long)gridDim.x * MEL_WPB) {
@@ -202,7 +209,7 @@ __global__ void __launch_bounds__(MEL_WPB * 32, 2) mel_fwd_warp_kernel(
 #pragma unroll
   for (int n1 = 0; n1 < 32; ++n1) {                            // z[m] = (x[2m] w[2m], x[2m+1] w[2m+1]), m = 32 n1 + t
     const int m = 32 * n1 + t;
-    const float2 hw = *reinterpret_cast<const float2*>(&s_hann[2 * m]);
+    const float2 hw = *reinterpret_cast<const float2*>(&g_hann[2 * m]);
     float2 v;
     if (interior) v = *reinterpret_cast<const float2*>(wv + s0 + 2 * m);
     else v = make_float2(wv[reflect_idx(s0 + 2 * m, L)], wv[reflect_idx(s0 + 2 * m + 1, L)]);
@@ -249,10 +256,25 @@ __global__ void __launch_bounds__(MEL_WPB * 32, 2) mel_fwd_warp_kernel(
   }
   __syncwarp();
   if (mel) {
-    for (int mm = t; mm < n_mels; mm += 32) {
-      float acc = 0.f;
-      for (int e = fb_ptr[mm]; e < fb_ptr[mm + 1]; ++e) acc = fmaf(fb_val[e], mg[fb_idx[e]], acc);
-      mel[frame * ld_mel + mm] = logf(fmaxf(acc, 1e-5f));
+    // sparse filterbank: 16 lanes cooperate on one mel row (two rows per pass), CSR staged in shared memory;
+    // fixed summation order => deterministic
+    const int hf = t >> 4, l16 = t & 15;
+    for (int base = 0; base < n_mels; base += 32) {
+      float keep = 0.f;
+#pragma unroll 4
+      for (int mp = 0; mp < 16; ++mp) {
+        const int m = base + 2 * mp + hf;
+        float acc = 0.f;
+        if (m < n_mels)
+          for (int e = s_fptr[m] + l16; e < s_fptr[m + 1]; e += 16) acc = fmaf(s_fval[e], mg[s_fidx[e]], acc);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+        if (l16 == mp) keep = acc;
+      }
+      const int m = base + 2 * l16 + hf;                         // the 32 lanes cover mels base .. base+31
+      if (m < n_mels) mel[frame * ld_mel + m] = logf(fmaxf(keep, 1e-5f));
     }
   }
   __syncwarp();                                                // the per-warp buffers are reused by the next frame
@@ -336,7 +358,7 @@ extern "C" int evk_mel_fwd(const float* wav, int32_t B, int32_t L, int32_t ldw, 
   const int T = frames_of(L, hop);
   if (T <= 0) return EVK_OK;
   const long long nframes = (long long)B * T;
-  if (g_mel_variant == 0) {                                      // reference variant: one 256-thread CTA per frame
+  if (g_mel_variant == 0 || n_mels > 143) {                                      // reference variant: one 256-thread CTA per frame
     mel_fwd_kernel<<<B * T, 256, 0, (cudaStream_t)stream>>>(wav, L, ldw, T, hop, n_mels, fb_ptr, fb_idx, fb_val, spec,
                                                             ld_spec, mel, ld_mel, cplx);
     return check_launch("mel_fwd_kernel");
