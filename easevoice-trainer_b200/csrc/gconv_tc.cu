@@ -81,8 +81,9 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gconv_tc_kernel(const __grid_co
   const int slab_bytes = KCH * p.a_pitch * 16;
   const int wt_bytes = p.TG * KCH * B_PITCH * 16;
   uint8_t* slab0 = tsm;                                         // [2][KCH][a_pitch][16 B]
-  uint8_t* wt0 = tsm + 2 * slab_bytes;                          // [2][TG][KCH][B_PITCH][16 B]
-  __shared__ __align__(8) uint64_t mbar[2];
+  uint8_t* wt0 = tsm + 2 * slab_bytes;                          // [NW][TG][KCH][B_PITCH][16 B]
+  constexpr int NW = 3;                                         // weight-stage ring depth
+  __shared__ __align__(8) uint64_t mbar[NW];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -101,8 +102,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gconv_tc_kernel(const __grid_co
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
   }
   if (tid == 32) {
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
+    for (int i = 0; i < NW; ++i) mbar_init(&mbar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n");
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n");
@@ -117,13 +117,27 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gconv_tc_kernel(const __grid_co
     uint8_t* dst = slab0 + buf * slab_bytes;
     const int c0 = ch * KC;
     const int total = p.slab_rows * KCH;
-    for (int i = tid; i < total; i += TC_THREADS) {
-      const int r = i / KCH, kc = i - r * KCH;
-      const int c = c0 + kc * 4, f = lo + r;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (f >= 0 && f < lim_rows && c < p.C) v = *reinterpret_cast<const float4*>(X + (long long)f * p.ldx + c);
-      uint4 t = make_uint4(f2tf32(v.x), f2tf32(v.y), f2tf32(v.z), f2tf32(v.w));
-      *reinterpret_cast<uint4*>(dst + ((size_t)kc * p.a_pitch + r) * 16) = t;
+    for (int i0 = tid; i0 < total; i0 += TC_THREADS * 4) {
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {                              // 4 independent 16-byte loads in flight per thread
+        const int i = i0 + k * TC_THREADS;
+        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < total) {
+          const int r = i / KCH, kc = i - r * KCH;
+          const int c = c0 + kc * 4, f = lo + r;
+          if (f >= 0 && f < lim_rows && c < p.C) v[k] = *reinterpret_cast<const float4*>(X + (long long)f * p.ldx + c);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int i = i0 + k * TC_THREADS;
+        if (i < total) {
+          const int r = i / KCH, kc = i - r * KCH;
+          uint4 t = make_uint4(f2tf32(v[k].x), f2tf32(v[k].y), f2tf32(v[k].z), f2tf32(v[k].w));
+          *reinterpret_cast<uint4*>(dst + ((size_t)kc * p.a_pitch + r) * 16) = t;
+        }
+      }
     }
   };
   auto load_w = [&](int ch, int g, int buf) {                   // cp.async (weights are tf32-rounded at pack time)
@@ -146,18 +160,21 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gconv_tc_kernel(const __grid_co
   load_slab(0, 0);
   load_w(0, 0, 0);
   cp_async_commit();
-  uint32_t uses[2] = {0, 0};                                     // completed-commit count per W buffer (phase tracking)
+  // Pipeline: unit u uses weight stage u % 3 and slab buffer ch % 2.  The loads of unit u+1 are issued as soon as the
+  // MMAs of unit u-2 have retired (their stage is then free), i.e. while the MMAs of unit u-1 may still be running.
+  // The slab buffer of chunk ch+1 was last read by chunk ch-1, whose last unit is <= u-NG <= u-2 when NG >= 2; for
+  // NG == 1 it is unit u-1, so that case waits for unit u-1 instead.
   for (int u = 0; u < U; ++u) {
     const int ch = u / p.NG, g = u - ch * p.NG;
     if (u + 1 < U) {
       const int ch1 = (u + 1) / p.NG, g1 = (u + 1) - ch1 * p.NG;
-      const int nb = (u + 1) & 1;
-      if (u >= 1) {                                              // MMAs of unit u-1 read W buffer nb (and older slabs)
-        mbar_wait(&mbar[nb], (uses[nb] - 1) & 1);
+      const int need = (g1 == 0 && p.NG == 1) ? u - 1 : u - 2;  // youngest unit whose MMAs must have retired
+      if (need >= 0) {
+        mbar_wait(&mbar[need % NW], (need / NW) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;\n");
       }
       if (g1 == 0) load_slab(ch1, ch1 & 1);
-      load_w(ch1, g1, nb);
+      load_w(ch1, g1, (u + 1) % NW);
       cp_async_commit();
       cp_async_wait<1>();
     } else {
@@ -168,7 +185,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gconv_tc_kernel(const __grid_co
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;\n");
       const uint32_t sl = smem_u32(slab0 + (ch & 1) * slab_bytes);
-      const uint32_t wt = smem_u32(wt0 + (u & 1) * wt_bytes);
+      const uint32_t wt = smem_u32(wt0 + (u % NW) * wt_bytes);
       const int ntaps = min(p.TG, p.Q - g * p.TG);
       for (int tq = 0; tq < ntaps; ++tq) {
         const int toff = (p.off[g * p.TG + tq] - p.off_min) * p.P;
@@ -181,16 +198,12 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gconv_tc_kernel(const __grid_co
           }
         }
       }
-      umma_commit(&mbar[u & 1]);
+      umma_commit(&mbar[u % NW]);
     }
-    uses[u & 1]++;
   }
   // wait for the last commit (all MMAs complete), then epilogue
-  {
-    const int lb = (U - 1) & 1;
-    mbar_wait(&mbar[lb], (uses[lb] - 1) & 1);
-    asm volatile("tcgen05.fence::after_thread_sync;\n");
-  }
+  mbar_wait(&mbar[(U - 1) % NW], ((U - 1) / NW) & 1);
+  asm volatile("tcgen05.fence::after_thread_sync;\n");
 
   float* Y = p.y + b * p.y_sb + h * p.y_sh;
   const float* R = p.res ? (p.res + b * p.r_sb + h * p.r_sh) : nullptr;
@@ -252,10 +265,10 @@ static int launch_tc(TP& p, cudaStream_t st) {
   // stage shape: KCH 16-byte K-chunks (KC = 4*KCH channels) and TG taps per stage
   auto plan = [&](int kch, int& tg, int& ng) {
     const long long tap_bytes = (long long)kch * B_PITCH * 16;
-    tg = (int)max(1LL, min((long long)p.Q, (36 * 1024) / tap_bytes));
+    tg = (int)max(1LL, min((long long)p.Q, (24 * 1024) / tap_bytes));
     ng = (p.Q + tg - 1) / tg;
     tg = (p.Q + ng - 1) / ng;
-    return 2 * (long long)kch * pitch * 16 + 2 * (long long)tg * tap_bytes;
+    return 2 * (long long)kch * pitch * 16 + 3 * (long long)tg * tap_bytes;
   };
   int KCH = p.C >= 32 ? 8 : (p.C >= 16 ? 4 : 2), TG = 1, NG = 1;
   long long smem = plan(KCH, TG, NG);
@@ -296,7 +309,9 @@ int gconv_tc_try(const evk_gconv_desc* d, cudaStream_t st) {
   }
   p.off_min = mn; p.off_max = mx;
   const long long npos = (long long)d->J * d->P;
-  const bool two = npos >= 4 * 128;                              // reuse each weight tile for two M tiles when rows allow
+  // reuse each weight tile for two M tiles only when the grid still holds >= 2 CTAs per SM
+  const int bn_sel = d->N > 64 ? 128 : (d->N > 32 ? 64 : (d->N > 16 ? 32 : 16));
+  const bool two = npos >= 4 * 128 && ((npos + 255) / 256) * ((d->N + bn_sel - 1) / bn_sel) * (long long)d->Z >= 2 * 148;
   const int N = d->N;
   // 256-wide N tiles double the flops per staged byte, but only pay off when the grid still fills the chip
   const long long ctas256 = ((npos + 255) / 256) * (N / 256) * (long long)d->Z;

@@ -204,6 +204,16 @@ __global__ void __launch_bounds__(MEL_WPB * 32, 2) mel_fwd_warp_kernel(
   const int b = (int)(frame / T), f = (int)(frame - (long long)b * T);
   const int pad = (NFFT - hop) / 2, s0 = f * hop - pad;
   const float* wv = wav + (long long)b * ldw;
+  {                                                            // pull the next frame of this warp towards L2 while this one computes
+    const long long nf = frame + (long long)gridDim.x * MEL_WPB;
+    if (nf < nframes) {
+      const int nb = (int)(nf / T), nfi = (int)(nf - (long long)nb * T);
+      const int ns0 = max(0, min(nfi * hop - pad, L - NFFT));
+      const float* np_ = wav + (long long)nb * ldw + ns0 + t * 64;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(np_));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(np_ + 32));
+    }
+  }
   float xr[32], xi[32];
   const bool interior = (s0 >= 0) && (s0 + NFFT <= L) && (((s0 & 1) == 0) && ((reinterpret_cast<uintptr_t>(wv) & 7) == 0));
 #pragma unroll
@@ -255,26 +265,12 @@ __global__ void __launch_bounds__(MEL_WPB * 32, 2) mel_fwd_warp_kernel(
     if (cp) cp[k] = X;
   }
   __syncwarp();
-  if (mel) {
-    // sparse filterbank: 16 lanes cooperate on one mel row (two rows per pass), CSR staged in shared memory;
-    // fixed summation order => deterministic
-    const int hf = t >> 4, l16 = t & 15;
-    for (int base = 0; base < n_mels; base += 32) {
-      float keep = 0.f;
-#pragma unroll 4
-      for (int mp = 0; mp < 16; ++mp) {
-        const int m = base + 2 * mp + hf;
-        float acc = 0.f;
-        if (m < n_mels)
-          for (int e = s_fptr[m] + l16; e < s_fptr[m + 1]; e += 16) acc = fmaf(s_fval[e], mg[s_fidx[e]], acc);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 8);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-        acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-        if (l16 == mp) keep = acc;
-      }
-      const int m = base + 2 * l16 + hf;                         // the 32 lanes cover mels base .. base+31
-      if (m < n_mels) mel[frame * ld_mel + m] = logf(fmaxf(keep, 1e-5f));
+  if (mel) {                                                   // sparse filterbank, CSR by mel row staged in shared memory
+    for (int mm = t; mm < n_mels; mm += 32) {
+      float acc = 0.f;
+      const int e1 = s_fptr[mm + 1];
+      for (int e = s_fptr[mm]; e < e1; ++e) acc = fmaf(s_fval[e], mg[s_fidx[e]], acc);
+      mel[frame * ld_mel + mm] = logf(fmaxf(acc, 1e-5f));
     }
   }
   __syncwarp();                                                // the per-warp buffers are reused by the next frame
