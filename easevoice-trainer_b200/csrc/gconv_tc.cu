@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gconv_tc_kernel(const __grid_co
   const int wt_bytes = p.TG * KCH * B_PITCH * 16;
   uint8_t* slab0 = tsm;                                         // [2][KCH][a_pitch][16 B]
   uint8_t* wt0 = tsm + 2 * slab_bytes;                          // [NW][TG][KCH][B_PITCH][16 B]
-  constexpr int NW = 3;                                         // weight-stage ring depth
+  constexpr int NW = 2;                                         // weight-stage ring depth (3 measured slower: smaller stages, lower flop/byte)
   __shared__ __align__(8) uint64_t mbar[NW];
   __shared__ uint32_t tmem_base_s;
 
@@ -168,7 +168,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gconv_tc_kernel(const __grid_co
     const int ch = u / p.NG, g = u - ch * p.NG;
     if (u + 1 < U) {
       const int ch1 = (u + 1) / p.NG, g1 = (u + 1) - ch1 * p.NG;
-      const int need = (g1 == 0 && p.NG == 1) ? u - 1 : u - 2;  // youngest unit whose MMAs must have retired
+      const int need = u + 1 - NW;                               // youngest unit whose MMAs must have retired (frees stage and slab)
       if (need >= 0) {
         mbar_wait(&mbar[need % NW], (need / NW) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;\n");
@@ -265,10 +265,10 @@ static int launch_tc(TP& p, cudaStream_t st) {
   // stage shape: KCH 16-byte K-chunks (KC = 4*KCH channels) and TG taps per stage
   auto plan = [&](int kch, int& tg, int& ng) {
     const long long tap_bytes = (long long)kch * B_PITCH * 16;
-    tg = (int)max(1LL, min((long long)p.Q, (24 * 1024) / tap_bytes));
+    tg = (int)max(1LL, min((long long)p.Q, (36 * 1024) / tap_bytes));
     ng = (p.Q + tg - 1) / tg;
     tg = (p.Q + ng - 1) / ng;
-    return 2 * (long long)kch * pitch * 16 + 3 * (long long)tg * tap_bytes;
+    return 2 * (long long)kch * pitch * 16 + 2 * (long long)tg * tap_bytes;
   };
   int KCH = p.C >= 32 ? 8 : (p.C >= 16 ? 4 : 2), TG = 1, NG = 1;
   long long smem = plan(KCH, TG, NG);
@@ -309,9 +309,7 @@ int gconv_tc_try(const evk_gconv_desc* d, cudaStream_t st) {
   }
   p.off_min = mn; p.off_max = mx;
   const long long npos = (long long)d->J * d->P;
-  // reuse each weight tile for two M tiles only when the grid still holds >= 2 CTAs per SM
-  const int bn_sel = d->N > 64 ? 128 : (d->N > 32 ? 64 : (d->N > 16 ? 32 : 16));
-  const bool two = npos >= 4 * 128 && ((npos + 255) / 256) * ((d->N + bn_sel - 1) / bn_sel) * (long long)d->Z >= 2 * 148;
+  const bool two = npos >= 4 * 128;                              // two M tiles per CTA: each weight tile is reused twice (measured: flop/byte wins over CTA count)
   const int N = d->N;
   // 256-wide N tiles double the flops per staged byte, but only pay off when the grid still fills the chip
   const long long ctas256 = ((npos + 255) / 256) * (N / 256) * (long long)d->Z;
