@@ -117,27 +117,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) gconv_tc_kernel(const __grid_co
     uint8_t* dst = slab0 + buf * slab_bytes;
     const int c0 = ch * KC;
     const int total = p.slab_rows * KCH;
-    for (int i0 = tid; i0 < total; i0 += TC_THREADS * 4) {
-      float4 v[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {                              // 4 independent 16-byte loads in flight per thread
-        const int i = i0 + k * TC_THREADS;
-        v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < total) {
-          const int r = i / KCH, kc = i - r * KCH;
-          const int c = c0 + kc * 4, f = lo + r;
-          if (f >= 0 && f < lim_rows && c < p.C) v[k] = *reinterpret_cast<const float4*>(X + (long long)f * p.ldx + c);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int i = i0 + k * TC_THREADS;
-        if (i < total) {
-          const int r = i / KCH, kc = i - r * KCH;
-          uint4 t = make_uint4(f2tf32(v[k].x), f2tf32(v[k].y), f2tf32(v[k].z), f2tf32(v[k].w));
-          *reinterpret_cast<uint4*>(dst + ((size_t)kc * p.a_pitch + r) * 16) = t;
-        }
-      }
+    for (int i = tid; i < total; i += TC_THREADS) {              // (a hand-unrolled 4-loads-in-flight variant measured 8 % slower)
+      const int r = i / KCH, kc = i - r * KCH;
+      const int c = c0 + kc * 4, f = lo + r;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f >= 0 && f < lim_rows && c < p.C) v = *reinterpret_cast<const float4*>(X + (long long)f * p.ldx + c);
+      uint4 t = make_uint4(f2tf32(v.x), f2tf32(v.y), f2tf32(v.z), f2tf32(v.w));
+      *reinterpret_cast<uint4*>(dst + ((size_t)kc * p.a_pitch + r) * 16) = t;
     }
   };
   auto load_w = [&](int ch, int g, int buf) {                   // cp.async (weights are tf32-rounded at pack time)
