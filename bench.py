@@ -109,6 +109,42 @@ def cpu_reference_step(Bc, T, threads, steps, warmup):
     return sum(times) / len(times)
 
 
+def torch_gpu_port_step(dev, T, steps=3):
+    """The reference's algorithm through STOCK PyTorch kernels (cuDNN / cuBLAS / cuFFT / ATen) on the same B200: the oracle
+    port moved to the GPU, fp32 with TF32 allowed exactly as the reference sets it (sovits.py:172-176), B = 16.  This is the
+    'reference 1-GPU PyTorch step' comparator of BASELINE.json's target; the reference itself cannot run on this box."""
+    import torch
+    from oracle import s2_oracle, mel_oracle
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    PG = {k: v.to(dev) for k, v in s2_oracle.init_params(s2_oracle.generator_param_spec(), 1234).items()}
+    PD = {k: v.to(dev) for k, v in s2_oracle.init_params(s2_oracle.discriminator_param_spec(), 4321).items()}
+    for k, v in PG.items():
+        if k not in s2_oracle.GEN_BUFFERS:
+            v.requires_grad_(True)
+    for v in PD.values():
+        v.requires_grad_(True)
+    wav, ssl, text, spec_len, text_len = [t.to(dev) for t in s2_oracle.synthetic_batch(B_PER_GPU, T, TEXT_LEN, 1234)]
+    spec = mel_oracle.spectrogram(wav.squeeze(1), 2048, HOP, 2048)
+    gp = [v for k, v in PG.items() if k not in s2_oracle.GEN_BUFFERS]
+    g = torch.Generator(device=dev).manual_seed(1)
+    ms = []
+    for it in range(steps + 2):
+        noise = torch.randn(B_PER_GPU, 192, T, generator=g, device=dev)
+        ids = (torch.rand(B_PER_GPU, generator=g, device=dev) * (spec_len - 32 + 1)).long()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        o = s2_oracle.s2_losses(PG, PD, (ssl, spec, spec_len, wav, text, text_len), noise, ids)
+        torch.autograd.grad(o["loss_disc"], list(PD.values()), retain_graph=True)
+        torch.autograd.grad(o["loss_gen_all"], gp, allow_unused=True)
+        e1.record()
+        torch.cuda.synchronize()
+        if it >= 2:
+            ms.append(e0.elapsed_time(e1))
+    return sum(ms) / len(ms)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -317,6 +353,16 @@ def run_ours(args):
                                                   how=f"{nset * reps} back-to-back launches of the training batch (16 x 10 s) over {nset} rotating buffer sets"),
                                      mel_only=dict(achieved=only_gbs, frac=only_gbs / hbm, ms=only_ms,
                                                    note="log-mel only (3 072 B/frame): FFT-arithmetic bound on the fp32 pipe, see DESIGN.md section 6"))
+        # ---- the same algorithm through stock PyTorch GPU kernels (context for BASELINE.json's ">= 10x the reference's
+        #      1-GPU PyTorch step" target); optimiser excluded, so it flatters the comparator
+        if not args.no_torch_port:
+            try:
+                tms = torch_gpu_port_step(dev, T)
+                extra["torch_gpu_port"] = dict(ms_per_step=tms, value=B_PER_GPU * UTT_SECONDS / (tms * 1e-3), unit=UNIT,
+                                               what="oracle port (reference algorithm) on stock PyTorch CUDA kernels, eager, fp32+TF32, "
+                                                    "fwd + both backwards, no optimiser step, same B200")
+            except Exception as e:                      # context only: never fail the benchmark because of it
+                extra["torch_gpu_port"] = dict(error=repr(e)[:200])
         # ---- CPU baseline on this box's host cores (bounded sample)
         threads = cpu_threads()
         if not args.no_cpu_baseline:
@@ -364,6 +410,7 @@ def main():
     ap.add_argument("--sr-label", type=int, default=22050, help="BASELINE.json quotes 10 s @ 22.05 kHz; 32000 = native s2.json rate")
     ap.add_argument("--cpu-batch", type=int, default=2, help="utterances in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-torch-port", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

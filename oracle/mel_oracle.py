@@ -78,7 +78,7 @@ def spectrogram(y, n_fft, hop, win):
 
 def spec_to_mel(spec, n_fft, n_mels, sr, fmin, fmax):
     """|X| [B, F, T] -> log-mel [B, n_mels, T]; mel_processing.py:77-90 (+:8-14)."""
-    basis = torch.from_numpy(mel_filterbank(sr, n_fft, n_mels, fmin, fmax)).to(spec.dtype)
+    basis = torch.from_numpy(mel_filterbank(sr, n_fft, n_mels, fmin, fmax)).to(device=spec.device, dtype=spec.dtype)
     return torch.log(torch.clamp(torch.matmul(basis, spec), min=1e-5))
 
 

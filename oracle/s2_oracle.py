@@ -263,7 +263,7 @@ def relpos_attention(P, pfx, x, c, attn_mask, n_heads, window):
             if n <= 0:
                 continue
             i0 = max(0, -r)
-            idx = torch.arange(i0, i0 + n)
+            idx = torch.arange(i0, i0 + n, device=scores.device)
             add[:, :, idx, idx + r] = rel[:, :, idx, r + window]
         scores = scores + add
     scores = scores.masked_fill(attn_mask == 0, -1e4)
@@ -276,7 +276,7 @@ def relpos_attention(P, pfx, x, c, attn_mask, n_heads, window):
             if n <= 0:
                 continue
             i0 = max(0, -r)
-            idx = torch.arange(i0, i0 + n)
+            idx = torch.arange(i0, i0 + n, device=p.device)
             contrib = p[:, :, idx, idx + r].unsqueeze(-1) * Ev[r + window]
             out = out.index_add(2, idx, contrib)
     out = out.transpose(2, 3).contiguous().view(B, C, Tt)
