@@ -381,11 +381,101 @@ def run_ours(args):
                              d2h_bytes_per_step=8),
                     gpu_launches=launches, cuda_graph=not args.no_graph, clocks=clocks, losses=losses)
         line.update(extra)
+    gpt = None
+    if args.gpt and (world == 1 or args.gpt > 1):
+        del st, net_g, net_d, batch
+        torch.cuda.empty_cache()
+        try:
+            gpt = gpt_section(args, dev, rank, world)
+        except Exception as e:                          # the headline line must survive a failure of the extra section
+            import traceback
+            traceback.print_exc()
+            gpt = dict(error=repr(e)[:300])
+    if rank == 0:
+        line["gpt"] = gpt
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def gpt_section(args, dev, rank, world):
+    """BASELINE.json configs[1]: stage-1 AR-GPT (configs/gpt.yaml: 24 layers, d=512, 16 heads) training_step, batch 16 x
+    (256 phonemes + 1024 semantic tokens) per GPU.  A step = one Lightning training_step (micro-batch fwd + bwd with
+    dropout 0.1 as the reference hard-codes, gradient accumulation; ScaledAdam update on every 4th batch index)."""
+    import torch
+    import torch.distributed as dist
+    from easevoice_trainer_b200 import ops
+    from easevoice_trainer_b200.models_gpt import Text2SemanticDecoder
+    from easevoice_trainer_b200.train import gpt_step
+    from easevoice_trainer_b200.configs import GPT_MODEL
+    B, X, Y = 16, 256, 1024
+    net = Text2SemanticDecoder({"model": GPT_MODEL}, seed=1234).to(dev).train()
+    st = gpt_step.GptStep(net, world_size=world)
+    host = gpt_step.synthetic_batch(B, X, Y, seed=4321 + rank, device="cpu")
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    batch = {k: v.to(dev) for k, v in host.items()}
+    batch["bert_feature"] = ops.to_channels_last(batch["bert_feature"]); batch["bert_channels_last"] = True
+    l0 = ops.launches()
+    st.batch_idx = 4                                  # an eager step that includes the optimizer update
+    st.step(batch)
+    launches = ops.launches() - l0
+    torch.cuda.synchronize()
+    peak_gb = torch.cuda.max_memory_allocated(dev) / 2**30
+    run = st.step if args.no_graph else st.graph_step
+    last = {}
+
+    def resident():
+        last["out"] = run(batch)
+
+    def e2e():
+        b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        b["bert_feature"] = ops.to_channels_last(b["bert_feature"]); b["bert_channels_last"] = True
+        out = run(b)
+        last["host"] = torch.stack([out[0].reshape(()), out[1].reshape(())]).cpu()
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps
+    for _ in range(max(args.warmup, 3)):
+        resident()
+    st.batch_idx = 1
+    steps = 8                                          # two accumulate-4 cycles: 8 micro-batches + 2 optimizer updates
+    ms = timed(resident, steps)
+    st.batch_idx = 1
+    for _ in range(2):
+        e2e()
+    st.batch_idx = 1
+    ms_e2e = timed(e2e, steps)
+    # optimizer update alone
+    st.batch_idx = 4
+    def opt_only():
+        st._ograph.replay() if not args.no_graph else st.opt.step()
+    ms_opt = timed(opt_only, 4)
+    tok = world * B * Y
+    flops = 6.0 * (B * (X + Y)) * (24 * (4 * 512 * 512 + 2 * 512 * 2048)) + 6.0 * B * Y * 512 * 1025 + 6.0 * B * X * 1024 * 512 \
+        + 24 * 3.5 * 4.0 * B * 16 * (X + Y) ** 2 * 32 * 0.62     # attention: fwd + 2.5x bwd (S recomputed twice), ~62% of L^2 visible
+    return dict(metric="stage-1 AR-GPT training_step semantic-tokens/sec", value=tok / (ms * 1e-3), unit="semantic-tokens/s",
+                ms_per_step=ms, steps=steps, config=dict(workload=f"gpt_step_B{B}_X{X}_Y{Y}_L24_d512_h16", dropout=0.1, accumulate=4,
+                                                         optimizer="ScaledAdam (flat, 3 launches)", parallelism=f"dp{world}"),
+                e2e=dict(value=tok / (ms_e2e * 1e-3), unit="semantic-tokens/s", ms_per_step=ms_e2e, h2d_bytes_per_step=h2d, d2h_bytes_per_step=8),
+                optimizer_ms=ms_opt, gpu_launches_per_step_with_update=launches, peak_mem_gb=peak_gb,
+                model_tflops=flops * world / (ms * 1e-3) / 1e12, cuda_graph=not args.no_graph,
+                loss=float(last["out"][0]), acc=float(last["out"][1]))
 
 
 def emit(line):
@@ -411,6 +501,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=2, help="utterances in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-torch-port", action="store_true")
+    ap.add_argument("--gpt", type=int, default=1, help="1: also time the stage-1 AR-GPT step at N=1; 2: at every N; 0: skip")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -1,0 +1,308 @@
+// Stage-1 AR GPT odds and ends: sinusoidal position add (embedding.py:36-81), summed cross-entropy + top-k accuracy
+// (t2s_model.py:486-489), and ScaledAdam (optim.py:123-622) over one flat fp32 arena.
+#include "evk_common.cuh"
+
+namespace evk {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// y[b][t0 + t][:] = x[b][t][:] + alpha * pe[t][:]
+__global__ void sinepos_add_kernel(const float* __restrict__ x, int ldx, long long x_sb, const float* __restrict__ pe, int ldpe,
+                                   const float* __restrict__ alpha, float* __restrict__ y, int ldy, long long y_sb, int B,
+                                   int T, int D) {
+  const float al = alpha[0];
+  const int d4 = D / 4;
+  const long long n = (long long)B * T * d4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % d4);
+    long long r = i / d4;
+    int t = (int)(r % T), b = (int)(r / T);
+    float4 xv = *reinterpret_cast<const float4*>(x + b * x_sb + (size_t)t * ldx + c * 4);
+    float4 pv = *reinterpret_cast<const float4*>(pe + (size_t)t * ldpe + c * 4);
+    float4 o = make_float4(xv.x + al * pv.x, xv.y + al * pv.y, xv.z + al * pv.z, xv.w + al * pv.w);
+    *reinterpret_cast<float4*>(y + b * y_sb + (size_t)t * ldy + c * 4) = o;
+  }
+}
+
+// dalpha += sum_{b,t,d} dy[b][t][d] * pe[t][d]
+__global__ void sinepos_bwd_kernel(const float* __restrict__ dy, int ldy, long long dy_sb, const float* __restrict__ pe, int ldpe,
+                                   float* __restrict__ dalpha, int B, int T, int D) {
+  __shared__ float red[33];
+  const long long n = (long long)B * T * D;
+  float acc = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int d = (int)(i % D);
+    long long r = i / D;
+    int t = (int)(r % T), b = (int)(r / T);
+    acc += dy[b * dy_sb + (size_t)t * ldy + d] * pe[(size_t)t * ldpe + d];
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) atomicAdd(dalpha, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// one warp per row: lse, nll, top-k hit (count of logits strictly above the target logit < k), valid = target != ignore
+__global__ void ce_fwd_kernel(const float* __restrict__ logits, int ld, const long long* __restrict__ tgt, int rows, int V,
+                              int topk, long long ignore, float* __restrict__ lse, float* __restrict__ nll,
+                              unsigned char* __restrict__ flags) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* l = logits + (size_t)row * ld;
+  const long long tg = tgt[row];
+  float mx = -INFINITY;
+  for (int c = lane; c < V; c += 32) mx = fmaxf(mx, l[c]);
+  mx = warp_max(mx);
+  const float lt = (tg >= 0 && tg < V) ? l[tg] : 0.f;
+  float se = 0.f;
+  int above = 0;
+  for (int c = lane; c < V; c += 32) {
+    float v = l[c];
+    se += expf(v - mx);
+    above += (v > lt) ? 1 : 0;
+  }
+  se = warp_sum(se);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) above += __shfl_xor_sync(0xffffffffu, above, o);
+  if (lane == 0) {
+    float ls = mx + logf(se);
+    lse[row] = ls;
+    nll[row] = ls - lt;
+    const bool valid = tg != ignore;
+    flags[row] = (unsigned char)((valid ? 1 : 0) | ((valid && above < topk) ? 2 : 0));
+  }
+}
+
+// out[0] = sum nll (fixed order), out[1] = hits / max(valid, 1)
+__global__ void ce_finalize_kernel(const float* __restrict__ nll, const unsigned char* __restrict__ flags, int rows,
+                                   float* __restrict__ out) {
+  __shared__ float red[33];
+  float s = 0.f, hv = 0.f, vv = 0.f;
+  for (int i = threadIdx.x; i < rows; i += blockDim.x) {
+    s += nll[i];
+    vv += (flags[i] & 1) ? 1.f : 0.f;
+    hv += (flags[i] & 2) ? 1.f : 0.f;
+  }
+  s = block_sum(s, red);
+  hv = block_sum(hv, red);
+  vv = block_sum(vv, red);
+  if (threadIdx.x == 0) {
+    out[0] = s;
+    out[1] = hv / fmaxf(vv, 1.f);
+  }
+}
+
+// dlogits[row][c] = gscale * (exp(l - lse) - [c == tgt])
+__global__ void ce_bwd_kernel(const float* __restrict__ logits, int ld, const long long* __restrict__ tgt,
+                              const float* __restrict__ lse, const float* __restrict__ gscale, float* __restrict__ dl, int lddl,
+                              int rows, int V) {
+  const float gs = gscale[0];
+  const long long n = (long long)rows * V;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    int c = (int)(i % V);
+    int r = (int)(i / V);
+    float p = expf(logits[(size_t)r * ld + c] - lse[r]);
+    dl[(size_t)r * lddl + c] = gs * (p - ((long long)c == tgt[r] ? 1.f : 0.f));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ScaledAdam.  chunk table: [nchunks][3] = (tensor id, begin, count) over the flat arenas.
+__global__ void sadam_reduce_kernel(const float* __restrict__ p, const float* __restrict__ g, const long long* __restrict__ chunks,
+                                    float gscale, float* __restrict__ stats) {
+  __shared__ float red[33];
+  const long long* ch = chunks + (size_t)blockIdx.x * 3;
+  const int t = (int)ch[0];
+  const long long beg = ch[1], cnt = ch[2];
+  float pp = 0.f, pg = 0.f, gg = 0.f;
+  for (long long i = threadIdx.x; i < cnt; i += blockDim.x) {
+    float pv = p[beg + i], gv = g[beg + i] * gscale;
+    pp += pv * pv; pg += pv * gv; gg += gv * gv;
+  }
+  pp = block_sum(pp, red);
+  pg = block_sum(pg, red);
+  gg = block_sum(gg, red);
+  if (threadIdx.x == 0) {
+    atomicAdd(stats + t * 3 + 0, pp);
+    atomicAdd(stats + t * 3 + 1, pg);
+    atomicAdd(stats + t * 3 + 2, gg);
+  }
+}
+
+struct SadamCfg {
+  float b1, b2, clip, slr, eps, rmin, rmax;
+  int period, sup;
+};
+
+__global__ void __launch_bounds__(1024) sadam_scalars_kernel(int nt, const long long* __restrict__ numel, float* __restrict__ stats,
+                                                             float* __restrict__ rms, float* __restrict__ sv,
+                                                             float* __restrict__ sg, float* __restrict__ coef,
+                                                             const float* __restrict__ hyper, long long* __restrict__ stepbuf,
+                                                             float* __restrict__ norms, float* __restrict__ thr,
+                                                             float* __restrict__ glob, SadamCfg c) {
+  __shared__ float red[33];
+  __shared__ float srt[1024];
+  __shared__ float s_cs;
+  const long long step = stepbuf[0];
+  const float lr = hyper[0];
+  if (step == 0)
+    for (int t = threadIdx.x; t < nt; t += blockDim.x)
+      if (numel[t] > 1) rms[t] = sqrtf(stats[t * 3] / (float)numel[t]);      // _init_state
+  __syncthreads();
+  float tot = 0.f;
+  for (int t = threadIdx.x; t < nt; t += blockDim.x) tot += (numel[t] > 1 ? rms[t] * rms[t] : 1.f) * stats[t * 3 + 2];
+  tot = block_sum(tot, red);
+  if (threadIdx.x == 0) s_cs = 1.f;
+  __syncthreads();
+  if (c.clip > 0.f && step > 0) {
+    const float tot_norm = sqrtf(tot);
+    if (threadIdx.x == 0) norms[step % c.period] = tot_norm;
+    __syncthreads();
+    if (step % c.period == 0) {
+      srt[threadIdx.x] = (int)threadIdx.x < c.period ? norms[threadIdx.x] : INFINITY;
+      __syncthreads();
+      for (int k = 2; k <= 1024; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+          int i = threadIdx.x, ixj = i ^ j;
+          if (ixj > i) {
+            bool up = (i & k) == 0;
+            float a = srt[i], b = srt[ixj];
+            if ((a > b) == up) { srt[i] = b; srt[ixj] = a; }
+          }
+          __syncthreads();
+        }
+      if (threadIdx.x == 0) {
+        int idx = min(c.period - 1, (c.period / 4) * 2);
+        thr[0] = c.clip * srt[idx];
+        thr[1] = 1.f;
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0 && step >= c.period && thr[1] != 0.f) s_cs = fminf(1.f, thr[0] / (tot_norm + 1e-20f));
+    __syncthreads();
+  }
+  const float cs = s_cs;
+  const int slot = (int)(step % c.sup);
+  for (int t = threadIdx.x; t < nt; t += blockDim.x) {
+    if (numel[t] > 1) {
+      sg[slot * nt + t] = cs * stats[t * 3 + 1];
+      float sstep = 0.f;
+      if (slot == c.sup - 1) {
+        const float r = sqrtf(stats[t * 3] / (float)numel[t]);
+        rms[t] = r;
+        if (step > 0) {
+          const double b2c = pow((double)c.b2, (double)c.sup);
+          float msq = 0.f, ssum = 0.f;
+          for (int k = 0; k < c.sup; ++k) { float v = sg[k * nt + t]; msq += v * v; ssum += v; }
+          msq /= (float)c.sup;
+          const float nv = sv[t] * (float)b2c + msq * (float)(1.0 - b2c);
+          sv[t] = nv;
+          const long long size_step = (step + 1) / c.sup;
+          const double bc = 1.0 - pow(b2c, (double)size_step);
+          sstep = -(lr * c.slr) * (float)sqrt(bc) * ssum / (sqrtf(nv) + c.eps);
+          if (r < c.rmin) sstep = 0.f;
+          if (r > c.rmax) sstep = -(lr * c.slr) * (float)c.sup;
+        }
+      }
+      coef[t * 2 + 0] = -lr * (1.f - c.b1) * fmaxf(rms[t], c.rmin);
+      coef[t * 2 + 1] = sstep * (1.f - c.b1);
+    } else {
+      coef[t * 2 + 0] = -(lr * c.slr) * (1.f - c.b1);
+      coef[t * 2 + 1] = 0.f;
+    }
+    stats[t * 3 + 0] = 0.f; stats[t * 3 + 1] = 0.f; stats[t * 3 + 2] = 0.f;
+  }
+  if (threadIdx.x == 0) {
+    const double bc2 = 1.0 - pow((double)c.b2, (double)(step + 1));
+    glob[0] = bc2 < 0.99 ? (float)(1.0 / bc2) : 1.f;
+    glob[1] = (float)(1.0 / bc2);
+    glob[2] = cs;
+    stepbuf[0] = step + 1;
+  }
+}
+
+__global__ void sadam_update_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ delta, float* __restrict__ v,
+                                    const long long* __restrict__ chunks, const long long* __restrict__ numel,
+                                    const float* __restrict__ coef, const float* __restrict__ glob, float gscale, float b1,
+                                    float b2, float eps, float smax, int zero_grad) {
+  const long long* ch = chunks + (size_t)blockIdx.x * 3;
+  const int t = (int)ch[0];
+  const long long beg = ch[1], cnt = ch[2];
+  const float alpha = coef[t * 2], sstep = coef[t * 2 + 1];
+  const bool scalar = numel[t] == 1;
+  const float vs = scalar ? glob[1] : glob[0];
+  for (long long i = threadIdx.x; i < cnt; i += blockDim.x) {
+    const long long e = beg + i;
+    const float gv = g[e] * gscale;
+    float pv = p[e];
+    float d = delta[e] * b1;
+    if (!scalar) d += sstep * pv;
+    const float vv = v[e] * b2 + (1.f - b2) * gv * gv;
+    v[e] = vv;
+    d += alpha * gv / (sqrtf(vv * vs) + eps);
+    if (scalar) pv = fminf(fmaxf(pv, -smax), smax);
+    delta[e] = d;
+    p[e] = pv + d;
+    if (zero_grad) g[e] = 0.f;
+  }
+}
+
+}  // namespace
+}  // namespace evk
+
+using namespace evk;
+
+extern "C" int evk_sinepos_add(const float* x, int ldx, int64_t x_sb, const float* pe, int ldpe, const float* alpha, float* y,
+                               int ldy, int64_t y_sb, int B, int T, int D, cudaStream_t st) {
+  EVK_REQUIRE(D % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0 && ldpe % 4 == 0 && x_sb % 4 == 0 && y_sb % 4 == 0, EVK_ERR_ARG,
+              "sinepos_add: D and pitches must be multiples of 4");
+  if (B * T == 0) return 0;
+  long long n = (long long)B * T * (D / 4);
+  sinepos_add_kernel<<<(int)min((long long)148 * 8, (n + 255) / 256), 256, 0, st>>>(x, ldx, x_sb, pe, ldpe, alpha, y, ldy, y_sb, B, T, D);
+  return check_launch("sinepos_add");
+}
+
+extern "C" int evk_sinepos_bwd(const float* dy, int ldy, int64_t dy_sb, const float* pe, int ldpe, float* dalpha, int B, int T,
+                               int D, cudaStream_t st) {
+  if (B * T == 0) return 0;
+  long long n = (long long)B * T * D;
+  sinepos_bwd_kernel<<<(int)min((long long)148 * 4, (n + 255) / 256), 256, 0, st>>>(dy, ldy, dy_sb, pe, ldpe, dalpha, B, T, D);
+  return check_launch("sinepos_bwd");
+}
+
+extern "C" int evk_ce_fwd(const float* logits, int ld, const int64_t* targets, int rows, int V, int topk, int64_t ignore_index,
+                          float* lse, float* nll, uint8_t* flags, float* out2, cudaStream_t st) {
+  EVK_REQUIRE(rows > 0 && V > 0, EVK_ERR_ARG, "ce_fwd: empty");
+  ce_fwd_kernel<<<cdiv(rows, 8), 256, 0, st>>>(logits, ld, (const long long*)targets, rows, V, topk, ignore_index, lse, nll, flags);
+  if (int rc = check_launch("ce_fwd")) return rc;
+  ce_finalize_kernel<<<1, 1024, 0, st>>>(nll, flags, rows, out2);
+  return check_launch("ce_finalize");
+}
+
+extern "C" int evk_ce_bwd(const float* logits, int ld, const int64_t* targets, const float* lse, const float* gscale, float* dl,
+                          int lddl, int rows, int V, cudaStream_t st) {
+  long long n = (long long)rows * V;
+  ce_bwd_kernel<<<(int)min((long long)148 * 16, (n + 255) / 256), 256, 0, st>>>(logits, ld, (const long long*)targets, lse, gscale, dl, lddl, rows, V);
+  return check_launch("ce_bwd");
+}
+
+extern "C" int evk_scaled_adam(float* p, float* g, float* delta, float* v, const int64_t* chunks, int nchunks,
+                               const int64_t* numel, int nt, float* stats, float* rms, float* sv, float* sg, float* coef,
+                               const float* hyper, int64_t* stepbuf, float* norms, float* thr, float* glob, float gscale,
+                               float beta1, float beta2, float clipping_scale, int clipping_update_period, float scalar_lr_scale,
+                               float eps, float param_min_rms, float param_max_rms, float scalar_max, int size_update_period,
+                               int zero_grad, cudaStream_t st) {
+  EVK_REQUIRE(nt > 0 && nchunks > 0, EVK_ERR_ARG, "scaled_adam: empty");
+  EVK_REQUIRE(clipping_update_period >= 1 && clipping_update_period <= 1024, EVK_ERR_UNSUPPORTED,
+              "scaled_adam: clipping_update_period %d > 1024", clipping_update_period);
+  EVK_REQUIRE(size_update_period >= 1 && size_update_period <= 16, EVK_ERR_UNSUPPORTED, "scaled_adam: size_update_period");
+  SadamCfg c{beta1, beta2, clipping_scale, scalar_lr_scale, eps, param_min_rms, param_max_rms, clipping_update_period,
+             size_update_period};
+  sadam_reduce_kernel<<<nchunks, 256, 0, st>>>(p, g, (const long long*)chunks, gscale, stats);
+  if (int rc = check_launch("sadam_reduce")) return rc;
+  sadam_scalars_kernel<<<1, 1024, 0, st>>>(nt, (const long long*)numel, stats, rms, sv, sg, coef, hyper, (long long*)stepbuf, norms, thr, glob, c);
+  if (int rc = check_launch("sadam_scalars")) return rc;
+  sadam_update_kernel<<<nchunks, 256, 0, st>>>(p, g, delta, v, (const long long*)chunks, (const long long*)numel, coef, glob, gscale, beta1, beta2, eps, scalar_max,
+                                               zero_grad);
+  return check_launch("sadam_update");
+}

@@ -1289,3 +1289,128 @@ def adamw_flat(p, g, m, v, hyper, lr_scale, betas, eps, wd, grad_scale=1.0, gnor
 
 def scalar_add(x, v):
     _call("evk_scalar_add", _p(x), ctypes.c_float(v))
+
+
+# ------------------------------------------------------------------------------------------------
+# stage-1 AR GPT (t2s_model.py:431-490)
+# ------------------------------------------------------------------------------------------------
+class _FlashAttnFn(torch.autograd.Function):
+    """fused prefix-LM self-attention on the packed in_proj output qkv [B, L, 3D]."""
+
+    @staticmethod
+    def forward(ctx, qkv, cfg):
+        H, X, xlen, ylen, scale_, p_drop, sid = cfg
+        qkv = qkv.contiguous()
+        B, Lq, D3 = qkv.shape
+        D = D3 // 3
+        dk = D // H
+        out = torch.empty((B, Lq, D), device=qkv.device, dtype=torch.float32)
+        lse = torch.empty((B * H, Lq), device=qkv.device, dtype=torch.float32)
+        base = qkv.data_ptr()
+        _call("evk_flash_attn_fwd", base, base + 4 * D, base + 8 * D, D3, _p(out), D, _p(lse), B, H, Lq, X, dk, _p(xlen), _p(ylen),
+              ctypes.c_float(scale_), ctypes.c_float(p_drop), _p(rng_state(qkv.device)), ctypes.c_uint64(sid))
+        ctx.cfg = cfg
+        ctx.save_for_backward(qkv, out, lse)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        H, X, xlen, ylen, scale_, p_drop, sid = ctx.cfg
+        qkv, out, lse = ctx.saved_tensors
+        B, Lq, D3 = qkv.shape
+        D = D3 // 3
+        dk = D // H
+        dout = dout.contiguous()
+        dqkv = torch.empty_like(qkv)
+        delta = torch.empty_like(lse)
+        base, dbase = qkv.data_ptr(), dqkv.data_ptr()
+        _call("evk_flash_attn_bwd", base, base + 4 * D, base + 8 * D, D3, _p(out), D, _p(lse), _p(dout), D, _p(delta),
+              dbase, dbase + 4 * D, dbase + 8 * D, D3, B, H, Lq, X, dk, _p(xlen), _p(ylen), ctypes.c_float(scale_),
+              ctypes.c_float(p_drop), _p(rng_state(qkv.device)), ctypes.c_uint64(sid))
+        return dqkv, None
+
+
+def flash_attention(qkv, *, heads, prefix, xlen, ylen, p_drop=0.0, tag="gpt.attn"):
+    """softmax(q k^T / sqrt(dk) + prefix-LM mask) v with optional probability dropout; qkv = in_proj(x) [B, L, 3D]."""
+    dk = qkv.shape[-1] // 3 // heads
+    cfg = (heads, int(prefix), xlen, ylen, 1.0 / math.sqrt(dk), float(p_drop), stream_id(tag))
+    return _FlashAttnFn.apply(qkv, cfg)
+
+
+class _GptEmbedFn(torch.autograd.Function):
+    """h = cat([xe + ax * pe[:X], ye + ay * pe[:Y]], dim=1)  (embedding.py:71-81 twice + t2s_model.py:462)."""
+
+    @staticmethod
+    def forward(ctx, xe, ye, ax, ay, pe):
+        xe, ye = xe.contiguous(), ye.contiguous()
+        B, X, D = xe.shape
+        Y = ye.shape[1]
+        Lq = X + Y
+        h = torch.empty((B, Lq, D), device=xe.device, dtype=torch.float32)
+        _call("evk_sinepos_add", _p(xe), D, X * D, _p(pe), D, _p(ax), h.data_ptr(), D, Lq * D, B, X, D)
+        _call("evk_sinepos_add", _p(ye), D, Y * D, _p(pe), D, _p(ay), h.data_ptr() + 4 * X * D, D, Lq * D, B, Y, D)
+        ctx.save_for_backward(pe)
+        ctx.k = (B, X, Y, D)
+        return h
+
+    @staticmethod
+    def backward(ctx, dh):
+        (pe,) = ctx.saved_tensors
+        B, X, Y, D = ctx.k
+        dh = dh.contiguous()
+        Lq = X + Y
+        da = torch.zeros(2, device=dh.device, dtype=torch.float32)
+        _call("evk_sinepos_bwd", dh.data_ptr(), D, Lq * D, _p(pe), D, da.data_ptr(), B, X, D)
+        _call("evk_sinepos_bwd", dh.data_ptr() + 4 * X * D, D, Lq * D, _p(pe), D, da.data_ptr() + 4, B, Y, D)
+        return dh[:, :X], dh[:, X:], da[0:1], da[1:2], None
+
+
+def gpt_embed(xe, ye, alpha_x, alpha_y, pe):
+    return _GptEmbedFn.apply(xe, ye, alpha_x, alpha_y, pe)
+
+
+class _CeFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, targets, topk, ignore, V):
+        logits = _cl(logits)
+        rows, Vp, ld = _rows(logits)
+        targets = targets.contiguous()
+        dev = logits.device
+        lse = torch.empty(rows, device=dev, dtype=torch.float32)
+        nll = torch.empty(rows, device=dev, dtype=torch.float32)
+        flags = torch.empty(rows, device=dev, dtype=torch.uint8)
+        out2 = torch.empty(2, device=dev, dtype=torch.float32)
+        _call("evk_ce_fwd", _p(logits), ld, _p(targets), rows, V, topk, ignore, _p(lse), _p(nll), _p(flags), _p(out2))
+        ctx.save_for_backward(logits, targets, lse)
+        ctx.V = V
+        ctx.mark_non_differentiable(out2)
+        return out2[0].clone(), out2
+
+    @staticmethod
+    def backward(ctx, gloss, _g2):
+        logits, targets, lse = ctx.saved_tensors
+        rows, Vp, ld = _rows(logits)
+        V = ctx.V
+        gl = gloss.reshape(1).contiguous().float()
+        dl = (torch.empty if Vp == V else torch.zeros)(logits.shape, device=logits.device, dtype=torch.float32)
+        _call("evk_ce_bwd", _p(logits), ld, _p(targets), _p(lse), _p(gl), _p(dl), Vp, rows, V)
+        return dl, None, None, None, None
+
+
+def ce_sum_topk(logits, targets, topk=3, ignore_index=1024, V=None):
+    """-> (sum cross-entropy (differentiable), device float32 [2] = (loss, top-k accuracy ignoring ignore_index)).
+    V: number of real classes when the last dim of `logits` is zero-padded."""
+    loss, out2 = _CeFn.apply(logits, targets, int(topk), int(ignore_index), int(V or logits.shape[-1]))
+    return loss, out2
+
+
+def scaled_adam(st, gscale=1.0, zero_grad=True):
+    """one ScaledAdam update over the arenas held by `st` (train/gpt_step.FlatScaledAdam)."""
+    c = st.cfg
+    _call("evk_scaled_adam", _p(st.flat_p), _p(st.flat_g), _p(st.flat_delta), _p(st.flat_v), _p(st.chunks), st.chunks.shape[0],
+          _p(st.numel), st.numel.shape[0], _p(st.stats), _p(st.rms), _p(st.sv), _p(st.sg), _p(st.coef), _p(st.hyper),
+          _p(st.stepbuf), _p(st.norms), _p(st.thr), _p(st.glob), ctypes.c_float(gscale), ctypes.c_float(c["betas"][0]),
+          ctypes.c_float(c["betas"][1]), ctypes.c_float(c["clipping_scale"]), int(c["clipping_update_period"]),
+          ctypes.c_float(c["scalar_lr_scale"]), ctypes.c_float(c["eps"]), ctypes.c_float(c["param_min_rms"]),
+          ctypes.c_float(c["param_max_rms"]), ctypes.c_float(c["scalar_max"]), int(c["size_update_period"]),
+          1 if zero_grad else 0)

@@ -251,6 +251,50 @@ int evk_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n,
                    float* gnorm_sq /* nullable, += */, evk_stream_t stream);
 int evk_scalar_add(float* x, float v, evk_stream_t stream);   /* x[0] += v (device-side step counters) */
 
+/* ------------------------------------------------------------------------------------------
+ * Stage-1 AR semantic-token GPT (t2s_model.py:431-490 forward_old, transformer.py:266-315, optim.py:123-622).
+ * Linear layers / LayerNorm / embedding / dropout reuse the entry points above.
+ * ------------------------------------------------------------------------------------------ */
+/* Fused prefix-LM attention, head dim 32.  q/k/v: [B, L, ld] with head h at columns h*32.. (three column blocks of the
+ * in_proj output).  Key j is visible to query i iff (j < X ? j < xlen[b] : (j - X < ylen[b] && j <= i)), which is the
+ * mask built at t2s_model.py:456-479; scores and mask are never materialised.  lse: [B*H, L] (log2 domain) is saved for
+ * the backward.  p_drop applies to the probabilities as F.scaled_dot_product_attention(dropout_p) does; the keep mask is
+ * a counter hash of (rng[0]=seed, rng[1]=offset, sid, b, h, i, j), regenerated in the backward. */
+int evk_flash_attn_fwd(const float* q, const float* k, const float* v, int32_t ld, float* o, int32_t ldo, float* lse, int32_t B,
+                       int32_t H, int32_t L, int32_t X, int32_t dk, const int64_t* xlen, const int64_t* ylen, float scale,
+                       float p_drop, const uint64_t* rng, uint64_t sid, evk_stream_t stream);
+/* delta: [B*H, L] scratch (written).  dq/dk/dv: [B, L, lddq] (+ h*32), every element written. */
+int evk_flash_attn_bwd(const float* q, const float* k, const float* v, int32_t ld, const float* o, int32_t ldo,
+                       const float* lse, const float* dout, int32_t lddo, float* delta, float* dq, float* dk, float* dv,
+                       int32_t lddq, int32_t B, int32_t H, int32_t L, int32_t X, int32_t dkdim, const int64_t* xlen,
+                       const int64_t* ylen, float scale, float p_drop, const uint64_t* rng, uint64_t sid, evk_stream_t stream);
+/* SinePositionalEmbedding with learnable alpha (embedding.py:36-81): y[b][t] = x[b][t] + alpha[0] * pe[t]; *_sb are batch
+ * strides in floats so y can be a row range of the concatenated [B, X+Y, D] sequence.  bwd: dalpha[0] += <dy, pe>. */
+int evk_sinepos_add(const float* x, int32_t ldx, int64_t x_sb, const float* pe, int32_t ldpe, const float* alpha, float* y,
+                    int32_t ldy, int64_t y_sb, int32_t B, int32_t T, int32_t D, evk_stream_t stream);
+int evk_sinepos_bwd(const float* dy, int32_t ldy, int64_t dy_sb, const float* pe, int32_t ldpe, float* dalpha, int32_t B,
+                    int32_t T, int32_t D, evk_stream_t stream);
+/* CrossEntropyLoss(reduction="sum") + MulticlassAccuracy(top_k, micro, ignore_index) (t2s_model.py:486-489).
+ * out2[0] = sum_r (lse_r - logit_r[target_r]); out2[1] = #hits / #valid, hit = fewer than top_k logits strictly above
+ * the target's.  lse/nll: [rows] scratch kept for the backward; flags: [rows] bytes.
+ * bwd: dl[r][c] = gscale[0] * (softmax(logits_r)[c] - [c == target_r]). */
+int evk_ce_fwd(const float* logits, int32_t ld, const int64_t* targets, int32_t rows, int32_t V, int32_t topk,
+               int64_t ignore_index, float* lse, float* nll, uint8_t* flags, float* out2, evk_stream_t stream);
+int evk_ce_bwd(const float* logits, int32_t ld, const int64_t* targets, const float* lse, const float* gscale, float* dl,
+               int32_t lddl, int32_t rows, int32_t V, evk_stream_t stream);
+/* ScaledAdam (optim.py:123-622) over flat arenas p/g/delta/v.  chunks: [nchunks][3] = (tensor id, begin, count), numel: [nt].
+ * Per-tensor state: rms, sv (scale_exp_avg_sq) [nt]; sg (scale_grads) [size_update_period][nt]; stats [nt][3] and
+ * coef [nt][2] are scratch (stats must be zero on first use; the call leaves it zero).  hyper: device [lr];
+ * stepbuf: device step counter (incremented); norms: [clipping_update_period]; thr: [2] = (threshold, valid);
+ * glob: [4] scratch (glob[2] = clipping scale of this step).  Gradients are read as g * gscale; zero_grad != 0 clears g.
+ * Three launches (per-tensor reductions, per-tensor scalars + median clipping, fused update); no host sync. */
+int evk_scaled_adam(float* p, float* g, float* delta, float* v, const int64_t* chunks, int32_t nchunks, const int64_t* numel,
+                    int32_t nt, float* stats, float* rms, float* sv, float* sg, float* coef, const float* hyper,
+                    int64_t* stepbuf, float* norms, float* thr, float* glob, float gscale, float beta1, float beta2,
+                    float clipping_scale, int32_t clipping_update_period, float scalar_lr_scale, float eps,
+                    float param_min_rms, float param_max_rms, float scalar_max, int32_t size_update_period,
+                    int32_t zero_grad, evk_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

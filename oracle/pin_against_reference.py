@@ -24,7 +24,7 @@ sys.path.insert(0, ROOT)
 REF = "/root/reference"
 GOLD = os.path.join(ROOT, "tests", "golden")
 
-from oracle import mel_oracle, s2_oracle  # noqa: E402
+from oracle import mel_oracle, s2_oracle, gpt_oracle  # noqa: E402
 
 warnings.filterwarnings("ignore")
 
@@ -206,6 +206,93 @@ def pin_s2(models, losses, commons):
             json.dump(gold, f, indent=1)
     return res
 
+def pin_gpt():
+    """Stage-1 AR GPT: forward_old loss/acc/grads and ScaledAdam trajectories vs the reference classes.
+
+    torchmetrics is absent from this image: MulticlassAccuracy(top_k=3, average="micro", ignore_index=EOS) is stubbed
+    with its published semantics (a sample counts when the target is among the k largest logits; samples whose target is
+    ignore_index are dropped), so the accuracy value is pinned against that restatement only.
+    """
+    tm = types.ModuleType("torchmetrics")
+    tmc = types.ModuleType("torchmetrics.classification")
+
+    class MulticlassAccuracy(torch.nn.Module):
+        def __init__(self, num_classes, top_k=1, average="micro", multidim_average="global", ignore_index=None):
+            super().__init__()
+            self.top_k, self.ignore_index = top_k, ignore_index
+
+        def forward(self, logits, target):                     # logits [B, V, T], target [B, T]
+            top = logits.topk(self.top_k, dim=1).indices
+            hit = (top == target.unsqueeze(1)).any(1)
+            valid = target != self.ignore_index
+            return (hit & valid).sum().float() / valid.sum().clamp(min=1).float()
+    tmc.MulticlassAccuracy = MulticlassAccuracy
+    tm.classification = tmc
+    sys.modules["torchmetrics"] = tm
+    sys.modules["torchmetrics.classification"] = tmc
+    from src.easevoice.soundstorm.auto_reg.models.t2s_model import Text2SemanticDecoder
+    from src.easevoice.soundstorm.auto_reg.modules.optim import ScaledAdam
+    res = {}
+    for tag, nl, B, X, Y, ragged in (("small", 3, 3, 12, 20, False), ("ragged", 2, 4, 9, 17, True)):
+        m = dict(gpt_oracle.GPT_MODEL, n_layer=nl)
+        ref = Text2SemanticDecoder({"model": m}).eval()        # eval: dropout off (parity configuration)
+        spec = gpt_oracle.gpt_param_spec(m)
+        sd = ref.state_dict()
+        assert {k: tuple(v.shape) for k, v in sd.items()} == spec, "state_dict contract"
+        P = gpt_oracle.init_params(spec, 11 + nl)
+        P["ar_text_position.alpha"].fill_(0.8); P["ar_audio_position.alpha"].fill_(1.3)
+        ref.load_state_dict(P)
+        x, xl, y, yl, bert = gpt_oracle.synthetic_gpt_batch(B, X, Y, 5, ragged)
+        loss_r, acc_r = ref.forward_old(x, xl, y, yl, bert)
+        loss_r.backward()
+        g_ref = {k: p.grad.clone() for k, p in ref.named_parameters()}
+        Pq = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+        loss_o, acc_o, logits, targets = gpt_oracle.forward_old(Pq, x, xl, y, yl, bert, m)
+        loss_o.backward()
+        dl = abs(float(loss_r) - float(loss_o)) / abs(float(loss_r))
+        da = abs(float(acc_r) - float(acc_o))
+        dg = max(maxdiff(g_ref[k], Pq[k].grad) / (float(g_ref[k].abs().max()) + 1e-12) for k in g_ref)
+        assert dl < 1e-5 and da < 1e-6 and dg < 2e-4, (tag, dl, da, dg)
+        res[tag] = {"loss_rel": dl, "acc_abs": da, "grad_rel_max": dg}
+        gold = {"model": m, "B": B, "X": X, "Y": Y, "ragged": ragged, "param_seed": 11 + nl, "batch_seed": 5,
+                "alpha_text": 0.8, "alpha_audio": 1.3, "loss": float(loss_r), "acc": float(acc_r),
+                "targets_sum": int(targets.sum()),
+                "grad_norms": {k: float(g_ref[k].norm()) for k in
+                               ("bert_proj.weight", "ar_text_position.alpha", "ar_audio_position.alpha",
+                                "ar_audio_embedding.word_embeddings.weight", "h.layers.0.self_attn.in_proj_weight",
+                                "h.layers.1.linear2.weight", "h.layers.1.norm2.bias", "ar_predict_layer.weight")}}
+        with open(os.path.join(GOLD, f"gpt_{tag}.json"), "w") as f:
+            json.dump(gold, f, indent=1)
+    # ---- ScaledAdam: 14 steps on a small mixed set (matrix, vector, scalar, tiny-rms tensor), lr 0.01 then 0.002
+    g = torch.Generator().manual_seed(3)
+    shapes = [(6, 5), (7,), (1,), (4, 3), (2, 3, 2)]
+    init = [torch.randn(s, generator=g) * sc for s, sc in zip(shapes, (1.0, 0.5, 1.0, 1e-6, 4.0))]
+    pr = [torch.nn.Parameter(t.clone()) for t in init]
+    opt = ScaledAdam(pr, lr=0.01, betas=(0.9, 0.95), clipping_scale=2.0, parameters_names=[[f"p{i}" for i in range(len(pr))]],
+                     show_dominant_parameters=False, clipping_update_period=8)
+    po = [t.clone() for t in init]
+    oo = gpt_oracle.ScaledAdamOracle(po, lr=0.01, clipping_update_period=8)
+    traj = []
+    worst = 0.0
+    for it in range(30):
+        grads = [torch.randn(s, generator=g) * (5.0 if it in (20, 27) else 1.0) for s in shapes]
+        for p, gr in zip(pr, grads):
+            p.grad = gr.clone()
+        opt.step()
+        oo.step(grads)
+        if it == 0:
+            for grp in opt.param_groups:
+                grp["lr"] = 0.002
+            oo.lr = 0.002
+        worst = max(worst, max(maxdiff(a.data, b) / (float(a.data.abs().max()) + 1e-12) for a, b in zip(pr, po)))
+        traj.append([float(p.data.double().norm()) for p in pr])
+    assert worst < 2e-6, worst
+    res["scaled_adam_rel_max"] = worst
+    with open(os.path.join(GOLD, "scaled_adam.json"), "w") as f:
+        json.dump({"shapes": shapes, "scales": [1.0, 0.5, 1.0, 1e-6, 4.0], "seed": 3, "steps": 30, "big_grad_steps": [20, 27],
+                   "clipping_update_period": 8, "lr_first": 0.01, "lr_rest": 0.002, "param_norms": traj}, f, indent=1)
+    return res
+
 
 def main():
     os.makedirs(GOLD, exist_ok=True)
@@ -215,6 +302,7 @@ def main():
     print(json.dumps(report, indent=1))
     mp.mel_basis.clear()  # see pin_mel: the reference's filterbank cache is not keyed by sampling rate
     report["s2"] = pin_s2(models, losses, commons)
+    report["gpt"] = pin_gpt()
     with open(os.path.join(GOLD, "pin_report.json"), "w") as f:
         json.dump(report, f, indent=1)
     print("PIN OK")

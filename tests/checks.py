@@ -21,7 +21,7 @@ import torch.nn.functional as F
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from oracle import mel_oracle, s2_oracle  # noqa: E402  (checker only)
+from oracle import mel_oracle, s2_oracle, gpt_oracle  # noqa: E402  (checker only)
 
 TOL_TC = 3e-3
 TOL_F32 = 2e-5
@@ -514,5 +514,227 @@ def check_api_layouts():
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# stage-1 AR GPT
+# ------------------------------------------------------------------------------------------------
+def _sdpa_oracle(qkv, H, X, xl, yl, keep=None, p=0.0):
+    """reference attention core on CPU: mask of t2s_model.py:456-479, softmax, optional given dropout keep-mask."""
+    B, L, D3 = qkv.shape
+    D = D3 // 3
+    dk = D // H
+    q, k, v = [t.view(B, L, H, dk).transpose(1, 2) for t in qkv.split(D, dim=-1)]
+    mask = gpt_oracle.prefix_lm_mask(xl, yl, X, L - X)
+    add = torch.zeros(mask.shape).masked_fill(mask, float("-inf")).unsqueeze(1)
+    P = torch.softmax(q @ k.transpose(-2, -1) / math.sqrt(dk) + add, dim=-1)
+    if keep is not None:
+        P = P * keep / (1.0 - p)
+    return (P @ v).transpose(1, 2).reshape(B, L, D)
+
+
+def check_gpt_kernels():
+    from easevoice_trainer_b200 import ops
+    out = []
+    # ---- fused prefix-LM attention, no dropout: forward + all three gradients, ragged lens, L not a tile multiple
+    for tag, B, H, X, Y, seed in (("small", 2, 2, 7, 30, 1), ("tiles", 2, 3, 70, 150, 2), ("x-only-tail", 1, 1, 64, 1, 3)):
+        g = _gen(seed)
+        L, D = X + Y, H * 32
+        qkv = torch.randn(B, L, 3 * D, generator=g)
+        xl = torch.randint(max(X // 2, 1), X + 1, (B,), generator=g); xl[0] = X
+        yl = torch.randint(max(Y // 2, 1), Y + 1, (B,), generator=g); yl[0] = Y
+        go = torch.randn(B, L, D, generator=g)
+        qr = qkv.clone().requires_grad_(True)
+        o_ref = _sdpa_oracle(qr, H, X, xl, yl)
+        o_ref.backward(go)
+        qd = qkv.to(DEV).requires_grad_(True)
+        o = ops.flash_attention(qd, heads=H, prefix=X, xlen=xl.to(DEV), ylen=yl.to(DEV))
+        o.backward(go.to(DEV))
+        out.append((f"flash {tag} out", rel(o, o_ref), TOL_TC))
+        gq, gk, gv = qd.grad.cpu().split(D, dim=-1)
+        rq, rk, rv = qr.grad.split(D, dim=-1)
+        out.append((f"flash {tag} dq", rel(gq, rq), TOL_TC * 2))
+        out.append((f"flash {tag} dk", rel(gk, rk), TOL_TC * 2))
+        out.append((f"flash {tag} dv", rel(gv, rv), TOL_TC * 2))
+    # ---- dropout: recover the keep mask with V = I (L = 32 keys, dk = 32), then check fwd/bwd against the oracle given it
+    B, H, X, Y, p = 2, 2, 12, 20, 0.25
+    L, D = 32, 64
+    g = _gen(9)
+    ops.manual_seed(77)
+    qkv = torch.randn(B, L, 3 * D, generator=g)
+    xl, yl = torch.tensor([12, 9]), torch.tensor([20, 13])
+    probe = qkv.clone()
+    probe[:, :, 2 * D:] = torch.eye(32).repeat(1, H)[None]
+    pd = ops.flash_attention(probe.to(DEV), heads=H, prefix=X, xlen=xl.to(DEV), ylen=yl.to(DEV), p_drop=p, tag="chk.drop").cpu()
+    pd = pd.view(B, L, H, 32).transpose(1, 2)                                   # [B,H,i,j] = dropped probabilities
+    p0 = ops.flash_attention(probe.to(DEV), heads=H, prefix=X, xlen=xl.to(DEV), ylen=yl.to(DEV)).cpu().view(B, L, H, 32).transpose(1, 2)
+    vis = p0 > 1e-6
+    keep = (pd != 0) | ~vis
+    frac = float(((pd == 0) & vis).sum()) / float(vis.sum())
+    out.append(("flash dropout drop-fraction vs p", abs(frac - p), 0.05))
+    out.append(("flash dropout kept values = P/(1-p)", rel(pd[keep & vis], (p0 / (1 - p))[keep & vis]), TOL_TC))
+    go = torch.randn(B, L, D, generator=g)
+    qr = qkv.clone().requires_grad_(True)
+    o_ref = _sdpa_oracle(qr, H, X, xl, yl, keep.float(), p)
+    o_ref.backward(go)
+    qd = qkv.to(DEV).requires_grad_(True)
+    o = ops.flash_attention(qd, heads=H, prefix=X, xlen=xl.to(DEV), ylen=yl.to(DEV), p_drop=p, tag="chk.drop")
+    o.backward(go.to(DEV))
+    out.append(("flash dropout out (same mask)", rel(o, o_ref), TOL_TC))
+    out.append(("flash dropout dqkv (mask regenerated in bwd)", rel(qd.grad, qr.grad), TOL_TC * 2))
+    # ---- sinusoid + alpha + concat
+    from easevoice_trainer_b200.models_gpt import sine_table
+    B, X, Y, D = 3, 5, 9, 64
+    xe, ye = torch.randn(B, X, D, generator=g), torch.randn(B, Y, D, generator=g)
+    ax, ay = torch.tensor([0.7]), torch.tensor([1.4])
+    pe = gpt_oracle.sine_pe(16, D)
+    out.append(("sine table == oracle", rel(sine_table(16, D), pe), 0.0))
+    ins = [t.clone().requires_grad_(True) for t in (xe, ye, ax, ay)]
+    ref = torch.cat([ins[0] + ins[2] * pe[:X], ins[1] + ins[3] * pe[:Y]], 1)
+    gh = torch.randn(B, X + Y, D, generator=g)
+    ref.backward(gh)
+    dins = [t.to(DEV).requires_grad_(True) for t in (xe, ye, ax, ay)]
+    h = ops.gpt_embed(*dins, pe.to(DEV))
+    h.backward(gh.to(DEV))
+    out.append(("gpt_embed h", rel(h, ref), TOL_F32))
+    for nm, a, b in zip(("dxe", "dye", "dalpha_x", "dalpha_y"), dins, ins):
+        out.append((f"gpt_embed {nm}", rel(a.grad, b.grad), TOL_F32))
+    # ---- CE(sum) + top-3 accuracy ignoring EOS, padded class dim
+    rows, V = 333, 1025
+    lg = torch.randn(rows, V, generator=g) * 3
+    tg = torch.randint(0, V, (rows,), generator=g); tg[::7] = 1024
+    for r in range(0, rows, 3):
+        lg[r, tg[r]] += 6.0
+    lr_ = lg.clone().requires_grad_(True)
+    loss_ref = F.cross_entropy(lr_, tg, reduction="sum")
+    (loss_ref * 0.5).backward()
+    top3 = lg.topk(3, dim=-1).indices
+    valid = tg != 1024
+    acc_ref = ((top3 == tg[:, None]).any(-1) & valid).sum().float() / valid.sum().float()
+    lp = torch.zeros(rows, 1028); lp[:, :V] = lg
+    ld_ = lp.to(DEV).requires_grad_(True)
+    loss, out2 = ops.ce_sum_topk(ld_, tg.to(DEV), 3, 1024, V=V)
+    (loss * 0.5).backward()
+    out.append(("ce loss sum", rel(loss, loss_ref), TOL_F32))
+    out.append(("ce top-3 acc (exact count)", abs(float(out2[1]) - float(acc_ref)), 1e-7))
+    out.append(("ce dlogits", rel(ld_.grad[:, :V], lr_.grad), TOL_F32))
+    out.append(("ce dlogits pad cols zero", float(ld_.grad[:, V:].abs().max()), 0.0))
+    return out
+
+
+def check_scaled_adam():
+    """30 steps on the pinned golden trajectory (tests/golden/scaled_adam.json, produced by the reference class)."""
+    from easevoice_trainer_b200.train.gpt_step import FlatScaledAdam
+    out = []
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "scaled_adam.json")))
+    g = _gen(gold["seed"])
+    shapes = [tuple(s) for s in gold["shapes"]]
+    init = [torch.randn(s, generator=g) * sc for s, sc in zip(shapes, gold["scales"])]
+    po = [t.clone() for t in init]
+    oo = gpt_oracle.ScaledAdamOracle(po, lr=gold["lr_first"], clipping_update_period=gold["clipping_update_period"])
+    params = [torch.nn.Parameter(t.clone().to(DEV)) for t in init]
+    opt = FlatScaledAdam([(f"p{i}", p) for i, p in enumerate(params)], lr=gold["lr_first"],
+                         clipping_update_period=gold["clipping_update_period"])
+    worst, worst_gold, cs_seen = 0.0, 0.0, 1.0
+    for it in range(gold["steps"]):
+        grads = [torch.randn(s, generator=g) * (5.0 if it in gold["big_grad_steps"] else 1.0) for s in shapes]
+        opt.accumulate([x.to(DEV) for x in grads])
+        opt.step()
+        cs = oo.step(grads)
+        cs_seen = min(cs_seen, float(cs))
+        if it == 0:
+            opt.set_lr(gold["lr_rest"]); oo.lr = gold["lr_rest"]
+        worst = max(worst, max(rel(a.data, b) for a, b in zip(params, po)))
+        worst_gold = max(worst_gold, max(abs(float(a.data.double().norm()) - n) / (n + 1e-12) for a, n in zip(params, gold["param_norms"][it])))
+    out.append(("scaled_adam 30-step trajectory vs oracle", worst, 2e-5))
+    out.append(("scaled_adam 30-step param norms vs reference golden", worst_gold, 2e-5))
+    out.append(("scaled_adam clipping engaged (cs < 1 seen)", 0.0 if cs_seen < 1.0 else 1.0, 0.5))
+    out.append(("scaled_adam grads zeroed", float(opt.flat_g.abs().max()), 0.0))
+    out.append(("scaled_adam step counter", abs(opt.step_count - gold["steps"]), 0))
+    return out
+
+
+def check_gpt(tag="small"):
+    """assembled forward_old + backward vs the oracle and the reference golden (dropout off), then 6 training_steps
+    (accumulate-4 + ScaledAdam) vs the oracle loop."""
+    from easevoice_trainer_b200.models_gpt import Text2SemanticDecoder
+    from easevoice_trainer_b200.train.gpt_step import GptStep
+    out = []
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", f"gpt_{tag}.json")))
+    m = gold["model"]
+    spec = gpt_oracle.gpt_param_spec(m)
+    P = gpt_oracle.init_params(spec, gold["param_seed"])
+    P["ar_text_position.alpha"].fill_(gold["alpha_text"]); P["ar_audio_position.alpha"].fill_(gold["alpha_audio"])
+    net = Text2SemanticDecoder({"model": m}, layer_dropout=0.0)
+    sd = net.state_dict()
+    out.append((f"gpt {tag} state_dict keys/shapes == reference", 0.0 if {k: tuple(v.shape) for k, v in sd.items()} == spec else 1.0, 0.0))
+    net.load_state_dict(P)
+    net = net.to(DEV)
+    x, xl, y, yl, bert = gpt_oracle.synthetic_gpt_batch(gold["B"], gold["X"], gold["Y"], gold["batch_seed"], gold["ragged"])
+    Pq = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    taps = {}
+    loss_o, acc_o, logits_o, tg_o = gpt_oracle.forward_old(Pq, x, xl, y, yl, bert, m, taps)
+    loss_o.backward()
+    loss, acc = net.forward_old(x.to(DEV), xl.to(DEV), y.to(DEV), yl.to(DEV), bert.to(DEV))
+    names = [n for n, _ in net.named_parameters()]
+    grads = torch.autograd.grad(loss, [p for _, p in net.named_parameters()])
+    y_in, tg = net.make_targets(y.to(DEV), yl.to(DEV))
+    out.append((f"gpt {tag} targets (pad_y_eos) exact", float((tg.cpu() != tg_o).sum()), 0.0))
+    out.append((f"gpt {tag} targets checksum == reference golden", abs(int(tg.sum()) - gold["targets_sum"]), 0))
+    out.append((f"gpt {tag} logits", rel(net.last_logits[..., :m["vocab_size"]].reshape(logits_o.shape), logits_o), TOL_TC * 3))
+    out.append((f"gpt {tag} loss vs oracle", abs(float(loss.detach()) - float(loss_o)) / abs(float(loss_o)), TOL_TC))
+    out.append((f"gpt {tag} loss vs reference golden", abs(float(loss.detach()) - gold["loss"]) / abs(gold["loss"]), TOL_TC))
+    out.append((f"gpt {tag} top-3 acc vs reference golden", abs(float(acc) - gold["acc"]), 2.0 / (gold["B"] * gold["Y"])))
+    worst, gl = 0.0, 0.0
+    num = den = 0.0
+    # d(alpha) = <dh, pe> projects the whole [B, L, D] gradient onto one direction (heavy cancellation): a relative
+    # perturbation eps of dh moves it by ~ eps * |dh| * rms(pe) in ABSOLUTE terms (rms(pe) = 1/sqrt 2), however small the
+    # result is.  So alpha is checked against the noise level measured on all the other tensors (4 sigma).
+    alpha_rows = []
+    for n, gk in zip(names, grads):
+        if n.endswith(".alpha"):
+            alpha_rows.append((n, abs(float(gk) - float(Pq[n].grad))))
+            continue
+        r = rel(gk, Pq[n].grad)
+        worst = max(worst, r)
+        num += float((gk.cpu().double() - Pq[n].grad.double()).pow(2).sum()); den += float(Pq[n].grad.double().pow(2).sum())
+        if n in gold["grad_norms"]:
+            gl = max(gl, abs(float(gk.norm()) - gold["grad_norms"][n]) / (gold["grad_norms"][n] + 1e-12))
+    alpha_tol = 4.0 * max(math.sqrt(num / den), 1e-4) * float(taps["h0"].grad.norm()) * math.sqrt(0.5)
+    for n, e in alpha_rows:
+        out.append((f"gpt {tag} d{n} (abs, projection-noise bound)", e, alpha_tol))
+    out.append((f"gpt {tag} grads worst tensor", worst, 2 * KINK_TOL))
+    out.append((f"gpt {tag} grads global", math.sqrt(num / den), KINK_TOL))
+    out.append((f"gpt {tag} grad norms vs reference golden", gl, 2e-2))
+    if tag == "small":
+        # 6 x training_step: update after batch_idx 4 only (5 accumulated micro-batches), lr 0.01 for that first update
+        step = GptStep(net)
+        Po = [v.detach().clone() for v in Pq.values()]
+        keys = list(Pq.keys())
+        oo = gpt_oracle.ScaledAdamOracle(Po, lr=0.01)
+        acc_g = [torch.zeros_like(v) for v in Po]
+        lo = []
+        for it in range(6):
+            xb, xlb, yb, ylb, bb = gpt_oracle.synthetic_gpt_batch(gold["B"], gold["X"], gold["Y"], 100 + it, it % 2 == 1)
+            Pr = {k: v.clone().requires_grad_(True) for k, v in zip(keys, Po)}
+            l_o = gpt_oracle.forward_old(Pr, xb, xlb, yb, ylb, bb, m)[0]
+            l_o.backward()
+            for a, k in zip(acc_g, keys):
+                a += Pr[k].grad
+            if it > 0 and it % 4 == 0:
+                oo.step(acc_g)
+                oo.lr = 0.002
+                acc_g = [torch.zeros_like(v) for v in Po]
+            l_d, _ = step.step(dict(phoneme_ids=xb.to(DEV), phoneme_ids_len=xlb.to(DEV), semantic_ids=yb.to(DEV),
+                                    semantic_ids_len=ylb.to(DEV), bert_feature=bb.to(DEV)))
+            lo.append(abs(float(l_d) - float(l_o)) / abs(float(l_o)))
+        out.append(("gpt 6 training_steps: loss track", max(lo), TOL_TC * 2))
+        out.append(("gpt 6 training_steps: exactly one optimizer step", abs(step.opt.step_count - 1), 0))
+        pw = max(rel(p.data, Po[keys.index(n)]) for n, p in net.named_parameters())
+        out.append(("gpt 6 training_steps: params vs oracle loop", pw, 2e-3))
+    return out
+
+
 ALL = [check_conv, check_conv_transpose, check_elementwise, check_attention, check_vq_losses_optim, check_mel,
-       lambda: check_s2("small"), lambda: check_s2("ragged"), check_api_layouts]
+       lambda: check_s2("small"), lambda: check_s2("ragged"), check_api_layouts,
+       check_gpt_kernels, check_scaled_adam, lambda: check_gpt("small"), lambda: check_gpt("ragged")]
+NAMES = ["conv", "conv_transpose", "elementwise", "attention", "vq_losses_optim", "mel", "s2_small", "s2_ragged", "api",
+         "gpt_kernels", "scaled_adam", "gpt_small", "gpt_ragged"]

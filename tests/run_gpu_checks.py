@@ -27,7 +27,7 @@ def main():
     L.evk_set_precise(1 if args.precise else 0)
     checks.PRECISE_MODE[0] = bool(args.precise)
     results, failed = [], 0
-    names = ["conv", "conv_transpose", "elementwise", "attention", "vq_losses_optim", "mel", "s2_small", "s2_ragged", "api"]
+    names = checks.NAMES
     for nm, fn in zip(names, checks.ALL):
         if args.only and args.only not in nm:
             continue

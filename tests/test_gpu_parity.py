@@ -4,7 +4,8 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-GROUPS = ["conv", "conv_transpose", "elementwise", "attention", "vq_losses_optim", "mel", "s2_small", "s2_ragged", "api"]
+GROUPS = ["conv", "conv_transpose", "elementwise", "attention", "vq_losses_optim", "mel", "s2_small", "s2_ragged", "api",
+          "gpt_kernels", "scaled_adam", "gpt_small", "gpt_ragged"]
 
 
 @pytest.fixture(scope="module")
@@ -39,3 +40,24 @@ def test_precise_mode_tightens_conv(evk):
     assert not bad, "\n".join(f"{n}: err={e:.3e}" for n, e in bad)
     lin = [e for n, e, t in rows if " y" in n[-3:]]
     assert max(lin) <= 1e-4, max(lin)
+
+
+def test_precise_mode_tightens_gpt(evk):
+    """3xTF32 in the fused attention + linear kernels: attention agrees with the fp32 oracle at fp32 level, and the
+    assembled GPT gradient error collapses (what remains are ReLU-kink flips)."""
+    from tests import checks
+    evk.evk_set_precise(1)
+    checks.PRECISE_MODE[0] = True
+    try:
+        rows = checks.check_gpt_kernels()
+        g_rows = checks.check_gpt("ragged")
+    finally:
+        evk.evk_set_precise(0)
+        checks.PRECISE_MODE[0] = False
+    flash = [(n, e) for n, e, t in rows if n.startswith("flash") and "drop-fraction" not in n]
+    bad = [(n, e) for n, e in flash if not e <= 2e-5]
+    assert not bad, bad
+    bad = [(n, e, t) for n, e, t in g_rows if not (e == e and e <= t)]
+    assert not bad, bad
+    glob = [e for n, e, t in g_rows if "grads global" in n][0]
+    assert glob <= 5e-3, glob
