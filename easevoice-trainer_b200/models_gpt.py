@@ -125,5 +125,5 @@ class Text2SemanticDecoder(ParamTree):
         Vp = (self.vocab_size + 3) // 4 * 4
         logits = ops.linear(hy, self.w("ar_predict_layer", pad0=Vp))
         loss, out2 = ops.ce_sum_topk(logits, tg.reshape(-1), self.top_k, self.EOS, V=self.vocab_size)
-        self.last_logits = logits
+        self.last_logits = logits.detach()        # detached: a retained graph would pin AccumulateGrad nodes to this stream
         return loss, out2[1]
