@@ -238,6 +238,14 @@ def run_ours(args):
     from easevoice_trainer_b200 import configs
     lib.init()
     trace("lib + process group up")
+    if args.only_gpt:
+        out = gpt_section(args, dev, rank, world)
+        if rank == 0:
+            emit(out)
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
     hps = configs.load_s2_config()
     torch.manual_seed(hps["train"]["seed"])
     net_g = models.SynthesizerTrn(hps["data"]["filter_length"] // 2 + 1, hps["train"]["segment_size"] // hps["data"]["hop_length"],
@@ -501,6 +509,7 @@ def main():
     ap.add_argument("--cpu-batch", type=int, default=2, help="utterances in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-torch-port", action="store_true")
+    ap.add_argument("--only-gpt", action="store_true", help="profiling aid: run just the stage-1 AR-GPT section and print its object")
     ap.add_argument("--gpt", type=int, default=1, help="1: also time the stage-1 AR-GPT step at N=1; 2: at every N; 0: skip")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
     args = ap.parse_args()

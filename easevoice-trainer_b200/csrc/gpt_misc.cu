@@ -94,15 +94,41 @@ __global__ void ce_finalize_kernel(const float* __restrict__ nll, const unsigned
 
 // dlogits[row][c] = gscale * (exp(l - lse) - [c == tgt])
 __global__ void ce_bwd_kernel(const float* __restrict__ logits, int ld, const long long* __restrict__ tgt,
-                              const float* __restrict__ lse, const float* __restrict__ gscale, float* __restrict__ dl, int lddl,
-                              int rows, int V) {
-  const float gs = gscale[0];
+                              const float* __restrict__ lse, const float* __restrict__ gscale, int rows_per_g,
+                              float* __restrict__ dl, int lddl, int rows, int V) {
   const long long n = (long long)rows * V;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     int c = (int)(i % V);
     int r = (int)(i / V);
     float p = expf(logits[(size_t)r * ld + c] - lse[r]);
-    dl[(size_t)r * lddl + c] = gs * (p - ((long long)c == tgt[r] ? 1.f : 0.f));
+    dl[(size_t)r * lddl + c] = gscale[r / rows_per_g] * (p - ((long long)c == tgt[r] ? 1.f : 0.f));
+  }
+}
+
+// DPO head (t2s_model.py:421-427, utils.py:160-192, reference_free, beta): A_b = -sum_t nll_c[b][t], R_b = -sum_t nll_r[b][t]
+//   loss_2 = mean_b softplus(-beta (A_b - R_b));   out3 = (loss_1 = sum nll_c, loss_2, loss_1 + loss_2)
+//   coef_c[b] = d total / d nll_c[b][t] = 1 + beta * sigmoid(-beta (A_b - R_b)) / B ;  coef_r[b] = -(coef_c[b] - 1)
+__global__ void dpo_head_kernel(const float* __restrict__ nll_c, int Yc, const float* __restrict__ nll_r, int Yr, int B, float beta,
+                                float* __restrict__ out3, float* __restrict__ coef_c, float* __restrict__ coef_r) {
+  __shared__ float red[33];
+  float l1 = 0.f, l2 = 0.f;
+  for (int b = 0; b < B; ++b) {
+    float sc = 0.f, sr = 0.f;
+    for (int t = threadIdx.x; t < Yc; t += blockDim.x) sc += nll_c[(size_t)b * Yc + t];
+    for (int t = threadIdx.x; t < Yr; t += blockDim.x) sr += nll_r[(size_t)b * Yr + t];
+    sc = block_sum(sc, red);
+    sr = block_sum(sr, red);
+    const float z = -beta * ((-sc) - (-sr));                 // -beta (A - R)
+    const float sp = z > 0.f ? z + log1pf(expf(-z)) : log1pf(expf(z));
+    const float sg = 1.f / (1.f + expf(-z));                 // sigmoid(-beta (A - R))
+    l1 += sc; l2 += sp;
+    if (threadIdx.x == 0) {
+      coef_c[b] = 1.f + beta * sg / (float)B;
+      coef_r[b] = -beta * sg / (float)B;
+    }
+  }
+  if (threadIdx.x == 0) {
+    out3[0] = l1; out3[1] = l2 / (float)B; out3[2] = l1 + l2 / (float)B;
   }
 }
 
@@ -279,10 +305,18 @@ extern "C" int evk_ce_fwd(const float* logits, int ld, const int64_t* targets, i
   return check_launch("ce_finalize");
 }
 
-extern "C" int evk_ce_bwd(const float* logits, int ld, const int64_t* targets, const float* lse, const float* gscale, float* dl,
-                          int lddl, int rows, int V, cudaStream_t st) {
+extern "C" int evk_dpo_head(const float* nll_c, int Yc, const float* nll_r, int Yr, int B, float beta, float* out3, float* coef_c,
+                            float* coef_r, cudaStream_t st) {
+  EVK_REQUIRE(B > 0 && Yc > 0 && Yr > 0, EVK_ERR_ARG, "dpo_head: empty");
+  dpo_head_kernel<<<1, 256, 0, st>>>(nll_c, Yc, nll_r, Yr, B, beta, out3, coef_c, coef_r);
+  return check_launch("dpo_head");
+}
+
+extern "C" int evk_ce_bwd(const float* logits, int ld, const int64_t* targets, const float* lse, const float* gscale,
+                          int rows_per_g, float* dl, int lddl, int rows, int V, cudaStream_t st) {
+  EVK_REQUIRE(rows_per_g > 0, EVK_ERR_ARG, "ce_bwd: rows_per_g");
   long long n = (long long)rows * V;
-  ce_bwd_kernel<<<(int)min((long long)148 * 16, (n + 255) / 256), 256, 0, st>>>(logits, ld, (const long long*)targets, lse, gscale, dl, lddl, rows, V);
+  ce_bwd_kernel<<<(int)min((long long)148 * 16, (n + 255) / 256), 256, 0, st>>>(logits, ld, (const long long*)targets, lse, gscale, rows_per_g, dl, lddl, rows, V);
   return check_launch("ce_bwd");
 }
 

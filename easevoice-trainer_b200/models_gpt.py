@@ -94,36 +94,77 @@ class Text2SemanticDecoder(ParamTree):
         tg = torch.nn.functional.pad(codes, (0, 1), value=0) + self.EOS * torch.nn.functional.pad(ymask, (0, 1), value=1)
         return tg[:, :-1].contiguous(), tg[:, 1:].contiguous()
 
-    def forward_old(self, x, x_lens, y, y_lens, bert_feature, targets=None, bert_channels_last=False):
-        """-> (loss, acc) like t2s_model.py:431-490; `loss` is differentiable, `acc` a device scalar.
-        bert_feature: [B, 1024, X] (reference layout), or [B, X, 1024] with bert_channels_last=True."""
-        B, X = x.shape
-        Y = y.shape[1]
-        D, H = self.model_dim, self.num_head
-        dev = x.device
-        x_lens, y_lens = x_lens.to(torch.int64).contiguous(), y_lens.to(torch.int64).contiguous()
-        bert_cl = bert_feature if bert_channels_last else ops.to_channels_last(bert_feature)
-        y_in, tg = self.make_targets(y, y_lens) if targets is None else targets
-        xe = ops.embedding(self.P("ar_text_embedding.word_embeddings.weight"), x.to(torch.int64))
-        xe = ops.linear(bert_cl, self.w("bert_proj", need_pb=False), self.b("bert_proj"), res=xe)
+    def _decode(self, xe, y_in, x_lens, y_lens, X, tagp=""):
+        """embedded text prefix + shifted semantic tokens -> padded logits [B, Y, Vp] (t2s_model.py:462-487)."""
+        B, Y = y_in.shape
+        D, H, dev = self.model_dim, self.num_head, xe.device
         ye = ops.embedding(self.P("ar_audio_embedding.word_embeddings.weight"), y_in)
         h = ops.gpt_embed(xe, ye, self.P("ar_text_position.alpha"), self.P("ar_audio_position.alpha"), self.pe(max(X, Y), dev))
-        h = self._drop(h, "gpt.pos")
+        h = self._drop(h, tagp + "gpt.pos")
         p_attn = self.layer_dropout if self.training else 0.0
         for i in range(self.num_layers):
             p = f"h.layers.{i}."
             qkv = ops.linear(h, ops.pack_weight(self.P(p + "self_attn.in_proj_weight")), self.P(p + "self_attn.in_proj_bias"))
-            a = ops.flash_attention(qkv, heads=H, prefix=X, xlen=x_lens, ylen=y_lens, p_drop=p_attn, tag=f"gpt.attn{i}")
+            a = ops.flash_attention(qkv, heads=H, prefix=X, xlen=x_lens, ylen=y_lens, p_drop=p_attn, tag=f"{tagp}gpt.attn{i}")
             a = ops.linear(a, self.w(p + "self_attn.out_proj"), self.b(p + "self_attn.out_proj"))
-            h = ops.layernorm(h, self.P(p + "norm1.weight"), self.P(p + "norm1.bias"), res=self._drop(a, f"gpt.d1.{i}"))
+            h = ops.layernorm(h, self.P(p + "norm1.weight"), self.P(p + "norm1.bias"), res=self._drop(a, f"{tagp}gpt.d1.{i}"))
             f = ops.linear(h, self.w(p + "linear1"), self.b(p + "linear1"), act=ops.ACT_RELU)
-            f = ops.linear(self._drop(f, f"gpt.df.{i}"), self.w(p + "linear2"), self.b(p + "linear2"))
-            h = ops.layernorm(h, self.P(p + "norm2.weight"), self.P(p + "norm2.bias"), res=self._drop(f, f"gpt.d2.{i}"))
-        if getattr(self, "_xoff", None) is None or self._xoff.shape[0] != B or int(self._xoff_val) != X or self._xoff.device != dev:
-            self._xoff, self._xoff_val = torch.full((B,), X, device=dev, dtype=torch.int64), X
+            f = ops.linear(self._drop(f, f"{tagp}gpt.df.{i}"), self.w(p + "linear2"), self.b(p + "linear2"))
+            h = ops.layernorm(h, self.P(p + "norm2.weight"), self.P(p + "norm2.bias"), res=self._drop(f, f"{tagp}gpt.d2.{i}"))
+        key = (B, X, str(dev))
+        if getattr(self, "_xoff_key", None) != key:
+            self._xoff, self._xoff_key = torch.full((B,), X, device=dev, dtype=torch.int64), key
         hy = ops.slice_rows(h, self._xoff, Y)
         Vp = (self.vocab_size + 3) // 4 * 4
-        logits = ops.linear(hy, self.w("ar_predict_layer", pad0=Vp))
+        return ops.linear(hy, self.w("ar_predict_layer", pad0=Vp))
+
+    def _embed_text(self, x, bert_feature, bert_channels_last):
+        bert_cl = bert_feature if bert_channels_last else ops.to_channels_last(bert_feature)
+        xe = ops.embedding(self.P("ar_text_embedding.word_embeddings.weight"), x.to(torch.int64))
+        return ops.linear(bert_cl, self.w("bert_proj", need_pb=False), self.b("bert_proj"), res=xe)
+
+    def forward(self, x, x_lens, y, y_lens, bert_feature, reject=None, bert_channels_last=False):
+        """DPO variant (t2s_model.py:393-429): CE(sum) on the given y plus a reference-free DPO term (beta 0.2) against
+        a synthetically corrupted `reject` = (reject_y, reject_y_lens); built by `make_reject_y` when not given.
+        -> (loss, acc)."""
+        if reject is None:
+            reject = make_reject_y(y, y_lens)
+        ry, ryl = reject
+        B, X = x.shape
+        x_lens, y_lens, ryl = [t.to(torch.int64).contiguous() for t in (x_lens, y_lens, ryl)]
+        y_in, tg = self.make_targets(y, y_lens)
+        ry_in, rtg = self.make_targets(ry, ryl)
+        # the text prefix is embedded once per branch in the reference (two make_input_data calls); the branches only share
+        # weights, so the second pass re-runs it to keep the dropout streams independent as well
+        lc = self._decode(self._embed_text(x, bert_feature, bert_channels_last), y_in, x_lens, y_lens, X)
+        lr_ = self._decode(self._embed_text(x, bert_feature, bert_channels_last), ry_in, x_lens, ryl, X, tagp="rej.")
+        loss, metrics = ops.dpo_ce(lc, tg, lr_, rtg, self.top_k, self.EOS, V=self.vocab_size, beta=0.2)
+        self.last_logits, self.last_dpo = lc.detach(), metrics
+        return loss, metrics[2]
+
+    def forward_old(self, x, x_lens, y, y_lens, bert_feature, targets=None, bert_channels_last=False):
+        """-> (loss, acc) like t2s_model.py:431-490; `loss` is differentiable, `acc` a device scalar.
+        bert_feature: [B, 1024, X] (reference layout), or [B, X, 1024] with bert_channels_last=True."""
+        B, X = x.shape
+        x_lens, y_lens = x_lens.to(torch.int64).contiguous(), y_lens.to(torch.int64).contiguous()
+        y_in, tg = self.make_targets(y, y_lens) if targets is None else targets
+        logits = self._decode(self._embed_text(x, bert_feature, bert_channels_last), y_in, x_lens, y_lens, X)
         loss, out2 = ops.ce_sum_topk(logits, tg.reshape(-1), self.top_k, self.EOS, V=self.vocab_size)
         self.last_logits = logits.detach()        # detached: a retained graph would pin AccumulateGrad nodes to this stream
         return loss, out2[1]
+
+
+def make_reject_y(y_o, y_lens, generator=None):
+    """utils.py:195-232: per item, duplicate a random span of the PADDED row (the reference's `randint(0, 1)` always picks
+    the repeat branch); rows are re-padded with 0 to the longest result.  Host-side integer work, as in the reference."""
+    rows, lens = [], []
+    for b in range(len(y_lens)):
+        y = y_o[b]
+        i0, i1 = sorted(torch.randint(0, len(y), size=(2,), generator=generator).tolist())
+        rows.append(torch.cat([y[:i0], y[i0:i1], y[i0:i1], y[i1:]]))
+        lens.append(len(rows[-1]))
+    Ym = max(lens)
+    out = torch.zeros((len(rows), Ym), dtype=y_o.dtype, device=y_o.device)
+    for b, r in enumerate(rows):
+        out[b, :len(r)] = r
+    return out, torch.tensor(lens, device=y_lens.device)

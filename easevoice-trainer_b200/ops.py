@@ -1393,7 +1393,7 @@ class _CeFn(torch.autograd.Function):
         V = ctx.V
         gl = gloss.reshape(1).contiguous().float()
         dl = (torch.empty if Vp == V else torch.zeros)(logits.shape, device=logits.device, dtype=torch.float32)
-        _call("evk_ce_bwd", _p(logits), ld, _p(targets), _p(lse), _p(gl), _p(dl), Vp, rows, V)
+        _call("evk_ce_bwd", _p(logits), ld, _p(targets), _p(lse), _p(gl), rows, _p(dl), Vp, rows, V)
         return dl, None, None, None, None
 
 
@@ -1402,6 +1402,58 @@ def ce_sum_topk(logits, targets, topk=3, ignore_index=1024, V=None):
     V: number of real classes when the last dim of `logits` is zero-padded."""
     loss, out2 = _CeFn.apply(logits, targets, int(topk), int(ignore_index), int(V or logits.shape[-1]))
     return loss, out2
+
+
+class _DpoCeFn(torch.autograd.Function):
+    """loss_1 + loss_2 of Text2SemanticDecoder.forward (t2s_model.py:417-427) from chosen / rejected logits."""
+
+    @staticmethod
+    def forward(ctx, lc, tc, lr_, tr, topk, ignore, V, beta):
+        lc, lr_ = _cl(lc), _cl(lr_)
+        B, Yc = tc.shape
+        Yr = tr.shape[1]
+        dev = lc.device
+        tc, tr = tc.reshape(-1).contiguous(), tr.reshape(-1).contiguous()
+        bufs = []
+        for lg, tg, rows in ((lc, tc, B * Yc), (lr_, tr, B * Yr)):
+            lse = torch.empty(rows, device=dev, dtype=torch.float32)
+            nll = torch.empty(rows, device=dev, dtype=torch.float32)
+            flags = torch.empty(rows, device=dev, dtype=torch.uint8)
+            o2 = torch.empty(2, device=dev, dtype=torch.float32)
+            _call("evk_ce_fwd", _p(lg), _rows(lg)[2], _p(tg), rows, V, topk, ignore, _p(lse), _p(nll), _p(flags), _p(o2))
+            bufs.append((lse, nll, o2))
+        out3 = torch.empty(3, device=dev, dtype=torch.float32)
+        coef = torch.empty((2, B), device=dev, dtype=torch.float32)
+        _call("evk_dpo_head", _p(bufs[0][1]), Yc, _p(bufs[1][1]), Yr, B, ctypes.c_float(beta), _p(out3), _p(coef[0]), _p(coef[1]))
+        ctx.save_for_backward(lc, tc, bufs[0][0], lr_, tr, bufs[1][0], coef)
+        ctx.k = (B, Yc, Yr, V)
+        metrics = torch.stack([out3[0], out3[1], bufs[0][2][1]])        # (loss_1, loss_2, top-k acc of the chosen branch)
+        ctx.mark_non_differentiable(metrics)
+        return out3[2].clone(), metrics
+
+    @staticmethod
+    def backward(ctx, g, _gm):
+        lc, tc, lsec, lr_, tr, lser, coef = ctx.saved_tensors
+        B, Yc, Yr, V = ctx.k
+        gc = _AxpbyFn_scale(coef, g)
+        outs = []
+        for lg, tg, lse, Yn, cf in ((lc, tc, lsec, Yc, gc[0]), (lr_, tr, lser, Yr, gc[1])):
+            rows, Vp, ld = _rows(lg)
+            dl = (torch.empty if Vp == V else torch.zeros)(lg.shape, device=lg.device, dtype=torch.float32)
+            _call("evk_ce_bwd", _p(lg), ld, _p(tg), _p(lse), _p(cf), Yn, _p(dl), Vp, rows, V)
+            outs.append(dl)
+        return outs[0], None, outs[1], None, None, None, None, None
+
+
+def _AxpbyFn_scale(coef, g):
+    """coef * g for a device scalar g (tiny [2, B] tensor)."""
+    return (coef * g.reshape(1, 1)).contiguous()
+
+
+def dpo_ce(logits_c, targets_c, logits_r, targets_r, topk=3, ignore_index=1024, V=None, beta=0.2):
+    """-> (loss_1 + loss_2 (differentiable), device [3] = (loss_1, loss_2, top-k acc))."""
+    return _DpoCeFn.apply(logits_c, targets_c, logits_r, targets_r, int(topk), int(ignore_index),
+                          int(V or logits_c.shape[-1]), float(beta))
 
 
 def scaled_adam(st, gscale=1.0, zero_grad=True):

@@ -106,8 +106,9 @@ class GptStep:
     ACCUM = 4
     LR_FIRST, LR_LOCKED = 0.01, 0.002          # lr_schedulers.py:36-65 (see module docstring)
 
-    def __init__(self, model, world_size=1, **optim_kw):
-        self.model, self.world = model, world_size
+    def __init__(self, model, world_size=1, dpo=False, **optim_kw):
+        self.model, self.world, self.dpo = model, world_size, dpo
+        self.lr = self.LR_FIRST
         self.opt = FlatScaledAdam(model.named_parameters(), **optim_kw)
         self.batch_idx = 0
         self._graph = None
@@ -118,6 +119,13 @@ class GptStep:
     def forward_backward(self, batch):
         """loss/acc + gradient accumulation for one micro-batch (no optimizer step)."""
         m = self.model
+        if self.dpo:                                   # t2s_lightning_module.py:44 (if_dpo): CE + reference-free DPO term
+            loss, acc = m.forward(batch["phoneme_ids"], batch["phoneme_ids_len"], batch["semantic_ids"], batch["semantic_ids_len"],
+                                  batch["bert_feature"], reject=batch.get("reject"),
+                                  bert_channels_last=batch.get("bert_channels_last", False))
+            grads = torch.autograd.grad(loss, self.opt.params, allow_unused=True)
+            self.opt.accumulate(grads)
+            return loss.detach(), acc
         loss, acc = m.forward_old(batch["phoneme_ids"], batch["phoneme_ids_len"], batch["semantic_ids"],
                                   batch["semantic_ids_len"], batch["bert_feature"], targets=batch.get("targets"),
                                   bert_channels_last=batch.get("bert_channels_last", False))
@@ -141,6 +149,7 @@ class GptStep:
         if self.wants_step():
             self.optimizer_step()
             self.opt.set_lr(self.LR_LOCKED)
+            self.lr = self.LR_LOCKED
         self.batch_idx += 1
         self.last = out
         return out
@@ -173,6 +182,7 @@ class GptStep:
         ops.rng_state().copy_(snap[1])
 
     def graph_step(self, batch):
+        assert not self.dpo, "the DPO variant draws its rejected sequences on the host: use step()"
         if self._graph is None:
             self._capture(batch)
         for k, v in batch.items():
@@ -186,6 +196,7 @@ class GptStep:
                 dist.all_reduce(self.opt.flat_g)
             self._ograph.replay()
             self.opt.set_lr(self.LR_LOCKED)
+            self.lr = self.LR_LOCKED
         self.batch_idx += 1
         self.last = self._gout
         return self._gout

@@ -19,3 +19,10 @@ def get_sovits_train_dir(project_dir, name):
     if not name:
         name = "sovits_" + generate_random_name()
     return os.path.join(project_dir, "models", "sovits_train", name)
+
+
+def get_gpt_train_dir(project_dir, name):
+    """src/train/helper.py:21-24."""
+    if not name:
+        name = "gpt_" + generate_random_name()
+    return os.path.join(project_dir, "models", "gpt_train", name)

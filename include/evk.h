@@ -277,11 +277,17 @@ int evk_sinepos_bwd(const float* dy, int32_t ldy, int64_t dy_sb, const float* pe
 /* CrossEntropyLoss(reduction="sum") + MulticlassAccuracy(top_k, micro, ignore_index) (t2s_model.py:486-489).
  * out2[0] = sum_r (lse_r - logit_r[target_r]); out2[1] = #hits / #valid, hit = fewer than top_k logits strictly above
  * the target's.  lse/nll: [rows] scratch kept for the backward; flags: [rows] bytes.
- * bwd: dl[r][c] = gscale[0] * (softmax(logits_r)[c] - [c == target_r]). */
+ * bwd: dl[r][c] = gscale[r / rows_per_g] * (softmax(logits_r)[c] - [c == target_r]). */
 int evk_ce_fwd(const float* logits, int32_t ld, const int64_t* targets, int32_t rows, int32_t V, int32_t topk,
                int64_t ignore_index, float* lse, float* nll, uint8_t* flags, float* out2, evk_stream_t stream);
-int evk_ce_bwd(const float* logits, int32_t ld, const int64_t* targets, const float* lse, const float* gscale, float* dl,
+int evk_ce_bwd(const float* logits, int32_t ld, const int64_t* targets, const float* lse, const float* gscale,
+               int32_t rows_per_g /* row r is scaled by gscale[r / rows_per_g]; == rows for one scalar */, float* dl,
                int32_t lddl, int32_t rows, int32_t V, evk_stream_t stream);
+/* DPO head of Text2SemanticDecoder.forward (t2s_model.py:393-429; utils.py:160-192 with reference_free=True): from the
+ * per-token nll of the chosen [B, Yc] and rejected [B, Yr] sequences: out3 = (sum CE of chosen, mean_b -logsigmoid(beta *
+ * (logp_chosen_b - logp_rejected_b)), their sum); coef_c/coef_r [B] = d out3[2] / d nll_{c,r}[b][t] (feeds evk_ce_bwd). */
+int evk_dpo_head(const float* nll_c, int32_t Yc, const float* nll_r, int32_t Yr, int32_t B, float beta, float* out3,
+                 float* coef_c, float* coef_r, evk_stream_t stream);
 /* ScaledAdam (optim.py:123-622) over flat arenas p/g/delta/v.  chunks: [nchunks][3] = (tensor id, begin, count), numel: [nt].
  * Per-tensor state: rms, sv (scale_exp_avg_sq) [nt]; sg (scale_grads) [size_update_period][nt]; stats [nt][3] and
  * coef [nt][2] are scratch (stats must be zero on first use; the call leaves it zero).  hyper: device [lr];

@@ -116,6 +116,27 @@ def forward_old(P, x, x_lens, y, y_lens, bert, m=GPT_MODEL, taps=None):
     return loss, acc, logits, targets
 
 
+def forward_dpo(P, x, x_lens, y, y_lens, bert, reject_y, reject_lens, m=GPT_MODEL, beta=0.2):
+    """t2s_model.py:393-429 with the rejected batch given (make_reject_y draws it at random, utils.py:195-232);
+    dpo_loss / get_batch_logps: utils.py:160-192 (reference_free=True)."""
+    loss1, acc, logits, targets = forward_old(P, x, x_lens, y, y_lens, bert, m)
+    _, _, rlogits, rtargets = forward_old(P, x, x_lens, reject_y, reject_lens, bert, m)
+    A = torch.gather(logits.log_softmax(-1), 2, targets.unsqueeze(2)).squeeze(2).sum(-1)
+    R = torch.gather(rlogits.log_softmax(-1), 2, rtargets.unsqueeze(2)).squeeze(2).sum(-1)
+    loss2 = (-F.logsigmoid(beta * (A - R))).mean()
+    return loss1 + loss2, acc, loss1, loss2
+
+
+def make_reject_given(y, spans):
+    """the repeat_P corruption of utils.py:196-202 with the random span endpoints supplied."""
+    rows = [torch.cat([y[b][:i0], y[b][i0:i1], y[b][i0:i1], y[b][i1:]]) for b, (i0, i1) in enumerate(spans)]
+    lens = [len(r) for r in rows]
+    out = torch.zeros((len(rows), max(lens)), dtype=y.dtype)
+    for b, r in enumerate(rows):
+        out[b, :len(r)] = r
+    return out, torch.tensor(lens)
+
+
 class ScaledAdamOracle:
     """Per-tensor restatement of ScaledAdam as configured at t2s_lightning_module.py:100-108."""
 

@@ -261,6 +261,27 @@ def pin_gpt():
                                ("bert_proj.weight", "ar_text_position.alpha", "ar_audio_position.alpha",
                                 "ar_audio_embedding.word_embeddings.weight", "h.layers.0.self_attn.in_proj_weight",
                                 "h.layers.1.linear2.weight", "h.layers.1.norm2.bias", "ar_predict_layer.weight")}}
+        # DPO variant (if_dpo): same weights/batch, rejected batch fixed by patching make_reject_y in the reference module
+        import src.easevoice.soundstorm.auto_reg.models.t2s_model as t2s_mod
+        spans = [(2 + b, 7 + 2 * b) for b in range(B)]
+        ry, ryl = gpt_oracle.make_reject_given(y, spans)
+        orig = t2s_mod.make_reject_y
+        t2s_mod.make_reject_y = lambda y_o, y_lens: (ry, ryl)
+        try:
+            ref.zero_grad()
+            dl_r, dacc_r = ref.forward(x, xl, y, yl, bert)
+            dl_r.backward()
+        finally:
+            t2s_mod.make_reject_y = orig
+        Pd = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+        dl_o, dacc_o, l1_o, l2_o = gpt_oracle.forward_dpo(Pd, x, xl, y, yl, bert, ry, ryl, m)
+        dl_o.backward()
+        ddl = abs(float(dl_r) - float(dl_o)) / abs(float(dl_r))
+        ddg = max(maxdiff(p.grad, Pd[k].grad) / (float(p.grad.abs().max()) + 1e-12) for k, p in ref.named_parameters())
+        assert ddl < 1e-5 and ddg < 2e-4, (tag, ddl, ddg)
+        res[tag].update(dpo_loss_rel=ddl, dpo_grad_rel_max=ddg)
+        gold.update(dpo=dict(spans=spans, loss=float(dl_r), loss_1=float(l1_o), loss_2=float(l2_o), acc=float(dacc_r),
+                             grad_norms={k: float(p.grad.norm()) for k, p in ref.named_parameters() if k in gold["grad_norms"]}))
         with open(os.path.join(GOLD, f"gpt_{tag}.json"), "w") as f:
             json.dump(gold, f, indent=1)
     # ---- ScaledAdam: 14 steps on a small mixed set (matrix, vector, scalar, tiny-rms tensor), lr 0.01 then 0.002

@@ -733,8 +733,96 @@ def check_gpt(tag="small"):
     return out
 
 
+def check_gpt_dpo_and_trainer():
+    """DPO variant of the step (if_dpo) vs the oracle + reference golden, then GPTTrain end to end on a tiny synthetic
+    dataset (files in the reference's layout): stdout protocol, checkpoint layout and resume."""
+    import contextlib
+    import io
+    import tempfile
+    from easevoice_trainer_b200.models_gpt import Text2SemanticDecoder, make_reject_y
+    out = []
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "gpt_ragged.json")))
+    m = gold["model"]
+    P = gpt_oracle.init_params(gpt_oracle.gpt_param_spec(m), gold["param_seed"])
+    P["ar_text_position.alpha"].fill_(gold["alpha_text"]); P["ar_audio_position.alpha"].fill_(gold["alpha_audio"])
+    net = Text2SemanticDecoder({"model": m}, layer_dropout=0.0)
+    net.load_state_dict(P)
+    net = net.to(DEV)
+    x, xl, y, yl, bert = gpt_oracle.synthetic_gpt_batch(gold["B"], gold["X"], gold["Y"], gold["batch_seed"], gold["ragged"])
+    ry, ryl = gpt_oracle.make_reject_given(y, [tuple(s) for s in gold["dpo"]["spans"]])
+    Pq = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    lo, acc_o, l1o, l2o = gpt_oracle.forward_dpo(Pq, x, xl, y, yl, bert, ry, ryl, m)
+    lo.backward()
+    loss, acc = net.forward(x.to(DEV), xl.to(DEV), y.to(DEV), yl.to(DEV), bert.to(DEV), reject=(ry.to(DEV), ryl.to(DEV)))
+    named = list(net.named_parameters())
+    grads = torch.autograd.grad(loss, [p for _, p in named])
+    out.append(("dpo loss vs oracle", abs(float(loss.detach()) - float(lo)) / abs(float(lo)), TOL_TC))
+    out.append(("dpo loss vs reference golden", abs(float(loss.detach()) - gold["dpo"]["loss"]) / abs(gold["dpo"]["loss"]), TOL_TC))
+    out.append(("dpo loss_2 term vs oracle", abs(float(net.last_dpo[1]) - float(l2o)) / (abs(float(l2o)) + 1e-6), 5e-2))
+    out.append(("dpo acc vs reference golden", abs(float(acc) - gold["dpo"]["acc"]), 2.0 / (gold["B"] * gold["Y"])))
+    num = den = 0.0
+    for (n, _), gk in zip(named, grads):
+        if n.endswith(".alpha"):
+            continue
+        num += float((gk.cpu().double() - Pq[n].grad.double()).pow(2).sum()); den += float(Pq[n].grad.double().pow(2).sum())
+    out.append(("dpo grads global", math.sqrt(num / den), KINK_TOL))
+    g = _gen(3)
+    r2, r2l = make_reject_y(y, yl, generator=g)
+    ok = all(int(r2l[b]) >= y.shape[1] and int(r2l[b]) <= 2 * y.shape[1] for b in range(len(yl))) and r2.shape[1] == int(r2l.max())
+    out.append(("make_reject_y: repeat-span shape contract", 0.0 if ok else 1.0, 0.0))
+    # ---- trainer end to end
+    from easevoice_trainer_b200.train.gpt import GPTTrain, GPTTrainParams
+    from easevoice_trainer_b200.train import data_gpt
+    import yaml
+    with tempfile.TemporaryDirectory() as td:
+        inp = os.path.join(td, "in"); os.makedirs(os.path.join(inp, "3-bert"))
+        table = {f"p{i}": i for i in range(732)}
+        rnd = _gen(11)
+        with open(os.path.join(inp, "2-name2text.txt"), "w") as f2, open(os.path.join(inp, "6-name2semantic.tsv"), "w") as f6:
+            f6.write("item_name\tsemantic_audio\n")
+            for i in range(12):
+                nph = int(torch.randint(8, 20, (1,), generator=rnd))
+                nsem = int(nph * 25 / float(torch.randint(5, 12, (1,), generator=rnd)))
+                ph = " ".join(f"p{int(v)}" for v in torch.randint(0, 732, (nph,), generator=rnd))
+                f2.write(f"utt{i}\t{ph}\tw2p\tnorm text\n")
+                f6.write(f"utt{i}\t" + " ".join(str(int(v)) for v in torch.randint(0, 1024, (nsem,), generator=rnd)) + "\n")
+                if i % 2 == 0:
+                    torch.save(torch.randn(1024, nph, generator=rnd), os.path.join(inp, "3-bert", f"utt{i}.pt"))
+        cfg = yaml.safe_load(open(os.path.join(ROOT, "configs", "gpt.yaml")))
+        cfg["model"]["n_layer"] = 2
+        cpath = os.path.join(td, "gpt.yaml")
+        yaml.safe_dump(cfg, open(cpath, "w"))
+        ds = data_gpt.Text2SemanticDataset(os.path.join(inp, "2-name2text.txt"), os.path.join(inp, "6-name2semantic.tsv"),
+                                           max_sec=54, phoneme_table=table)
+        params = GPTTrainParams(batch_size=24, total_epochs=2, save_every_epoch=1, gpu_ids="0", model_path="", train_input_dir=inp,
+                                output_model_name="tiny", project_dir=td)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            res = GPTTrain(params, dataset=ds, config_path=cpath).train()
+        lines = [l for l in buf.getvalue().splitlines() if l.startswith("loss-of-easevoice")]
+        rec = [json.loads(l[len("loss-of-easevoice"):]) for l in lines]
+        out.append(("GPTTrain: one loss line per step with acc/lr/epoch", 0.0 if rec and all(k in rec[0] for k in ("step", "loss", "acc", "lr", "epoch")) else 1.0, 0.0))
+        out.append(("GPTTrain: loss finite", 0.0 if all(math.isfinite(r["loss"]) for r in rec) else 1.0, 0.0))
+        files = sorted(os.listdir(res.model_path))
+        ck = os.listdir(os.path.join(res.model_path, "logs", "ckpt"))
+        ok = "tiny-e1.ckpt" in files and "tiny-e2.ckpt" in files and len(ck) == 1 and ck[0].startswith("epoch=1-step=")
+        out.append(("GPTTrain: output layout (<name>-e{E}.ckpt + logs/ckpt/epoch=E-step=S.ckpt, latest only)", 0.0 if ok else 1.0, 0.0))
+        w = torch.load(os.path.join(res.model_path, "tiny-e2.ckpt"), map_location="cpu", weights_only=False)
+        okw = all(k.startswith("model.") and v.dtype == torch.float16 for k, v in w["weight"].items()) and w["info"] == "GPT-e2" and "config" in w
+        out.append(("GPTTrain: export = fp16 weights under 'model.' + config + info", 0.0 if okw else 1.0, 0.0))
+        # resume: a third epoch continues from epoch=1 (loads weights + ScaledAdam state)
+        params.total_epochs = 3
+        buf2 = io.StringIO()
+        with contextlib.redirect_stdout(buf2):
+            GPTTrain(params, dataset=ds, config_path=cpath).train()
+        rec2 = [json.loads(l[len("loss-of-easevoice"):]) for l in buf2.getvalue().splitlines() if l.startswith("loss-of-easevoice")]
+        out.append(("GPTTrain: resume runs only the missing epoch", 0.0 if rec2 and all(r["epoch"] == 2 for r in rec2) else 1.0, 0.0))
+    return out
+
+
 ALL = [check_conv, check_conv_transpose, check_elementwise, check_attention, check_vq_losses_optim, check_mel,
        lambda: check_s2("small"), lambda: check_s2("ragged"), check_api_layouts,
-       check_gpt_kernels, check_scaled_adam, lambda: check_gpt("small"), lambda: check_gpt("ragged")]
+       check_gpt_kernels, check_scaled_adam, lambda: check_gpt("small"), lambda: check_gpt("ragged"),
+       check_gpt_dpo_and_trainer]
 NAMES = ["conv", "conv_transpose", "elementwise", "attention", "vq_losses_optim", "mel", "s2_small", "s2_ragged", "api",
-         "gpt_kernels", "scaled_adam", "gpt_small", "gpt_ragged"]
+         "gpt_kernels", "scaled_adam", "gpt_small", "gpt_ragged", "gpt_dpo_trainer"]

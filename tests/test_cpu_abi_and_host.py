@@ -157,3 +157,65 @@ def test_collate_and_bucket_sampler():
             assert len(ks) == 1
         seen.append({k for x in bs for k in x})
     assert seen[0] | seen[1] == set(range(len(lens)))
+
+
+def test_gpt_state_dict_contract_and_step_schedule():
+    """Text2SemanticDecoder mirror: reference state_dict keys/shapes (Lightning adds "model."); training_step schedule
+    (t2s_lightning_module.py:52-56): update when batch_idx > 0 and batch_idx % 4 == 0."""
+    from oracle import gpt_oracle
+    from easevoice_trainer_b200.models_gpt import Text2SemanticDecoder, sine_table, make_reject_y
+    from easevoice_trainer_b200.configs import GPT_MODEL
+    m = dict(GPT_MODEL, n_layer=2)
+    net = Text2SemanticDecoder({"model": m})
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == gpt_oracle.gpt_param_spec(m)
+    assert all(v.dtype == torch.float32 for v in net.state_dict().values())
+    assert torch.equal(sine_table(40, 512), gpt_oracle.sine_pe(40, 512))
+    y = torch.randint(0, 1024, (3, 20)); yl = torch.tensor([20, 11, 7])
+    y_in, tg = net.make_targets(y, yl)
+    assert torch.equal(tg[:, :-1], y_in[:, 1:]) and (tg[1, 11:] == 1024).all() and (tg[0, -1] == 1024) and torch.equal(y_in[2, :7], y[2, :7]) \
+        and torch.equal(tg[2, :6], y[2, 1:7]) and tg[2, 6] == 1024 and (y_in[2, 7:] == 1024).all()
+    ry, rl = make_reject_y(y, yl, torch.Generator().manual_seed(0))
+    assert ry.shape[1] == int(rl.max()) and (rl >= 20).all()
+    from easevoice_trainer_b200.train.gpt_step import GptStep
+    sched = []
+    class _S:                                   # only the schedule logic is exercised on CPU
+        ACCUM = GptStep.ACCUM
+    s = _S()
+    for i in range(10):
+        s.batch_idx = i
+        sched.append(GptStep.wants_step(s))
+    assert [i for i, v in enumerate(sched) if v] == [4, 8]
+
+
+def test_gpt_dataset_collate_and_sampler(tmp_path):
+    from easevoice_trainer_b200.train import data_gpt
+    table = {f"p{i}": i for i in range(732)}
+    g = torch.Generator().manual_seed(0)
+    (tmp_path / "3-bert").mkdir()
+    with open(tmp_path / "2-name2text.txt", "w") as f2, open(tmp_path / "6-name2semantic.tsv", "w") as f6:
+        f6.write("item_name\tsemantic_audio\n")
+        for i in range(30):
+            nph = 10 + i
+            nsem = nph * 25 // 8 if i != 7 else nph * 25 * 2          # utt7: 0.5 phonemes/s -> filtered (min_ps_ratio 3)
+            f2.write(f"u{i}\t" + " ".join(f"p{(3 * i + k) % 732}" for k in range(nph)) + "\tw\tt\n")
+            f6.write(f"u{i}\t" + " ".join(str((7 * i + k) % 1024) for k in range(nsem)) + "\n")
+            if i % 3 == 0:
+                torch.save(torch.randn(1024, nph, generator=g), tmp_path / "3-bert" / f"u{i}.pt")
+    ds = data_gpt.Text2SemanticDataset(str(tmp_path / "2-name2text.txt"), str(tmp_path / "6-name2semantic.tsv"), max_sec=54, phoneme_table=table)
+    assert len(ds) == 29 * 3 and "u7" not in ds.item_names        # < 100 items are replicated max(2, int(100 / n)) times
+    b = ds.collate([ds[0], ds[5], ds[9]])
+    X, Y = int(b["phoneme_ids_len"].max()), int(b["semantic_ids_len"].max())
+    assert b["phoneme_ids"].shape == (3, X) and b["semantic_ids"].shape == (3, Y) and b["bert_feature"].shape == (3, 1024, X)
+    assert b["phoneme_ids"].dtype == torch.int64 and b["semantic_ids"].dtype == torch.int64
+    i = int(b["semantic_ids_len"].argmin())
+    assert (b["semantic_ids"][i, b["semantic_ids_len"][i]:] == 1024).all() and (b["phoneme_ids"][i, b["phoneme_ids_len"][i]:] == 0).all()
+    assert float(b["bert_feature"][1].abs().sum()) == 0.0 or ds.item_names[5] in ("u0", "u3", "u6", "u9", "u12", "u15", "u18", "u21", "u24", "u27")
+    parts = []
+    for r in range(2):
+        sp = data_gpt.DistributedBucketSampler(ds, 2, r, batch_size=4)
+        sp.set_epoch(3)
+        parts.append(list(sp))
+    assert len(parts[0]) == len(parts[1]) == (len(ds) + 1) // 2
+    assert set(parts[0]) | set(parts[1]) == set(range(len(ds)))    # every sample visited; ranks take alternating slots
+    sp0 = data_gpt.DistributedBucketSampler(ds, 2, 0, batch_size=4); sp0.set_epoch(3)
+    assert list(sp0) == parts[0]                                   # deterministic in (seed, epoch)

@@ -75,3 +75,79 @@ def test_s2_small_losses_match_reference_golden():
         assert abs(float(o[k]) - gold[k]) <= 2e-4 * abs(gold[k]), (k, float(o[k]), gold[k])
     assert int(o["codes"].sum()) == gold["codes_sum"]
     assert np.allclose(o["y_hat"][0, 0, 100:108].numpy(), gold["y_hat_0_0_100_108"], rtol=1e-3, atol=1e-6)
+
+
+# ---- stage-1 AR GPT -------------------------------------------------------------------------------------------------
+def _gpt_case(tag):
+    import json
+    from oracle import gpt_oracle
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", f"gpt_{tag}.json")))
+    m = gold["model"]
+    P = gpt_oracle.init_params(gpt_oracle.gpt_param_spec(m), gold["param_seed"])
+    P["ar_text_position.alpha"].fill_(gold["alpha_text"]); P["ar_audio_position.alpha"].fill_(gold["alpha_audio"])
+    batch = gpt_oracle.synthetic_gpt_batch(gold["B"], gold["X"], gold["Y"], gold["batch_seed"], gold["ragged"])
+    return gold, m, P, batch
+
+
+def test_gpt_param_spec_matches_reference_count():
+    from oracle import gpt_oracle
+    spec = gpt_oracle.gpt_param_spec()
+    n = sum(int(torch.tensor(s).prod()) for s in spec.values())
+    assert n == 77_606_402                      # SURVEY.md section 8 / reference Text2SemanticDecoder at configs/gpt.yaml
+    assert sum(int(torch.tensor(s).prod()) for k, s in spec.items() if k.startswith("h.")) == 75_657_216
+
+
+def test_gpt_forward_old_matches_reference_golden():
+    from oracle import gpt_oracle
+    for tag in ("small", "ragged"):
+        gold, m, P, (x, xl, y, yl, bert) = _gpt_case(tag)
+        Pq = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+        loss, acc, logits, targets = gpt_oracle.forward_old(Pq, x, xl, y, yl, bert, m)
+        loss.backward()
+        assert abs(float(loss) - gold["loss"]) / gold["loss"] < 1e-5
+        assert abs(float(acc) - gold["acc"]) < 1e-6
+        assert int(targets.sum()) == gold["targets_sum"]
+        for k, n in gold["grad_norms"].items():
+            assert abs(float(Pq[k].grad.norm()) - n) / n < 2e-4, k
+
+
+def test_gpt_dpo_matches_reference_golden():
+    from oracle import gpt_oracle
+    gold, m, P, (x, xl, y, yl, bert) = _gpt_case("ragged")
+    ry, ryl = gpt_oracle.make_reject_given(y, [tuple(s) for s in gold["dpo"]["spans"]])
+    loss, acc, l1, l2 = gpt_oracle.forward_dpo(P, x, xl, y, yl, bert, ry, ryl, m)
+    assert abs(float(loss) - gold["dpo"]["loss"]) / gold["dpo"]["loss"] < 1e-5
+    assert abs(float(l1) + float(l2) - float(loss)) < 1e-3
+
+
+def test_prefix_lm_mask_properties():
+    """t2s_model.py:456-479: text rows never see audio; audio row i sees text + audio <= i; padded keys are never seen."""
+    from oracle import gpt_oracle
+    X, Y = 5, 7
+    xl, yl = torch.tensor([5, 3]), torch.tensor([7, 4])
+    mk = gpt_oracle.prefix_lm_mask(xl, yl, X, Y)
+    assert mk[:, :X, X:].all()
+    assert not mk[0, X:, :X].any() and mk[1, :, 3:X].all()
+    for i in range(Y):
+        assert not mk[0, X + i, X:X + i + 1].any() and mk[0, X + i, X + i + 1:].all()
+    assert mk[1, :, X + 4:].all()
+    assert (~mk).any(-1).all()                  # no fully-masked row (would be NaN in the reference's softmax)
+
+
+def test_scaled_adam_oracle_matches_reference_golden_trajectory():
+    import json
+    from oracle import gpt_oracle
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "scaled_adam.json")))
+    g = torch.Generator().manual_seed(gold["seed"])
+    shapes = [tuple(s) for s in gold["shapes"]]
+    params = [torch.randn(s, generator=g) * sc for s, sc in zip(shapes, gold["scales"])]
+    opt = gpt_oracle.ScaledAdamOracle(params, lr=gold["lr_first"], clipping_update_period=gold["clipping_update_period"])
+    clipped = False
+    for it in range(gold["steps"]):
+        grads = [torch.randn(s, generator=g) * (5.0 if it in gold["big_grad_steps"] else 1.0) for s in shapes]
+        clipped |= opt.step(grads) < 1.0
+        if it == 0:
+            opt.lr = gold["lr_rest"]
+        for p, n in zip(params, gold["param_norms"][it]):
+            assert abs(float(p.double().norm()) - n) / (n + 1e-12) < 1e-6
+    assert clipped
