@@ -356,6 +356,7 @@ __global__ void __launch_bounds__(NT) gconv_w_kernel(const __grid_constant__ GP 
 int g_precise = 0;          // 3xTF32 products on the mma.sync kernels (parity tests)
 int g_backend_tc = 1;       // use the tcgen05/TMEM kernel for eligible (stride-1) launches
 int gconv_tc_try(const evk_gconv_desc* d, cudaStream_t st);
+int gemm_tma_try(const evk_gconv_desc* d, cudaStream_t st);
 
 static int fill_gp(const evk_gconv_desc* d, GP& p) {
   EVK_REQUIRE(d != nullptr, EVK_ERR_ARG, "gconv: null descriptor");
@@ -435,6 +436,7 @@ static int launch_f(GP& p, cudaStream_t st) {
 using namespace evk;
 
 extern "C" int evk_set_precise(int32_t on) { g_precise = on ? 1 : 0; return EVK_OK; }
+extern "C" int evk_get_precise(void) { return g_precise; }
 extern "C" int evk_set_backend(int32_t tcgen05) { g_backend_tc = tcgen05 ? 1 : 0; return EVK_OK; }
 
 extern "C" int evk_gconv_fwd(const evk_gconv_desc* d, evk_stream_t stream) {
@@ -446,6 +448,8 @@ extern "C" int evk_gconv_fwd(const evk_gconv_desc* d, evk_stream_t stream) {
   EVK_REQUIRE(d->y != nullptr && d->x != nullptr && d->w != nullptr, EVK_ERR_ARG, "gconv_fwd: null tensor");
   cudaStream_t st = (cudaStream_t)stream;
   if (g_backend_tc && !g_precise && (d->ldx % 4) == 0) {
+    rc = gemm_tma_try(d, st);          // tap-free dense contractions: TMA-fed persistent tcgen05 GEMM
+    if (rc <= 0) return rc;
     rc = gconv_tc_try(d, st);
     if (rc <= 0) return rc;
   }

@@ -14,6 +14,7 @@ import torch
 from . import lib as L
 
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH = 0, 1, 2, 3
+USE_TMA_WGRAD = True     # weight gradients of tap-free layers: transposes + split-K TMA/tcgen05 GEMM
 UN_SCALE, UN_LRELU, UN_TANH, UN_MISH, UN_RELU, UN_TANH_FROM_OUT = 0, 1, 2, 3, 4, 5
 
 _launches = 0          # number of libevk kernel-launching calls (bench.py reports it)
@@ -358,7 +359,20 @@ class _ConvFn(torch.autograd.Function):
             dpa = torch.zeros_like(pa)
             _, _, ldx = _rows(x)
             mma = _aligned(x, ldx) and _aligned(dy, N) and (G == 1 or (Cg % 4 == 0 and Ng % 4 == 0))
-            if mma:
+            rows = B * Tin
+            if (mma and USE_TMA_WGRAD and Q == 1 and stride == 1 and P == 1 and G == 1 and in_len is None and rows >= 2048
+                    and rows % 4 == 0 and C >= 64 and N >= 64 and not _lib().evk_get_precise()):
+                # dW[n][c] = sum_r dY[r][n] X[r][c]: both operands transposed once (rows become the contiguous K dim), then
+                # the TMA-fed tcgen05 GEMM with split-K accumulates straight into the packed-weight gradient
+                xt = torch.empty((C, rows), device=dy.device, dtype=torch.float32)
+                dyt = torch.empty((N, rows), device=dy.device, dtype=torch.float32)
+                _call("evk_transpose_bct_btc", _p(x), _p(xt), 1, C, rows, ldx, 0)
+                _call("evk_transpose_bct_btc", _p(dy), _p(dyt), 1, N, rows, N, 0)
+                tiles = ((N + 127) // 128) * ((C + 255) // 256 if C > 128 else 1)
+                splits = max(1, min(32, (148 + tiles // 2) // tiles, rows // 512))
+                _call("evk_gemm_tf32", _p(dyt), rows, _p(xt), rows, _p(dpa), lda, N, C, rows, None, None, 0, 0, ctypes.c_float(0.0),
+                      splits)
+            elif mma:
                 d = _desc(x=x, w=dpa, y=dy, res=None, bias=None, in_len=in_len, out_len=None,
                           x_sb=Tin * P * ldx, x_sh=Cg if G > 1 else 0, w_sb=0, w_sh=Ng * lda if G > 1 else 0, w_sq=N * lda,
                           y_sb=J * P * N, y_sh=Ng if G > 1 else 0, r_sb=0, r_sh=0, ldx=ldx, ldw=lda, ldy=N, ldr=0, b_sh=0,
@@ -1466,3 +1480,15 @@ def scaled_adam(st, gscale=1.0, zero_grad=True):
           ctypes.c_float(c["scalar_lr_scale"]), ctypes.c_float(c["eps"]), ctypes.c_float(c["param_min_rms"]),
           ctypes.c_float(c["param_max_rms"]), ctypes.c_float(c["scalar_max"]), int(c["size_update_period"]),
           1 if zero_grad else 0)
+
+
+def gemm_tf32(a, b, out=None, bias=None, res=None, act=ACT_NONE, slope=0.0, splits=1):
+    """out[M, N] (+)= a[M, K] @ b[N, K]^T on the TMA-fed tcgen05 GEMM (no autograd).  splits > 1 accumulates into `out`."""
+    M, K = a.shape
+    N = b.shape[0]
+    assert b.shape[1] == K and a.stride(1) == 1 and b.stride(1) == 1
+    if out is None:
+        out = (torch.zeros if splits > 1 else torch.empty)((M, N), device=a.device, dtype=torch.float32)
+    _call("evk_gemm_tf32", _p(a), a.stride(0), _p(b), b.stride(0), _p(out), out.stride(0), M, N, K, _p(bias), _p(res),
+          res.stride(0) if res is not None else 0, act, ctypes.c_float(slope), splits)
+    return out

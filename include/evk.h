@@ -66,6 +66,7 @@ int evk_gconv_fwd(const evk_gconv_desc* d, evk_stream_t stream);
 /* 0 (default): one TF32 product per MAC.  1: 3xTF32 error-compensated products (~fp32 accuracy, 3x tensor work);
  * the parity tests use it to separate indexing errors from TF32 operand rounding. Process-wide. */
 int evk_set_precise(int32_t on);
+int evk_get_precise(void);
 /* 1 (default): stride-1 launches run on the tcgen05/TMEM kernel (gconv_tc.cu); 0: mma.sync kernels only. */
 int evk_set_backend(int32_t tcgen05);
 /* Weight gradient of the same operator:  W[z][q][n][c] += sum_{j,w} Yg[z][orow][n] * X[z][irow][c]
@@ -250,6 +251,18 @@ int evk_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n,
                    float lr_scale, float beta1, float beta2, float eps, float wd, float grad_scale,
                    float* gnorm_sq /* nullable, += */, evk_stream_t stream);
 int evk_scalar_add(float* x, float v, evk_stream_t stream);   /* x[0] += v (device-side step counters) */
+
+/* ------------------------------------------------------------------------------------------
+ * Dense TF32 GEMM on the TMA-fed persistent tcgen05 kernel: D[M][N] = epi(A[M][K] * B[N][K]^T + bias[n] + res[m][n]),
+ * fp32 storage, row pitches lda/ldb/ldd/ldr in floats (lda, ldb multiples of 4; A, B 16-byte aligned).  This is the
+ * kernel evk_gconv_fwd dispatches tap-free (Linear / 1x1 conv) launches to; it is exported for weight gradients on
+ * pre-transposed operands: splits > 1 partitions K across CTAs and ACCUMULATES into D with fp32 atomics (D must hold
+ * the value to add to, bias/res/act must be null/0).  evk_set_backend_tma(0) routes those launches back to the tap kernel.
+ * ------------------------------------------------------------------------------------------ */
+int evk_gemm_tf32(const float* A, int32_t lda, const float* B, int32_t ldb, float* D, int32_t ldd, int32_t M, int32_t N,
+                  int32_t K, const float* bias, const float* res, int32_t ldr, int32_t act, float slope, int32_t splits,
+                  evk_stream_t stream);
+int evk_set_backend_tma(int32_t on);
 
 /* ------------------------------------------------------------------------------------------
  * Stage-1 AR semantic-token GPT (t2s_model.py:431-490 forward_old, transformer.py:266-315, optim.py:123-622).

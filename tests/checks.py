@@ -820,9 +820,52 @@ def check_gpt_dpo_and_trainer():
     return out
 
 
+def check_gemm_tma():
+    """TMA-fed persistent tcgen05 GEMM (csrc/gemm_tma.cu): direct entry point + the Linear dispatch path."""
+    from easevoice_trainer_b200 import ops
+    out = []
+    if PRECISE_MODE[0]:
+        return out
+    g = _gen(21)
+    for tag, M, N, K, splits, epi in (("tails", 1000, 300, 100, 1, False), ("ffn", 4096, 512, 2048, 1, True),
+                                       ("wide", 2500, 1536, 512, 1, True), ("narrow N=96", 3000, 96, 256, 1, False),
+                                       ("multi-tile persistent", 40000, 512, 96, 1, False),
+                                       ("split-K wgrad shape", 512, 384, 8192, 8, False), ("split-K ragged", 200, 130, 1000, 5, False)):
+        a = torch.randn(M, K, generator=g)
+        b = torch.randn(N, K, generator=g) / math.sqrt(K)
+        bias = torch.randn(N, generator=g) if epi else None
+        res = torch.randn(M, N, generator=g) if epi else None
+        ref = a.double() @ b.double().t()
+        if epi:
+            ref = torch.relu(ref + bias.double() + res.double())
+        init = torch.randn(M, N, generator=g) if splits > 1 else None
+        o = ops.gemm_tf32(a.to(DEV), b.to(DEV), out=init.to(DEV) if init is not None else None, bias=bias.to(DEV) if epi else None,
+                          res=res.to(DEV) if epi else None, act=ops.ACT_RELU if epi else ops.ACT_NONE, splits=splits)
+        if init is not None:
+            ref = ref + init.double()
+        out.append((f"gemm_tma {tag} M{M} N{N} K{K} s{splits}", rel(o, ref), TOL_TC))
+    # Linear through evk_gconv_fwd (eligible shapes dispatch to the TMA kernel), with autograd
+    B, T, C, N = 8, 300, 512, 1536
+    x = torch.randn(B, T, C, generator=g)
+    w = torch.randn(N, C, generator=g) / math.sqrt(C)
+    bias = torch.randn(N, generator=g) * 0.1
+    gy = torch.randn(B, T, N, generator=g)
+    xr, wr, br = [t.clone().requires_grad_(True) for t in (x, w, bias)]
+    yr = F.linear(xr, wr, br)
+    yr.backward(gy)
+    xd, wd, bd = [t.to(DEV).requires_grad_(True) for t in (x, w, bias)]
+    y = ops.linear(xd, ops.pack_weight(wd), bd)
+    y.backward(gy.to(DEV))
+    out.append(("linear via TMA gemm y", rel(y, yr), TOL_TC))
+    out.append(("linear via TMA gemm dx", rel(xd.grad, xr.grad), TOL_TC))
+    out.append(("linear via TMA gemm dw", rel(wd.grad, wr.grad), TOL_TC))
+    out.append(("linear via TMA gemm dbias", rel(bd.grad, br.grad), TOL_F32 * 10))
+    return out
+
+
 ALL = [check_conv, check_conv_transpose, check_elementwise, check_attention, check_vq_losses_optim, check_mel,
        lambda: check_s2("small"), lambda: check_s2("ragged"), check_api_layouts,
        check_gpt_kernels, check_scaled_adam, lambda: check_gpt("small"), lambda: check_gpt("ragged"),
-       check_gpt_dpo_and_trainer]
+       check_gpt_dpo_and_trainer, check_gemm_tma]
 NAMES = ["conv", "conv_transpose", "elementwise", "attention", "vq_losses_optim", "mel", "s2_small", "s2_ragged", "api",
-         "gpt_kernels", "scaled_adam", "gpt_small", "gpt_ragged", "gpt_dpo_trainer"]
+         "gpt_kernels", "scaled_adam", "gpt_small", "gpt_ragged", "gpt_dpo_trainer", "gemm_tma"]
