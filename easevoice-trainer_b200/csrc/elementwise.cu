@@ -238,6 +238,25 @@ __global__ void transpose_kernel(const float* __restrict__ x, float* __restrict_
   }
 }
 
+// [B][T][ldx] (C valid) -> [B][C][ldy] (T + shift valid): y[b][c][u] = x[b][u - shift][c], zero for u < shift.
+// The contraction index of a weight gradient becomes contiguous.
+__global__ void transpose_rows_kernel(const float* __restrict__ x, int ldx, long long x_sb, float* __restrict__ y, int ldy,
+                                      long long y_sb, int T, int C, int shift) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * 32;
+  const float* xb = x + b * x_sb;
+  float* yb = y + b * y_sb;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int t = t0 + i - shift, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && t >= 0 && t < T) ? xb[(long long)t * ldx + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i, u = t0 + threadIdx.x;
+    if (u < T + shift && c < C) yb[(long long)c * ldy + u] = tile[threadIdx.x][i];
+  }
+}
+
 __global__ void embedding_kernel(const float* __restrict__ tab, int ldt, const long long* __restrict__ idx, long long rows,
                                  int rep, float* __restrict__ y, int ldy, int C) {
   EW_LOOP(i, rows * C) {
@@ -458,6 +477,15 @@ extern "C" int evk_transpose_bct_btc(const float* x, float* y, int32_t B, int32_
   EVK_REQUIRE(grid.y <= 65535 && grid.z <= 65535, EVK_ERR_ARG, "transpose: grid too large");
   transpose_kernel<<<grid, block, 0, ST>>>(x, y, C, T, ld, to_btc);
   return check_launch("transpose");
+}
+extern "C" int evk_transpose_rows(const float* x, int32_t ldx, int64_t x_sb, float* y, int32_t ldy, int64_t y_sb, int32_t B, int32_t T,
+                                  int32_t C, int32_t shift, evk_stream_t stream) {
+  EVK_REQUIRE(x && y && ldx >= C && shift >= 0 && ldy >= T + shift, EVK_ERR_ARG, "transpose_rows: bad arguments");
+  if ((long long)B * C * T == 0) return EVK_OK;
+  dim3 grid(cdiv(T + shift, 32), cdiv(C, 32), B), block(32, 8);
+  EVK_REQUIRE(grid.y <= 65535 && grid.z <= 65535, EVK_ERR_ARG, "transpose_rows: grid too large");
+  transpose_rows_kernel<<<grid, block, 0, ST>>>(x, ldx, x_sb, y, ldy, y_sb, T, C, shift);
+  return check_launch("transpose_rows");
 }
 extern "C" int evk_embedding(const float* table, int32_t ldt, const int64_t* idx, int64_t rows, int32_t rep, float* y,
                              int32_t ldy, int32_t C, evk_stream_t stream) {

@@ -28,9 +28,17 @@ constexpr int GT_THREADS = 192;
 struct GemmP {
   float* d; int ldd;
   const float* bias; const float* res; int ldr;
-  int M, N, K, act; float slope;
+  int M, N, K, act; float slope;                     // M = output positions per batch item, K = input channels
   int tiles_m, tiles_n, splits, kb_per_split;        // kb = K blocks of 32
   int atomic;
+  // implicit-GEMM convolution mode (stride 1): Z batch items, Q taps, period P; tap q reads input row pos + off[q]*P
+  int Z, Q, P;
+  int mode;                                          // 0: GEMM / conv forward-like;  1: conv weight gradient (see evk_conv_wgrad_tma)
+  int kbs;                                           // mode 1: K blocks per batch item
+  long long d_sq;                                    // mode 1: output pitch between taps
+  long long y_sb, r_sb;
+  const int* out_len;
+  int off[EVK_MAX_TAPS];
 };
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -53,9 +61,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)));
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(smem_u32(dst)),
-               "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
                : "memory");
 }
 // K-major, SWIZZLE_128B: start>>4 | LBO(ignored)=1 | SBO = 1024 B (8 rows x 128 B) | version 1 | layout 2
@@ -88,10 +96,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+struct MapB4 { CUtensorMap m[4]; };                  // mode 1 uses one map per (tap shift mod 4) residue copy, mode 0 only m[0]
+
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                                 const __grid_constant__ CUtensorMap mapB,
+                                                                 const __grid_constant__ MapB4 mapB4,
                                                                  const __grid_constant__ GemmP p) {
+  const CUtensorMap& mapB = mapB4.m[0];
   constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int TCOLS = 2 * BN;
   static_assert(TCOLS <= 512 && (TCOLS & (TCOLS - 1)) == 0, "TMEM columns");
@@ -107,7 +118,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;\n");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&mapA)));
-    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&mapB)));
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&mapB4.m[0])));
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "n"(TCOLS));
@@ -119,23 +130,42 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
   const uint32_t tmem_base = tmem_base_s;
 
   const int tiles_mn = p.tiles_m * p.tiles_n;
-  const int total = tiles_mn * p.splits;
-  const int kb_total = (p.K + BK - 1) / BK;
+  // mode 0: tile -> (outer = batch item or K split, m tile, n tile); K iterations = taps x channel blocks (splits > 1 only
+  //         in plain GEMM mode, Z == Q == 1).   mode 1: outer = (tap, K split); K iterations = batch items x row blocks.
+  const int total = p.mode ? tiles_mn * p.splits * p.Q : tiles_mn * p.splits * p.Z;
+  const int kb_total = p.mode ? p.Z * p.kbs : (p.K + BK - 1) / BK;
+  auto k_range = [&](int outer, int& k0, int& k1) {
+    if (p.mode) { const int sp = outer % p.splits; k0 = sp * p.kb_per_split; k1 = min(kb_total, k0 + p.kb_per_split); }
+    else if (p.splits > 1) { k0 = outer * p.kb_per_split; k1 = min(kb_total, k0 + p.kb_per_split); }
+    else { k0 = 0; k1 = p.Q * kb_total; }
+  };
 
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int sp = tile / tiles_mn, mn = tile - sp * tiles_mn;
+        const int outer = tile / tiles_mn, mn = tile - outer * tiles_mn;
         const int tm = mn / p.tiles_n, tn = mn - tm * p.tiles_n;
-        const int kb0 = sp * p.kb_per_split, kb1 = min(kb_total, kb0 + p.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int z = (p.splits > 1 || p.mode) ? 0 : outer;
+        int k0, k1;
+        k_range(outer, k0, k1);
+        for (int ki = k0; ki < k1; ++ki, ++it) {
           const int s = it % STAGES;
           mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
           mbar_expect_tx(&full[s], STAGE_BYTES);
           uint8_t* sa = gsm + (size_t)s * STAGE_BYTES;
-          tma_load_2d(sa, &mapA, kb * BK, tm * BM, &full[s]);
-          tma_load_2d(sa + A_BYTES, &mapB, kb * BK, tn * BN, &full[s]);
+          if (p.mode) {
+            const int b = ki / p.kbs, kb = ki - b * p.kbs, q = outer / p.splits;
+            tma_load_3d(sa, &mapA, kb * BK, tm * BM, b, &full[s]);
+            // TMA needs the inner coordinate 16-byte aligned: X[t + sh] is read from the copy delayed by r = (-sh) mod 4
+            // (xt_r[u] = X[u - r]) at the aligned coordinate t + sh + r
+            const int sh = p.off[q] * p.P, r = (((-sh) % 4) + 4) % 4;
+            tma_load_3d(sa + A_BYTES, &mapB4.m[r], kb * BK + (sh + r), tn * BN, b, &full[s]);
+          } else {
+            const int q = ki / kb_total, kb = ki - q * kb_total;
+            tma_load_3d(sa, &mapA, kb * BK, tm * BM + p.off[q] * p.P, z, &full[s]);
+            tma_load_3d(sa + A_BYTES, &mapB, kb * BK, tn * BN, q, &full[s]);
+          }
         }
       }
     }
@@ -145,8 +175,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
       constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
-        const int sp = tile / tiles_mn;
-        const int kb0 = sp * p.kb_per_split, kb1 = min(kb_total, kb0 + p.kb_per_split);
+        int kb0, kb1;
+        k_range(tile / tiles_mn, kb0, kb1);
         const int a = tcount & 1;
         mbar_wait(&acc_empty[a], ((tcount >> 1) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;\n");
@@ -169,8 +199,12 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
     const int lq = warp & 3;                                    // TMEM lane quadrant this warp may read
     int tcount = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
-      const int sp = tile / tiles_mn, mn = tile - sp * tiles_mn;
+      const int outer = tile / tiles_mn, mn = tile - outer * tiles_mn;
       const int tm = mn / p.tiles_n, tn = mn - tm * p.tiles_n;
+      const int z = (p.splits > 1 || p.mode) ? 0 : outer;
+      float* dz = p.mode ? p.d + (size_t)(outer / p.splits) * p.d_sq : p.d + (size_t)z * p.y_sb;
+      const float* rz = p.res ? p.res + (size_t)z * p.r_sb : nullptr;
+      const int olen = p.out_len ? p.out_len[z] : 0x7fffffff;
       const int a = tcount & 1;
       mbar_wait(&acc_full[a], (tcount >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n");
@@ -201,7 +235,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
           const int rl = i * 4 + r_sub, row = row_base + rl;
           if (row >= p.M || nn >= p.N) continue;
           float t[4] = {tr[rl * 33 + c4], tr[rl * 33 + c4 + 1], tr[rl * 33 + c4 + 2], tr[rl * 33 + c4 + 3]};
-          float* dp = p.d + (size_t)row * p.ldd + nn;
+          float* dp = dz + (size_t)row * p.ldd + nn;
+          const bool keep = (row / p.P) < olen;
           if (p.atomic) {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
@@ -209,8 +244,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
             continue;
           }
           t[0] += bv.x; t[1] += bv.y; t[2] += bv.z; t[3] += bv.w;
-          if (p.res) {
-            const float* rp = p.res + (size_t)row * p.ldr + nn;
+          if (rz) {
+            const float* rp = rz + (size_t)row * p.ldr + nn;
             if (full4 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
               const float4 rv = *reinterpret_cast<const float4*>(rp);
               t[0] += rv.x; t[1] += rv.y; t[2] += rv.z; t[3] += rv.w;
@@ -225,6 +260,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
             if (p.act == EVK_ACT_LRELU) t[e] = t[e] > 0.f ? t[e] : t[e] * p.slope;
             else if (p.act == EVK_ACT_RELU) t[e] = fmaxf(t[e], 0.f);
             else if (p.act == EVK_ACT_TANH) t[e] = tanhf(t[e]);
+            if (!keep) t[e] = 0.f;
           }
           if (full4 && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
             *reinterpret_cast<float4*>(dp) = make_float4(t[0], t[1], t[2], t[3]);
@@ -265,24 +301,40 @@ EncodeFn get_encode() {
   return fn;
 }
 
-// row-major [rows][K] fp32 with pitch ld (floats): box = [box_rows][32 floats], 128-byte swizzle
-bool make_map(CUtensorMap* m, const float* base, long long rows, long long K, long long ld, int box_rows) {
+// [outer][rows][K] fp32 (row pitch ld, outer pitch sb, in floats): box = [1][box_rows][32 floats], 128-byte swizzle.
+// Rows outside [0, rows) -- negative tap offsets included -- and channels past K are zero-filled by the TMA unit.
+bool make_map(CUtensorMap* m, const float* base, long long outer, long long sb, long long rows, long long K, long long ld, int box_rows) {
+  if (K <= 0 || rows <= 0 || outer <= 0 || K > 0xffffffffll || rows > 0xffffffffll) return false;
   EncodeFn enc = get_encode();
   if (!enc) return false;
-  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  cuuint64_t gdim[3] = {(cuuint64_t)K, (cuuint64_t)rows, (cuuint64_t)outer};
+  cuuint64_t gstr[2] = {(cuuint64_t)ld * 4, (cuuint64_t)(outer > 1 ? sb : rows * ld) * 4};
+  cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 int g_sm_count = 0;
 
+struct Operands {
+  const float* A; int lda; long long a_sb, a_rows;     // activations: [Z][a_rows][K]
+  const float* B; int ldb; long long b_sq;             // weights:     [Q][N][K]
+  long long b_rs;                                      // mode 1: pitch between the four residue copies of X^T
+};
+
 template <int BN, int STAGES>
-int launch_gemm(const float* A, int lda, const float* B, int ldb, GemmP& p, int splits, cudaStream_t st) {
-  CUtensorMap ma, mb;
-  if (!make_map(&ma, A, p.M, p.K, lda, BM) || !make_map(&mb, B, p.N, p.K, ldb, BN)) return 1;
+int launch_gemm(const Operands& o, GemmP& p, int splits, cudaStream_t st) {
+  CUtensorMap ma;
+  MapB4 mb;
+  if (p.mode) {            // A = dY^T [Z][M = N_out][K = rows], B = residue copies of X^T [Z][N = C_in][in_rows - r]
+    if (!make_map(&ma, o.A, p.Z, o.a_sb, p.M, p.K, o.lda, BM)) return 1;
+    for (int r = 0; r < 4; ++r)
+      if (!make_map(&mb.m[r], o.B + r * o.b_rs, p.Z, o.b_sq, p.N, o.a_rows + r, o.ldb, BN)) return 1;
+  } else {
+    if (!make_map(&ma, o.A, p.Z, o.a_sb, o.a_rows, p.K, o.lda, BM) || !make_map(&mb.m[0], o.B, p.Q, o.b_sq, p.N, p.K, o.ldb, BN)) return 1;
+    mb.m[1] = mb.m[2] = mb.m[3] = mb.m[0];
+  }
   constexpr int STAGE_BYTES = (BM + BN) * BK * 4;
   constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024;
   auto kern = gemm_tma_kernel<BN, STAGES>;
@@ -298,20 +350,23 @@ int launch_gemm(const float* A, int lda, const float* B, int ldb, GemmP& p, int 
   }
   p.tiles_m = cdiv(p.M, BM);
   p.tiles_n = cdiv(p.N, BN);
-  const int kb_total = cdiv(p.K, BK);
+  const int kb_total = p.mode ? p.Z * p.kbs : cdiv(p.K, BK);
   splits = max(1, min(splits, kb_total));
   p.kb_per_split = cdiv(kb_total, splits);
   p.splits = cdiv(kb_total, p.kb_per_split);
-  const long long total = (long long)p.tiles_m * p.tiles_n * p.splits;
+  const long long total = (long long)p.tiles_m * p.tiles_n * p.splits * (p.mode ? p.Q : p.Z);
+  if (total > 0x7fffffff) return 1;
   if (total <= 0) return EVK_OK;
   const int grid = (int)(total < (long long)g_sm_count ? total : (long long)g_sm_count);
   kern<<<grid, GT_THREADS, SMEM, st>>>(ma, mb, p);
   return check_launch("gemm_tma_kernel");
 }
 
-int run_gemm(const float* A, int lda, const float* B, int ldb, GemmP& p, int splits, cudaStream_t st) {
-  if (p.N > 128) return launch_gemm<256, 4>(A, lda, B, ldb, p, splits, st);
-  return launch_gemm<128, 6>(A, lda, B, ldb, p, splits, st);
+int run_gemm(const Operands& o, GemmP& p, int splits, cudaStream_t st) {
+  if (p.N > 128) return launch_gemm<256, 4>(o, p, splits, st);
+  if (p.N > 64) return launch_gemm<128, 6>(o, p, splits, st);
+  if (p.N > 32) return launch_gemm<64, 8>(o, p, splits, st);
+  return launch_gemm<32, 8>(o, p, splits, st);
 }
 
 }  // namespace
@@ -321,19 +376,32 @@ int g_backend_tma = 1;
 // returns 0 on success, < 0 on error, 1 if this launch is not eligible (caller falls through to gconv_tc / mma.sync)
 int gemm_tma_try(const evk_gconv_desc* d, cudaStream_t st) {
   if (!g_backend_tma) return 1;
-  if (d->Q != 1 || d->is != 1 || d->os != 1 || d->o0 != 0 || d->P != 1 || d->H != 1 || d->off[0] != 0) return 1;
-  if (d->in_len || d->out_len || d->J != d->Tin) return 1;
+  if (d->is != 1 || d->os != 1 || d->o0 != 0 || d->H != 1 || d->Q < 1 || d->Q > EVK_MAX_TAPS) return 1;
+  if (d->in_len) return 1;                                  // ragged inputs are masked at staging time by the tap kernel
   if ((d->C % 4) || (d->ldx % 4) || (d->ldw % 4) || (d->ldy % 4) || (d->res && (d->ldr % 4))) return 1;
   if (((uintptr_t)d->x | (uintptr_t)d->w | (uintptr_t)d->y) & 15) return 1;
-  const long long rows = (long long)d->Z * d->J;
-  if (d->Z > 1 && (d->x_sb != (long long)d->Tin * d->ldx || d->y_sb != (long long)d->J * d->ldy || d->w_sb != 0 ||
-                   (d->res && d->r_sb != (long long)d->J * d->ldr)))
-    return 1;
-  if (rows < 512 || d->C < 64 || d->N < 64 || rows > 0x7fffffff) return 1;       // small problems: the tap kernel's finer tiles win
+  if ((d->x_sb % 4) || (d->w_sq % 4) || (d->Z > 1 && d->w_sb != 0) || d->w_sq < 0 || d->x_sb < 0) return 1;
+  const long long npos = (long long)d->J * d->P, in_rows = (long long)d->Tin * d->P;
   GemmP p{};
   p.d = d->y; p.ldd = d->ldy; p.bias = d->bias; p.res = d->res; p.ldr = d->ldr;
-  p.M = (int)rows; p.N = d->N; p.K = d->C; p.act = d->act; p.slope = d->slope; p.atomic = 0;
-  return run_gemm(d->x, d->ldx, d->w, d->ldw, p, 1, st);
+  p.N = d->N; p.K = d->C; p.act = d->act; p.slope = d->slope; p.atomic = 0;
+  p.Q = d->Q; p.P = d->P; p.out_len = d->out_len;
+  for (int i = 0; i < EVK_MAX_TAPS; ++i) p.off[i] = i < d->Q ? d->off[i] : 0;
+  Operands o{};
+  o.B = d->w; o.ldb = d->ldw; o.b_sq = d->w_sq;
+  const bool flat = d->Q == 1 && d->off[0] == 0 && d->P == 1 && !d->out_len && d->J == d->Tin &&
+                    (d->Z == 1 || (d->x_sb == in_rows * d->ldx && d->y_sb == npos * d->ldy && (!d->res || d->r_sb == npos * d->ldr)));
+  if (flat) {                                               // Linear / 1x1 conv: batch folds into the row dimension
+    const long long rows = (long long)d->Z * npos;
+    if (rows < 512 || d->C < 64 || d->N < 64 || rows > 0x7fffffff) return 1;
+    p.M = (int)rows; p.Z = 1; p.y_sb = 0; p.r_sb = 0;
+    o.A = d->x; o.lda = d->ldx; o.a_sb = 0; o.a_rows = rows;
+  } else {                                                  // stride-1 conv: one TMA box per (tap, channel block), OOB rows = padding
+    if (npos < 64 || (long long)d->Z * npos < 2048 || d->C < 32 || d->N < 32 || npos > 0x7fffffff) return 1;
+    p.M = (int)npos; p.Z = d->Z; p.y_sb = d->y_sb; p.r_sb = d->r_sb;
+    o.A = d->x; o.lda = d->ldx; o.a_sb = d->x_sb; o.a_rows = in_rows;
+  }
+  return run_gemm(o, p, 1, st);
 }
 
 }  // namespace evk
@@ -352,7 +420,34 @@ extern "C" int evk_gemm_tf32(const float* A, int32_t lda, const float* B, int32_
   GemmP p{};
   p.d = D; p.ldd = ldd; p.bias = bias; p.res = res; p.ldr = ldr; p.M = M; p.N = N; p.K = K; p.act = act; p.slope = slope;
   p.atomic = splits > 1 ? 1 : 0;
-  int rc = run_gemm(A, lda, B, ldb, p, splits, st);
+  p.Z = 1; p.Q = 1; p.P = 1;
+  Operands o{A, lda, 0, M, B, ldb, 0, 0};
+  int rc = run_gemm(o, p, splits, st);
   EVK_REQUIRE(rc != 1, EVK_ERR_UNSUPPORTED, "gemm_tf32: cuTensorMapEncodeTiled unavailable or rejected the operand");
+  return rc;
+}
+
+
+// Weight gradient of a stride-1 (dilated / period-folded) convolution on the TMA/tcgen05 GEMM:
+//   dW[q][n][c] += sum_b sum_pos dY[b][pos][n] * X[b][pos + off[q]*P][c]
+// with both operands pre-transposed so that the contraction index is contiguous: dyt [B][N][ld_dy] (rows = J*P valid),
+// xt [4][B][C][ld_x]: copy r is X^T delayed by r positions, xt_r[b][c][u] = X[b][u - r][c] (Tin*P + r valid; TMA box
+// coordinates along the contiguous dimension must be 16-byte aligned, so a tap shift s reads copy r = (-s) mod 4 at the
+// aligned offset s + r; only the copies that occur need to be filled).  One output tile per (tap, n tile, c tile, K split); out-of-range rows (the conv padding)
+// are zero-filled by the copy engine.  Accumulates with fp32 atomics into dW (pitch ldw, tap pitch w_sq).
+extern "C" int evk_conv_wgrad_tma(const float* dyt, int32_t ld_dy, int64_t dy_sb, const float* xt, int32_t ld_x, int64_t x_sb, int64_t x_rs, float* dW,
+                                  int32_t ldw, int64_t w_sq, int32_t B, int32_t N, int32_t C, int32_t out_rows, int32_t in_rows,
+                                  int32_t Q, int32_t P, const int32_t* off, int32_t splits, cudaStream_t st) {
+  EVK_REQUIRE(B > 0 && N > 0 && C > 0 && out_rows > 0 && in_rows > 0 && Q > 0 && Q <= EVK_MAX_TAPS && off, EVK_ERR_ARG, "conv_wgrad_tma: bad sizes");
+  EVK_REQUIRE((ld_dy % 4) == 0 && (ld_x % 4) == 0 && (dy_sb % 4) == 0 && (x_sb % 4) == 0 && (x_rs % 4) == 0 && in_rows > 4 &&
+                  ((((uintptr_t)dyt) | ((uintptr_t)xt)) & 15) == 0,
+              EVK_ERR_ARG, "conv_wgrad_tma: operands must be 16-byte aligned with pitches that are multiples of 4 floats");
+  GemmP p{};
+  p.d = dW; p.ldd = ldw; p.d_sq = w_sq; p.M = N; p.N = C; p.K = out_rows; p.atomic = 1; p.mode = 1;
+  p.Z = B; p.Q = Q; p.P = P; p.kbs = cdiv(out_rows, BK);
+  for (int i = 0; i < EVK_MAX_TAPS; ++i) p.off[i] = i < Q ? off[i] : 0;
+  Operands o{dyt, ld_dy, dy_sb, in_rows, xt, ld_x, x_sb, x_rs};
+  int rc = run_gemm(o, p, splits < 1 ? 1 : splits, st);
+  EVK_REQUIRE(rc != 1, EVK_ERR_UNSUPPORTED, "conv_wgrad_tma: cuTensorMapEncodeTiled unavailable or rejected the operand");
   return rc;
 }

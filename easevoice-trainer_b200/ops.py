@@ -360,18 +360,24 @@ class _ConvFn(torch.autograd.Function):
             _, _, ldx = _rows(x)
             mma = _aligned(x, ldx) and _aligned(dy, N) and (G == 1 or (Cg % 4 == 0 and Ng % 4 == 0))
             rows = B * Tin
-            if (mma and USE_TMA_WGRAD and Q == 1 and stride == 1 and P == 1 and G == 1 and in_len is None and rows >= 2048
-                    and rows % 4 == 0 and C >= 64 and N >= 64 and not _lib().evk_get_precise()):
-                # dW[n][c] = sum_r dY[r][n] X[r][c]: both operands transposed once (rows become the contiguous K dim), then
-                # the TMA-fed tcgen05 GEMM with split-K accumulates straight into the packed-weight gradient
-                xt = torch.empty((C, rows), device=dy.device, dtype=torch.float32)
-                dyt = torch.empty((N, rows), device=dy.device, dtype=torch.float32)
-                _call("evk_transpose_bct_btc", _p(x), _p(xt), 1, C, rows, ldx, 0)
-                _call("evk_transpose_bct_btc", _p(dy), _p(dyt), 1, N, rows, N, 0)
-                tiles = ((N + 127) // 128) * ((C + 255) // 256 if C > 128 else 1)
-                splits = max(1, min(32, (148 + tiles // 2) // tiles, rows // 512))
-                _call("evk_gemm_tf32", _p(dyt), rows, _p(xt), rows, _p(dpa), lda, N, C, rows, None, None, 0, 0, ctypes.c_float(0.0),
-                      splits)
+            if (mma and USE_TMA_WGRAD and stride == 1 and G == 1 and in_len is None and B * J * P >= 2048 and J * P >= 64
+                    and C >= 32 and N >= 32 and not _lib().evk_get_precise()):
+                # dW[q][n][c] = sum_{b,pos} dY[b][pos][n] X[b][pos + off_q P][c]: both operands are transposed once (positions
+                # become the contiguous K dim), then the TMA-fed tcgen05 GEMM runs one output tile per (tap, n, c, K split)
+                # with the tap shift as a TMA coordinate (out-of-range rows = conv padding, zero-filled by the copy engine)
+                Ri, Ro = Tin * P, J * P
+                ldi, ldo = (Ri + 3 + 31) // 32 * 32, (Ro + 31) // 32 * 32        # 128-byte aligned rows for the TMA boxes
+                xt = torch.empty((4, B, C, ldi), device=dy.device, dtype=torch.float32)
+                dyt = torch.empty((B, N, ldo), device=dy.device, dtype=torch.float32)
+                for r in sorted({(-o_ * P) % 4 for o_ in offs}):         # delayed copies: xt[r][b][c][u] = x[b][u - r][c]
+                    _call("evk_transpose_rows", _p(x), ldx, Ri * ldx, _p(xt[r]), ldi, C * ldi, B, Ri, C, r)
+                _call("evk_transpose_rows", _p(dy), N, Ro * N, _p(dyt), ldo, N * ldo, B, Ro, N, 0)
+                tiles = Q * ((N + 127) // 128) * ((C + 255) // 256 if C > 128 else 1)
+                kblocks = B * ((Ro + 31) // 32)
+                splits = max(1, min(64, 148 // tiles, kblocks // 8))            # one full wave of (tile, split) CTAs
+                offa = (ctypes.c_int32 * Q)(*offs)
+                _call("evk_conv_wgrad_tma", _p(dyt), ldo, N * ldo, _p(xt), ldi, C * ldi, B * C * ldi, _p(dpa), lda, N * lda, B, N, C,
+                      Ro, Ri, Q, P, offa, splits)
             elif mma:
                 d = _desc(x=x, w=dpa, y=dy, res=None, bias=None, in_len=in_len, out_len=None,
                           x_sb=Tin * P * ldx, x_sh=Cg if G > 1 else 0, w_sb=0, w_sh=Ng * lda if G > 1 else 0, w_sq=N * lda,

@@ -71,6 +71,12 @@ def check_conv():
         ("discS 16->64 k41 s4 g4 (direct)", 2, 1000, 16, 64, 41, 4, 20, 1, 1, 4, 1, False, False),
         ("discS 256->1024 k41 s4 g64 (direct)", 2, 130, 256, 1024, 41, 4, 20, 1, 1, 64, 1, False, False),
         ("conv_post 16->1 k7 tanh", 2, 700, 16, 1, 7, 1, 3, 1, 1, 1, 3, False, False),
+        # large enough for the TMA implicit-GEMM path (csrc/gemm_tma.cu conv mode): taps via box coordinates, OOB = padding
+        ("TMA resblock k11 d1 128ch +res", 3, 1500, 128, 128, 11, 1, 5, 1, 1, 1, 1, True, False),
+        ("TMA resblock k7 d5 64ch", 2, 2100, 64, 64, 7, 1, 15, 5, 1, 1, 1, False, False),
+        ("TMA conv_pre k7 192->512", 5, 500, 192, 512, 7, 1, 3, 1, 1, 1, 0, False, False),
+        ("TMA discP 512->1024 k5 s1 p=3", 3, 310, 512, 1024, 5, 1, 2, 1, 3, 1, 1, False, False),
+        ("TMA k3 32->96 (C tail zero-fill)", 2, 1100, 36, 96, 3, 1, 1, 1, 1, 1, 0, False, False),
     ]
     for i, (name, B, Tin, C, N, Q, stride, pad, dil, P, G, act, use_res, masks) in enumerate(cfgs):
         g = _gen(100 + i)
