@@ -33,6 +33,8 @@ struct GemmP {
   int atomic;
   // implicit-GEMM convolution mode (stride 1): Z batch items, Q taps, period P; tap q reads input row pos + off[q]*P
   int Z, Q, P;
+  int os, o0;                                        // output position of tile row pos: ((o0 + (pos / P) * os) * P + pos % P)
+  int src[EVK_MAX_TAPS];                             // mode 0: which of the (up to 4) A tensor maps tap q reads (stride phases)
   int mode;                                          // 0: GEMM / conv forward-like;  1: conv weight gradient (see evk_conv_wgrad_tma)
   int kbs;                                           // mode 1: K blocks per batch item
   long long d_sq;                                    // mode 1: output pitch between taps
@@ -96,12 +98,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-struct MapB4 { CUtensorMap m[4]; };                  // mode 1 uses one map per (tap shift mod 4) residue copy, mode 0 only m[0]
-
+struct MapB4 { CUtensorMap m[4]; };                  // B: mode 1 uses one map per delayed copy of X^T, mode 0 only m[0]
+                                                     // A: mode 0 uses one map per stride phase of the input, mode 1 only m[0]
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_constant__ CUtensorMap mapA,
+__global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_constant__ MapB4 mapA4,
                                                                  const __grid_constant__ MapB4 mapB4,
                                                                  const __grid_constant__ GemmP p) {
+  const CUtensorMap& mapA = mapA4.m[0];
   const CUtensorMap& mapB = mapB4.m[0];
   constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
   constexpr int TCOLS = 2 * BN;
@@ -117,7 +120,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;\n");
-    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&mapA)));
+    asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&mapA4.m[0])));
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&mapB4.m[0])));
   }
   if (warp == 1) {
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
             tma_load_3d(sa + A_BYTES, &mapB4.m[r], kb * BK + (sh + r), tn * BN, b, &full[s]);
           } else {
             const int q = ki / kb_total, kb = ki - q * kb_total;
-            tma_load_3d(sa, &mapA, kb * BK, tm * BM + p.off[q] * p.P, z, &full[s]);
+            tma_load_3d(sa, &mapA4.m[p.src[q]], kb * BK, tm * BM + p.off[q] * p.P, z, &full[s]);
             tma_load_3d(sa + A_BYTES, &mapB, kb * BK, tn * BN, q, &full[s]);
           }
         }
@@ -235,8 +238,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
           const int rl = i * 4 + r_sub, row = row_base + rl;
           if (row >= p.M || nn >= p.N) continue;
           float t[4] = {tr[rl * 33 + c4], tr[rl * 33 + c4 + 1], tr[rl * 33 + c4 + 2], tr[rl * 33 + c4 + 3]};
-          float* dp = dz + (size_t)row * p.ldd + nn;
-          const bool keep = (row / p.P) < olen;
+          const int jo = p.o0 + (row / p.P) * p.os;
+          const size_t orow = (size_t)jo * p.P + (row % p.P);
+          float* dp = dz + orow * p.ldd + nn;
+          const bool keep = jo < olen;
           if (p.atomic) {
 #pragma unroll
             for (int e = 0; e < 4; ++e)
@@ -245,7 +250,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
           }
           t[0] += bv.x; t[1] += bv.y; t[2] += bv.z; t[3] += bv.w;
           if (rz) {
-            const float* rp = rz + (size_t)row * p.ldr + nn;
+            const float* rp = rz + orow * p.ldr + nn;
             if (full4 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
               const float4 rv = *reinterpret_cast<const float4*>(rp);
               t[0] += rv.x; t[1] += rv.y; t[2] += rv.z; t[3] += rv.w;
@@ -321,18 +326,23 @@ struct Operands {
   const float* A; int lda; long long a_sb, a_rows;     // activations: [Z][a_rows][K]
   const float* B; int ldb; long long b_sq;             // weights:     [Q][N][K]
   long long b_rs;                                      // mode 1: pitch between the four residue copies of X^T
+  int a_phases; long long a_ps;                        // mode 0: stride phases of the input and their pitch
 };
 
 template <int BN, int STAGES>
 int launch_gemm(const Operands& o, GemmP& p, int splits, cudaStream_t st) {
-  CUtensorMap ma;
-  MapB4 mb;
+  MapB4 ma, mb;
   if (p.mode) {            // A = dY^T [Z][M = N_out][K = rows], B = residue copies of X^T [Z][N = C_in][in_rows - r]
-    if (!make_map(&ma, o.A, p.Z, o.a_sb, p.M, p.K, o.lda, BM)) return 1;
+    if (!make_map(&ma.m[0], o.A, p.Z, o.a_sb, p.M, p.K, o.lda, BM)) return 1;
+    ma.m[1] = ma.m[2] = ma.m[3] = ma.m[0];
     for (int r = 0; r < 4; ++r)
       if (!make_map(&mb.m[r], o.B + r * o.b_rs, p.Z, o.b_sq, p.N, o.a_rows + r, o.ldb, BN)) return 1;
   } else {
-    if (!make_map(&ma, o.A, p.Z, o.a_sb, o.a_rows, p.K, o.lda, BM) || !make_map(&mb.m[0], o.B, p.Q, o.b_sq, p.N, p.K, o.ldb, BN)) return 1;
+    for (int ph = 0; ph < 4; ++ph) {
+      if (ph < o.a_phases) { if (!make_map(&ma.m[ph], o.A + ph * o.a_ps, p.Z, o.a_sb, o.a_rows, p.K, o.lda, BM)) return 1; }
+      else ma.m[ph] = ma.m[0];
+    }
+    if (!make_map(&mb.m[0], o.B, p.Q, o.b_sq, p.N, p.K, o.ldb, BN)) return 1;
     mb.m[1] = mb.m[2] = mb.m[3] = mb.m[0];
   }
   constexpr int STAGE_BYTES = (BM + BN) * BK * 4;
@@ -373,30 +383,36 @@ int run_gemm(const Operands& o, GemmP& p, int splits, cudaStream_t st) {
 
 int g_backend_tma = 1;
 
-// returns 0 on success, < 0 on error, 1 if this launch is not eligible (caller falls through to gconv_tc / mma.sync)
-int gemm_tma_try(const evk_gconv_desc* d, cudaStream_t st) {
+// returns 0 on success, < 0 on error, 1 if this launch is not eligible (caller falls through to gconv_tc / mma.sync).
+// phases > 1: d->x points at `phases` stride-phase copies of the input (pitch x_ps floats, see evk_phase_split) and tap q
+// reads copy src[q] with row shift off[q] -- a strided conv expressed as a stride-1 multi-source tap sum.
+int gemm_tma_run(const evk_gconv_desc* d, int phases, long long x_ps, const int* src, cudaStream_t st) {
   if (!g_backend_tma) return 1;
-  if (d->is != 1 || d->os != 1 || d->o0 != 0 || d->H != 1 || d->Q < 1 || d->Q > EVK_MAX_TAPS) return 1;
+  if (d->is != 1 || d->os < 1 || d->o0 < 0 || d->H != 1 || d->Q < 1 || d->Q > EVK_MAX_TAPS || phases < 1 || phases > 4) return 1;
   if (d->in_len) return 1;                                  // ragged inputs are masked at staging time by the tap kernel
   if ((d->C % 4) || (d->ldx % 4) || (d->ldw % 4) || (d->ldy % 4) || (d->res && (d->ldr % 4))) return 1;
   if (((uintptr_t)d->x | (uintptr_t)d->w | (uintptr_t)d->y) & 15) return 1;
-  if ((d->x_sb % 4) || (d->w_sq % 4) || (d->Z > 1 && d->w_sb != 0) || d->w_sq < 0 || d->x_sb < 0) return 1;
+  if ((d->x_sb % 4) || (d->w_sq % 4) || (x_ps % 4) || (d->Z > 1 && d->w_sb != 0) || d->w_sq < 0 || d->x_sb < 0) return 1;
   const long long npos = (long long)d->J * d->P, in_rows = (long long)d->Tin * d->P;
   GemmP p{};
   p.d = d->y; p.ldd = d->ldy; p.bias = d->bias; p.res = d->res; p.ldr = d->ldr;
   p.N = d->N; p.K = d->C; p.act = d->act; p.slope = d->slope; p.atomic = 0;
-  p.Q = d->Q; p.P = d->P; p.out_len = d->out_len;
-  for (int i = 0; i < EVK_MAX_TAPS; ++i) p.off[i] = i < d->Q ? d->off[i] : 0;
+  p.Q = d->Q; p.P = d->P; p.out_len = d->out_len; p.os = d->os; p.o0 = d->o0;
+  for (int i = 0; i < EVK_MAX_TAPS; ++i) {
+    p.off[i] = i < d->Q ? d->off[i] : 0;
+    p.src[i] = (src && i < d->Q) ? src[i] : 0;
+    if (p.src[i] < 0 || p.src[i] >= phases) return 1;
+  }
   Operands o{};
-  o.B = d->w; o.ldb = d->ldw; o.b_sq = d->w_sq;
-  const bool flat = d->Q == 1 && d->off[0] == 0 && d->P == 1 && !d->out_len && d->J == d->Tin &&
+  o.B = d->w; o.ldb = d->ldw; o.b_sq = d->w_sq; o.a_phases = phases; o.a_ps = x_ps;
+  const bool flat = phases == 1 && d->Q == 1 && d->off[0] == 0 && d->P == 1 && !d->out_len && d->J == d->Tin && d->os == 1 && d->o0 == 0 &&
                     (d->Z == 1 || (d->x_sb == in_rows * d->ldx && d->y_sb == npos * d->ldy && (!d->res || d->r_sb == npos * d->ldr)));
   if (flat) {                                               // Linear / 1x1 conv: batch folds into the row dimension
     const long long rows = (long long)d->Z * npos;
     if (rows < 512 || d->C < 64 || d->N < 64 || rows > 0x7fffffff) return 1;
     p.M = (int)rows; p.Z = 1; p.y_sb = 0; p.r_sb = 0;
     o.A = d->x; o.lda = d->ldx; o.a_sb = 0; o.a_rows = rows;
-  } else {                                                  // stride-1 conv: one TMA box per (tap, channel block), OOB rows = padding
+  } else {                                                  // stride-1 tap sum: one TMA box per (tap, channel block), OOB rows = padding
     if (npos < 64 || (long long)d->Z * npos < 2048 || d->C < 32 || d->N < 32 || npos > 0x7fffffff) return 1;
     p.M = (int)npos; p.Z = d->Z; p.y_sb = d->y_sb; p.r_sb = d->r_sb;
     o.A = d->x; o.lda = d->ldx; o.a_sb = d->x_sb; o.a_rows = in_rows;
@@ -404,11 +420,24 @@ int gemm_tma_try(const evk_gconv_desc* d, cudaStream_t st) {
   return run_gemm(o, p, 1, st);
 }
 
+int gemm_tma_try(const evk_gconv_desc* d, cudaStream_t st) { return gemm_tma_run(d, 1, 0, nullptr, st); }
+
 }  // namespace evk
 
 using namespace evk;
 
 extern "C" int evk_set_backend_tma(int32_t on) { g_backend_tma = on ? 1 : 0; return EVK_OK; }
+
+// Strided convolution forward on the TMA/tcgen05 kernel.  d describes the conv as a STRIDE-1 tap sum over `phases` (= the
+// conv stride, <= 4) phase copies of the input produced by evk_phase_split: d->x = copy 0, copies x_ps floats apart, each
+// [Z][Tin * P][ldx] with d->Tin = ceil(T / stride); tap q reads copy src[q] at row shift off[q] (src, d->off: host arrays).
+// Returns EVK_ERR_UNSUPPORTED when the launch is not eligible (caller keeps the strided mma.sync kernel).
+extern "C" int evk_gconv_fwd_phased(const evk_gconv_desc* d, int32_t phases, int64_t x_ps, const int32_t* src, cudaStream_t st) {
+  EVK_REQUIRE(d && src, EVK_ERR_ARG, "gconv_fwd_phased: null argument");
+  int rc = gemm_tma_run(d, phases, x_ps, src, st);
+  EVK_REQUIRE(rc != 1, EVK_ERR_UNSUPPORTED, "gconv_fwd_phased: launch not eligible for the TMA kernel");
+  return rc;
+}
 
 extern "C" int evk_gemm_tf32(const float* A, int32_t lda, const float* B, int32_t ldb, float* D, int32_t ldd, int32_t M, int32_t N,
                              int32_t K, const float* bias, const float* res, int32_t ldr, int32_t act, float slope, int32_t splits,
@@ -421,7 +450,8 @@ extern "C" int evk_gemm_tf32(const float* A, int32_t lda, const float* B, int32_
   p.d = D; p.ldd = ldd; p.bias = bias; p.res = res; p.ldr = ldr; p.M = M; p.N = N; p.K = K; p.act = act; p.slope = slope;
   p.atomic = splits > 1 ? 1 : 0;
   p.Z = 1; p.Q = 1; p.P = 1;
-  Operands o{A, lda, 0, M, B, ldb, 0, 0};
+  Operands o{A, lda, 0, M, B, ldb, 0, 0, 1, 0};
+  p.os = 1; p.o0 = 0;
   int rc = run_gemm(o, p, splits, st);
   EVK_REQUIRE(rc != 1, EVK_ERR_UNSUPPORTED, "gemm_tf32: cuTensorMapEncodeTiled unavailable or rejected the operand");
   return rc;
@@ -444,9 +474,9 @@ extern "C" int evk_conv_wgrad_tma(const float* dyt, int32_t ld_dy, int64_t dy_sb
               EVK_ERR_ARG, "conv_wgrad_tma: operands must be 16-byte aligned with pitches that are multiples of 4 floats");
   GemmP p{};
   p.d = dW; p.ldd = ldw; p.d_sq = w_sq; p.M = N; p.N = C; p.K = out_rows; p.atomic = 1; p.mode = 1;
-  p.Z = B; p.Q = Q; p.P = P; p.kbs = cdiv(out_rows, BK);
+  p.Z = B; p.Q = Q; p.P = P; p.kbs = cdiv(out_rows, BK); p.os = 1; p.o0 = 0;
   for (int i = 0; i < EVK_MAX_TAPS; ++i) p.off[i] = i < Q ? off[i] : 0;
-  Operands o{dyt, ld_dy, dy_sb, in_rows, xt, ld_x, x_sb, x_rs};
+  Operands o{dyt, ld_dy, dy_sb, in_rows, xt, ld_x, x_sb, x_rs, 1, 0};
   int rc = run_gemm(o, p, splits < 1 ? 1 : splits, st);
   EVK_REQUIRE(rc != 1, EVK_ERR_UNSUPPORTED, "conv_wgrad_tma: cuTensorMapEncodeTiled unavailable or rejected the operand");
   return rc;

@@ -14,6 +14,7 @@ import torch
 from . import lib as L
 
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH = 0, 1, 2, 3
+USE_TMA_STRIDED = True   # strided conv forward: phase-split input + stride-1 multi-source tap sum on the TMA kernel
 USE_TMA_WGRAD = True     # weight gradients of tap-free layers: transposes + split-K TMA/tcgen05 GEMM
 UN_SCALE, UN_LRELU, UN_TANH, UN_MISH, UN_RELU, UN_TANH_FROM_OUT = 0, 1, 2, 3, 4, 5
 
@@ -310,8 +311,27 @@ class _ConvFn(torch.autograd.Function):
             res = _cl(res)
         off = [q * dil - pad for q in range(Q)]
         gk = dict(H=G, x_sh=Cg, w_sh=Ng * lda, y_sh=Ng, b_sh=Ng) if G > 1 else {}
-        _fwd_like(x, Tin, pa, 0, 1, Q, lda, N * lda, Cg, Ng, y, J=J, P=P, is_=stride, os_=1, o0=0, Tout=J, off=off,
-                  bias=bias, res=res, act=act, slope=slope, in_len=in_len, out_len=out_len, **gk)
+        _, _, ldx = _rows(x)
+        if (USE_TMA_STRIDED and 1 < stride <= 4 and G == 1 and in_len is None and C % 4 == 0 and C >= 32 and N >= 32 and lda % 4 == 0
+                and B * J * P >= 2048 and J * P >= 64 and _aligned(x, ldx) and not _lib().evk_get_precise()):
+            # strided conv = stride-1 tap sum over `stride` phase copies of the input (tap u = q*dil - pad reads phase u mod s
+            # at shift floor(u / s)): runs on the TMA/tcgen05 kernel instead of the strided mma.sync one
+            Jp = (Tin + stride - 1) // stride
+            xs = torch.empty((stride, B, Jp * P, C), device=x.device, dtype=torch.float32)
+            _call("evk_phase_split", _p(x), ldx, Tin * P * ldx, _p(xs), B * Jp * P * C, B, Tin, P, C, stride, Jp)
+            ldr = _rows(res)[2] if res is not None else 0
+            d = _desc(x=xs, w=pa, y=y, res=res, bias=bias, in_len=None, out_len=out_len, x_sb=Jp * P * C, x_sh=0, w_sb=0, w_sh=0,
+                      w_sq=N * lda, y_sb=J * P * N, y_sh=0, r_sb=J * P * ldr, r_sh=0, ldx=C, ldw=lda, ldy=N, ldr=ldr, b_sh=0,
+                      Z=B, H=1, C=C, N=N, Q=Q, G=1, Tin=Jp, J=J, P=P, is_=1, os_=1, o0=0, Tout=J, act=act, slope=float(slope),
+                      off=[u // stride for u in off])
+            srca = (ctypes.c_int32 * Q)(*[u % stride for u in off])
+            global _launches
+            _launches += 1
+            _timed("evk_gconv_fwd_phased", lambda: L.check(_lib().evk_gconv_fwd_phased(ctypes.byref(d), stride, B * Jp * P * C, srca, _st())),
+                   2.0 * B * J * P * N * C * Q)
+        else:
+            _fwd_like(x, Tin, pa, 0, 1, Q, lda, N * lda, Cg, Ng, y, J=J, P=P, is_=stride, os_=1, o0=0, Tout=J, off=off,
+                      bias=bias, res=res, act=act, slope=slope, in_len=in_len, out_len=out_len, **gk)
         ctx.cfg = cfg
         ctx.dims = (B, Tin, C, N, J, lda)
         ctx.has = (bias is not None, res is not None)

@@ -273,6 +273,14 @@ int evk_set_backend_tma(int32_t on);
 int evk_conv_wgrad_tma(const float* dyt, int32_t ld_dy, int64_t dy_sb, const float* xt, int32_t ld_x, int64_t x_sb, int64_t x_rs, float* dW,
                        int32_t ldw, int64_t w_sq, int32_t B, int32_t N, int32_t C, int32_t out_rows, int32_t in_rows,
                        int32_t Q, int32_t P, const int32_t* off, int32_t splits, evk_stream_t stream);
+/* Strided conv forward on the same kernel: the input is first split into `stride` phase copies
+ *   xs[rho][b][j*P + w][c] = x[b][(j*stride + rho)*P + w][c]   (zero for j*stride + rho >= T; j < Jp = ceil(T / stride))
+ * and the conv becomes a stride-1 tap sum in which tap q (u = q*dil - pad) reads copy src[q] = u mod stride at row shift
+ * off[q] = floor(u / stride).  d describes that stride-1 form (d->x = copy 0, d->Tin = Jp, d->is = 1, d->off = shifts);
+ * copies are x_ps floats apart; src is a HOST array.  Returns EVK_ERR_UNSUPPORTED if the launch is not eligible. */
+int evk_phase_split(const float* x, int32_t ldx, int64_t x_sb, float* xs, int64_t xs_ps, int32_t B, int32_t T, int32_t P,
+                    int32_t C, int32_t stride, int32_t Jp, evk_stream_t stream);
+int evk_gconv_fwd_phased(const evk_gconv_desc* d, int32_t phases, int64_t x_ps, const int32_t* src, evk_stream_t stream);
 /* [B][T][ldx] (C valid, batch pitch x_sb) -> [B][C][ldy] (T + shift valid, batch pitch y_sb):
  * y[b][c][u] = x[b][u - shift][c], zero for u < shift. */
 int evk_transpose_rows(const float* x, int32_t ldx, int64_t x_sb, float* y, int32_t ldy, int64_t y_sb, int32_t B, int32_t T,

@@ -77,6 +77,11 @@ def check_conv():
         ("TMA conv_pre k7 192->512", 5, 500, 192, 512, 7, 1, 3, 1, 1, 1, 0, False, False),
         ("TMA discP 512->1024 k5 s1 p=3", 3, 310, 512, 1024, 5, 1, 2, 1, 3, 1, 1, False, False),
         ("TMA k3 32->96 (C tail zero-fill)", 2, 1100, 36, 96, 3, 1, 1, 1, 1, 1, 0, False, False),
+        # strided forwards through evk_phase_split + the multi-source tap sum; dgrad phases use the os/o0 output mapping
+        ("TMA discP 128->512 k5 s3 p=2 (phased)", 4, 341, 128, 512, 5, 3, 2, 1, 2, 1, 1, False, False),
+        ("TMA discP 32->128 k5 s3 p=5 (phased)", 3, 410, 32, 128, 5, 3, 2, 1, 5, 1, 0, False, False),
+        ("TMA ssl_proj k2 s2 768->768 (phased)", 6, 700, 768, 768, 2, 2, 0, 1, 1, 1, 0, False, False),
+        ("TMA k41 s4 64->64 (phased)", 3, 3000, 64, 64, 41, 4, 20, 1, 1, 1, 1, False, False),
     ]
     for i, (name, B, Tin, C, N, Q, stride, pad, dil, P, G, act, use_res, masks) in enumerate(cfgs):
         g = _gen(100 + i)
@@ -149,7 +154,8 @@ def check_conv_transpose():
     from easevoice_trainer_b200 import ops
     out = []
     for i, (cin, cout, k, s, T) in enumerate([(512, 256, 16, 10, 32), (256, 128, 16, 8, 57), (128, 64, 8, 2, 130),
-                                               (64, 32, 2, 2, 300), (32, 16, 2, 2, 500)]):
+                                               (64, 32, 2, 2, 300), (32, 16, 2, 2, 500),
+                                               (256, 128, 16, 8, 1100), (64, 32, 4, 2, 1500)]):   # large: TMA kernel, os/o0 epilogue
         g = _gen(200 + i)
         x = torch.randn(2, cin, T, generator=g)
         v = torch.randn(cin, cout, k, generator=g) * 0.05
