@@ -319,11 +319,13 @@ def run_ours(args):
         fl = sum(r["flops"] * r["count"] for r in table)
         tm = sum(r["ms"] * r["count"] for r in table)
         ach = fl / (tm * 1e-3) / 1e12
-        extra["roofline"] = dict(bound="tensor", kernel="gconv_f_kernel (TF32 mma.sync implicit-GEMM conv, fwd + dgrad launches)",
+        extra["roofline"] = dict(bound="tensor", kernel="gemm_tma_kernel (TMA-fed persistent tcgen05 TF32 implicit-GEMM: conv fwd / dgrad / strided-phase launches; "
+                                                        "the 16-channel stage stays on gconv_tc_kernel)",
                                  achieved=ach, peak=tf_sus, unit="TFLOP/s", frac=ach / tf_sus, traffic=None,
                                  peak_source=f"{src} cuBLAS bf16 sustained; the kernel computes in TF32 whose nominal peak is half of bf16",
-                                 how="flops-weighted over the heaviest layer shapes of the step, each 20 back-to-back launches "
-                                     "between CUDA events on rotating (> L2) buffers",
+                                 how="flops-weighted over the heaviest layer shapes of the step, each 24 back-to-back launches "
+                                     "(graph replay) between CUDA events on 6 rotating (> L2) buffer sets; strided layers include their phase-split pass; "
+                                     "traffic: profiles/r1_ncu_full_gemm_tma.md",
                                  layers=[{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in table])
         # ---- fused mel kernel standalone: 16 x 10 s at the label rate, |X| + log-mel emitted
         Lw = batch["wav"].shape[1]

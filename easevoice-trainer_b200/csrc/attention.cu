@@ -117,11 +117,13 @@ __global__ void rel_dE_kernel(const float* __restrict__ band, const float* __res
   const int rd = blockIdx.y * blockDim.x + threadIdx.x;
   if (rd >= W * dk) return;
   const int r = rd / dk, d = rd - r * dk;
-  const long long r0 = (long long)blockIdx.x * rows_per_block, r1 = min(nrows, r0 + rows_per_block);
+  const int r0 = blockIdx.x * rows_per_block, r1 = (int)min(nrows, (long long)r0 + rows_per_block);   // nrows < 2^31 (checked by the host)
   float acc = 0.f;
-  for (long long zi = r0; zi < r1; ++zi) {
-    const int i = (int)(zi % T), z = (int)(zi / T), b = z / H, h = z - b * H;
-    acc = fmaf(band[zi * W + r], x[((long long)b * T + i) * ldx + h * dk + d], acc);
+  int i = r0 % T, z = r0 / T;
+  for (int zi = r0; zi < r1; ++zi) {
+    const int b = z / H, h = z - b * H;
+    acc = fmaf(band[(long long)zi * W + r], x[((long long)b * T + i) * ldx + h * dk + d], acc);
+    if (++i == T) { i = 0; ++z; }
   }
   atomicAdd(&dE[rd], acc);
 }
@@ -201,7 +203,8 @@ extern "C" int evk_relk_bwd(const float* drel, const float* q, int32_t ldq, cons
   relk_dq_kernel<<<g1(nrows * dk), 256, 0, ST>>>(drel, E, H, T, dk, W, dq, lddq, nrows * dk);
   int rc = check_launch("relk_dq");
   if (rc) return rc;
-  const int rpb = 256;
+  EVK_REQUIRE(nrows < 0x7fffffffLL, EVK_ERR_ARG, "relk_bwd: too many rows");
+  const int rpb = 32;
   dim3 grid(cdiv(nrows, rpb), cdiv(W * dk, 128));
   rel_dE_kernel<<<grid, 128, 0, ST>>>(drel, q, ldq, H, T, dk, W, dE, nrows, rpb);
   return check_launch("relk_dE");
@@ -232,7 +235,8 @@ extern "C" int evk_relv_bwd(const float* band, const float* dout, int32_t lddo, 
   relk_logits_kernel<<<g1(nrows * W), 256, 0, ST>>>(dout, lddo, E, H, T, dk, W, dband, nrows * W);
   int rc = check_launch("relv_dband");
   if (rc) return rc;
-  const int rpb = 256;
+  EVK_REQUIRE(nrows < 0x7fffffffLL, EVK_ERR_ARG, "relv_bwd: too many rows");
+  const int rpb = 32;
   dim3 grid(cdiv(nrows, rpb), cdiv(W * dk, 128));
   rel_dE_kernel<<<grid, 128, 0, ST>>>(band, dout, lddo, H, T, dk, W, dE, nrows, rpb);
   return check_launch("relv_dE");

@@ -380,24 +380,42 @@ class _ConvFn(torch.autograd.Function):
             _, _, ldx = _rows(x)
             mma = _aligned(x, ldx) and _aligned(dy, N) and (G == 1 or (Cg % 4 == 0 and Ng % 4 == 0))
             rows = B * Tin
-            if (mma and USE_TMA_WGRAD and stride == 1 and G == 1 and in_len is None and B * J * P >= 2048 and J * P >= 64
-                    and C >= 32 and N >= 32 and not _lib().evk_get_precise()):
-                # dW[q][n][c] = sum_{b,pos} dY[b][pos][n] X[b][pos + off_q P][c]: both operands are transposed once (positions
+            if (mma and USE_TMA_WGRAD and 1 <= stride <= 4 and (stride == 1 or dil == 1) and G == 1 and in_len is None
+                    and B * J * P >= 2048 and J * P >= 64 and C >= 32 and N >= 32 and C % 4 == 0 and not _lib().evk_get_precise()):
+                # dW[q][n][c] = sum_{b,pos} dY[b][pos][n] X[b][pos + shift_q][c]: both operands are transposed once (positions
                 # become the contiguous K dim), then the TMA-fed tcgen05 GEMM runs one output tile per (tap, n, c, K split)
-                # with the tap shift as a TMA coordinate (out-of-range rows = conv padding, zero-filled by the copy engine)
-                Ri, Ro = Tin * P, J * P
-                ldi, ldo = (Ri + 3 + 31) // 32 * 32, (Ro + 31) // 32 * 32        # 128-byte aligned rows for the TMA boxes
-                xt = torch.empty((4, B, C, ldi), device=dy.device, dtype=torch.float32)
+                # with the tap shift as a TMA coordinate (out-of-range rows = conv padding, zero-filled by the copy engine).
+                # A strided conv is first split into `stride` phase copies of X (as in the forward): taps u = q - pad with
+                # u mod stride == rho form a stride-1 problem on copy rho with shifts floor(u / stride).
+                Ro = J * P
+                ldo = (Ro + 31) // 32 * 32                                   # 128-byte aligned rows for the TMA boxes
                 dyt = torch.empty((B, N, ldo), device=dy.device, dtype=torch.float32)
-                for r in sorted({(-o_ * P) % 4 for o_ in offs}):         # delayed copies: xt[r][b][c][u] = x[b][u - r][c]
-                    _call("evk_transpose_rows", _p(x), ldx, Ri * ldx, _p(xt[r]), ldi, C * ldi, B, Ri, C, r)
                 _call("evk_transpose_rows", _p(dy), N, Ro * N, _p(dyt), ldo, N * ldo, B, Ro, N, 0)
-                tiles = Q * ((N + 127) // 128) * ((C + 255) // 256 if C > 128 else 1)
-                kblocks = B * ((Ro + 31) // 32)
-                splits = max(1, min(64, 148 // tiles, kblocks // 8))            # one full wave of (tile, split) CTAs
-                offa = (ctypes.c_int32 * Q)(*offs)
-                _call("evk_conv_wgrad_tma", _p(dyt), ldo, N * ldo, _p(xt), ldi, C * ldi, B * C * ldi, _p(dpa), lda, N * lda, B, N, C,
-                      Ro, Ri, Q, P, offa, splits)
+                if stride == 1:
+                    srcs = [(x, ldx, Tin, list(range(Q)), offs)]
+                else:
+                    Jp = (Tin + stride - 1) // stride
+                    xs = torch.empty((stride, B, Jp * P, C), device=dy.device, dtype=torch.float32)
+                    _call("evk_phase_split", _p(x), ldx, Tin * P * ldx, _p(xs), B * Jp * P * C, B, Tin, P, C, stride, Jp)
+                    srcs = []
+                    for rho in range(stride):
+                        qs = [q for q in range(Q) if offs[q] % stride == rho]
+                        if qs:
+                            srcs.append((xs[rho], C, Jp, qs, [offs[q] // stride for q in qs]))
+                for xsrc, ldsrc, Tsrc, qs, shifts in srcs:
+                    Ri = Tsrc * P
+                    ldi = (Ri + 3 + 31) // 32 * 32
+                    xt = torch.empty((4, B, C, ldi), device=dy.device, dtype=torch.float32)
+                    for r in sorted({(-sh * P) % 4 for sh in shifts}):      # delayed copies: xt[r][b][c][u] = x[b][u - r][c]
+                        _call("evk_transpose_rows", _p(xsrc), ldsrc, Ri * ldsrc, _p(xt[r]), ldi, C * ldi, B, Ri, C, r)
+                    nq = len(qs)
+                    qstep = (qs[1] - qs[0]) if nq > 1 else 1
+                    tiles = nq * ((N + 127) // 128) * ((C + 255) // 256 if C > 128 else 1)
+                    kblocks = B * ((Ro + 31) // 32)
+                    splits = max(1, min(64, 148 // tiles, kblocks // 8))        # one full wave of (tile, split) CTAs
+                    offa = (ctypes.c_int32 * nq)(*shifts)
+                    _call("evk_conv_wgrad_tma", _p(dyt), ldo, N * ldo, _p(xt), ldi, C * ldi, B * C * ldi,
+                          dpa.data_ptr() + 4 * qs[0] * N * lda, lda, qstep * N * lda, B, N, C, Ro, Ri, nq, P, offa, splits)
             elif mma:
                 d = _desc(x=x, w=dpa, y=dy, res=None, bias=None, in_len=in_len, out_len=None,
                           x_sb=Tin * P * ldx, x_sh=Cg if G > 1 else 0, w_sb=0, w_sh=Ng * lda if G > 1 else 0, w_sq=N * lda,
