@@ -96,13 +96,19 @@ __device__ __forceinline__ void split4(const float (&x)[4], uint32_t (&hi)[4], u
 }
 template <bool PR>
 __device__ __forceinline__ void mma_p(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4], float b0, float b1) {
-  uint32_t bh[2] = {f2tf32(b0), f2tf32(b1)};
   if (PR) {
+    uint32_t bh[2] = {f2tf32(b0), f2tf32(b1)};
     uint32_t bl[2] = {f2tf32(b0 - __uint_as_float(bh[0])), f2tf32(b1 - __uint_as_float(bh[1]))};
     mma_tf32(c, al, bh);
     mma_tf32(c, ah, bl);
+    mma_tf32(c, ah, bh);
+  } else {
+    // the B operand (K / V / Q / dO tile rows from shared memory) is fed as raw fp32 bits: the tensor core ignores the low
+    // 13 mantissa bits (truncation, as the TMA-fed tcgen05 GEMMs do); 128 of the 160 cvt.rna per key tile sat on the
+    // critical path next to only 64 mma.  A operands (Q, dO, K, V fragments loaded once; P / dS) stay round-to-nearest.
+    uint32_t bh[2] = {__float_as_uint(b0), __float_as_uint(b1)};
+    mma_tf32(c, ah, bh);
   }
-  mma_tf32(c, ah, bh);
 }
 
 // C[16 x 64] = A[16 x 32] * T^T, T = smem tile [64 rows x 32] ("row n, channel k" -> B(k, n))
