@@ -406,8 +406,10 @@ class _ConvFn(torch.autograd.Function):
                     Ri = Tsrc * P
                     ldi = (Ri + 3 + 31) // 32 * 32
                     xt = torch.empty((4, B, C, ldi), device=dy.device, dtype=torch.float32)
-                    for r in sorted({(-sh * P) % 4 for sh in shifts}):      # delayed copies: xt[r][b][c][u] = x[b][u - r][c]
-                        _call("evk_transpose_rows", _p(xsrc), ldsrc, Ri * ldsrc, _p(xt[r]), ldi, C * ldi, B, Ri, C, r)
+                    mask = 0
+                    for sh in shifts:                                           # delayed copies: xt[r][b][c][u] = x[b][u - r][c]
+                        mask |= 1 << ((-sh * P) % 4)
+                    _call("evk_transpose_rows_multi", _p(xsrc), ldsrc, Ri * ldsrc, _p(xt), ldi, C * ldi, B * C * ldi, B, Ri, C, mask)
                     nq = len(qs)
                     qstep = (qs[1] - qs[0]) if nq > 1 else 1
                     tiles = nq * ((N + 127) // 128) * ((C + 255) // 256 if C > 128 else 1)

@@ -285,6 +285,9 @@ int evk_gconv_fwd_phased(const evk_gconv_desc* d, int32_t phases, int64_t x_ps, 
  * y[b][c][u] = x[b][u - shift][c], zero for u < shift. */
 int evk_transpose_rows(const float* x, int32_t ldx, int64_t x_sb, float* y, int32_t ldy, int64_t y_sb, int32_t B, int32_t T,
                        int32_t C, int32_t shift, evk_stream_t stream);
+/* every delayed copy r (bit r of mask, r = 0..3) in one pass over x: y[r*y_rs + ...][b][c][u] = x[b][u - r][c]. */
+int evk_transpose_rows_multi(const float* x, int32_t ldx, int64_t x_sb, float* y, int32_t ldy, int64_t y_sb, int64_t y_rs,
+                             int32_t B, int32_t T, int32_t C, int32_t mask, evk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Stage-1 AR semantic-token GPT (t2s_model.py:431-490 forward_old, transformer.py:266-315, optim.py:123-622).
