@@ -47,3 +47,45 @@ def test_two_rank_gradient_exchange_equals_global_batch():
     mp.spawn(_worker, nprocs=2, args=(2, 29512, ret), join=True)
     assert ret["n"] == 5_641_362
     assert ret["err"] < 1e-5, ret["err"]
+
+
+def _gpt_worker(rank, world, port, ret):
+    """stage-1: micro-batch gradients accumulate in the flat arena, ONE all-reduce per optimizer step (the reference's
+    Lightning DDP reduces every micro-batch), the 1/world mean is applied by the ScaledAdam kernels."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from easevoice_trainer_b200.train.gpt_step import FlatScaledAdam
+    from oracle import gpt_oracle
+    m = dict(gpt_oracle.GPT_MODEL, n_layer=1)
+    P = gpt_oracle.init_params(gpt_oracle.gpt_param_spec(m), 5)
+    params = {k: torch.nn.Parameter(v.clone()) for k, v in P.items()}
+    opt = FlatScaledAdam(params.items())
+    total = [torch.zeros_like(v) for v in params.values()]
+    for mb in range(3):                                       # three accumulated micro-batches, global batch 4 = 2 ranks x 2
+        x, xl, y, yl, bert = gpt_oracle.synthetic_gpt_batch(4, 6, 10, 100 + mb, ragged=True)
+        sl = slice(rank * 2, rank * 2 + 2)
+        loss = gpt_oracle.forward_old(params, x[sl], xl[sl], y[sl], yl[sl], bert[sl], m)[0]
+        opt.accumulate(torch.autograd.grad(loss, list(params.values())))
+        if rank == 0:                                         # DDP semantics: mean over ranks of the per-rank (summed) loss gradients
+            for r in range(world):
+                s2 = slice(r * 2, r * 2 + 2)
+                lf = gpt_oracle.forward_old(params, x[s2], xl[s2], y[s2], yl[s2], bert[s2], m)[0]
+                for t, g in zip(total, torch.autograd.grad(lf, list(params.values()))):
+                    t += g / world
+    dist.all_reduce(opt.flat_g)
+    flat = opt.flat_g / world
+    if rank == 0:
+        ref = torch.cat([t.reshape(-1) for t in total])
+        ret["gpt_err"] = float((flat - ref).norm() / ref.norm())
+        ret["gpt_n"] = flat.numel()
+        ret["chunks_cover"] = int(opt.chunks[:, 2].sum()) == flat.numel() and int(opt.numel.sum()) == flat.numel()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gpt_accumulate_then_single_allreduce():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_gpt_worker, nprocs=2, args=(2, 29514, ret), join=True)
+    assert ret["chunks_cover"]
+    assert ret["gpt_err"] < 1e-5, ret["gpt_err"]
