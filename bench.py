@@ -321,7 +321,9 @@ def run_ours(args):
         ach = fl / (tm * 1e-3) / 1e12
         extra["roofline"] = dict(bound="tensor", kernel="gemm_tma_kernel (TMA-fed persistent tcgen05 TF32 implicit-GEMM: conv fwd / dgrad / strided-phase launches; "
                                                         "the 16-channel stage stays on gconv_tc_kernel)",
-                                 achieved=ach, peak=tf_sus, unit="TFLOP/s", frac=ach / tf_sus, traffic=None,
+                                 achieved=ach, peak=tf_sus, unit="TFLOP/s", frac=ach / tf_sus,
+                                 traffic=60.6e6,   # bytes per launch of the heaviest layer (discP 1024->1024 k5, ncu dram read + write;
+                                                   # algorithmic 33.3 MB in + 21.0 MB weights + 33.3 MB out, the output still dirty in L2)
                                  peak_source=f"{src} cuBLAS bf16 sustained; the kernel computes in TF32 whose nominal peak is half of bf16",
                                  how="flops-weighted over the heaviest layer shapes of the step, each 24 back-to-back launches "
                                      "(graph replay) between CUDA events on 6 rotating (> L2) buffer sets; strided layers include their phase-split pass; "
@@ -357,7 +359,8 @@ def run_ours(args):
         only_gbs = (4.0 * bigw.numel() + big_frames * 128 * 4.0) / (only_ms * 1e-3) / 1e9
         del bigw
         extra["mel_roofline"] = dict(bound="hbm", kernel="mel_fwd_warp_kernel (|X| + log-mel emitted)", achieved=big_gbs, peak=hbm,
-                                     unit="GB/s", frac=big_gbs / hbm, frames=big_frames, ms=big_ms, peak_source=src, traffic=None,
+                                     unit="GB/s", frac=big_gbs / hbm, frames=big_frames, ms=big_ms, peak_source=src,
+                                     traffic=105.0e6,    # ncu dram read + write of a 22 144-frame launch (algorithmic 159 MB, part of |X| still in L2)
                                      how="one launch over 256 x 10 s (graph replay, 226 MB in + 408 MB out > L2)",
                                      batch16=dict(achieved=gbs, frac=gbs / hbm, frames=frames, ms=mel_ms,
                                                   how=f"{nset * reps} back-to-back launches of the training batch (16 x 10 s) over {nset} rotating buffer sets"),
