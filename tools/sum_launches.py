@@ -1,3 +1,5 @@
+"""Summarise an ncu launch list (`--metrics gpu__time_duration.sum --csv --log-file X.csv`) per kernel name.
+  python tools/sum_launches.py gpurun_out/launches.csv [top_n]"""
 import csv, sys, collections, re
 rows = list(csv.reader(l for l in open(sys.argv[1], errors="ignore") if l.startswith('"')))
 hdr = rows[0]; ki = hdr.index("Kernel Name"); vi = hdr.index("Metric Value"); ui = hdr.index("Metric Unit")
