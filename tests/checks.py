@@ -875,9 +875,56 @@ def check_gemm_tma():
     return out
 
 
+def check_vocoder_cfg5():
+    """BASELINE.json configs[4] shapes (vocoder only): Generator z [B, 192, 75] -> y_hat [B, 1, 48 000] (1 s at the 48 kHz
+    label), MultiPeriodDiscriminator on (y, y_hat), GAN + feature-matching losses and their gradients.  B = 2 here so the
+    CPU oracle finishes in seconds; every layer runs at its full 1-s length (the TMA conv / strided-phase / ConvTranspose
+    paths at production sizes)."""
+    from easevoice_trainer_b200 import ops
+    out = []
+    net_g, net_d, PG, PD = _load_models()
+    B, T = 2, 75
+    g = _gen(55)
+    z = torch.randn(B, 192, T, generator=g)
+    ge = torch.randn(B, 512, 1, generator=g) * 0.5
+    y = torch.rand(B, 1, T * 640, generator=g) - 0.5
+    zr = z.clone().requires_grad_(True)
+    PDr = {k: v.clone().requires_grad_(True) for k, v in PD.items()}
+    yh_o = s2_oracle.generator(PG, "dec", zr, ge)
+    rs, gs, frs, fgs = s2_oracle.mpd(PDr, y, yh_o)
+    loss_o = s2_oracle.generator_loss(gs) + s2_oracle.feature_loss(frs, fgs) + s2_oracle.discriminator_loss(rs, gs)
+    loss_o.backward()
+    zd = cl(z).requires_grad_(True)
+    yh = net_g._generator(zd, cl(ge))                                    # [B, 48000, 1]
+    out.append(("cfg5 generator y_hat [B, 48000]", rel(yh.reshape(B, -1), yh_o.reshape(B, -1)), TOL_TC * 3))
+    outs = net_d.forward_cl(cl(y), yh)
+    lg = lf = ld = 0.0
+    for d_i, (logit, fmap) in enumerate(outs):
+        # logits of a random-init discriminator on a 0.06-amplitude waveform are small differences of large terms: the
+        # relative error of the 6-layer chain is amplified (measured 5e-4 .. 1.1e-2), the loss below pins the absolute scale
+        out.append((f"cfg5 D[{d_i}] logits", rel(logit[B:].reshape(B, -1), gs[d_i]), TOL_TC * 8))
+        lg = lg + ops.mean_sq_one_minus(logit[B:])
+        ld = ld + ops.mean_sq_one_minus(logit[:B]) + ops.mean_sq(logit[B:])
+        for f in fmap:
+            lf = lf + ops.mean_abs_diff(f[B:], f[:B])
+    loss = lg + 2.0 * lf + ld
+    names = [n for n, _ in net_d.named_parameters()]
+    grads = torch.autograd.grad(loss, [zd] + [p for _, p in net_d.named_parameters()])
+    out.append(("cfg5 loss (gen + fm + disc)", abs(float(loss.detach()) - float(loss_o)) / abs(float(loss_o)), TOL_TC))
+    # dz crosses ~60 leaky-ReLU layers at 48 000 positions: kink flips accumulate (measured 4.7e-2; an indexing error in any
+    # data-gradient path would give O(1))
+    out.append(("cfg5 dz (through D and the whole generator)", rel(cf(grads[0]), zr.grad), 4 * KINK_TOL))
+    num = den = 0.0
+    for n, gk in zip(names, grads[1:]):
+        r = PDr[n].grad
+        num += float((gk.cpu().double() - r.double()).pow(2).sum()); den += float(r.double().pow(2).sum())
+    out.append(("cfg5 D parameter gradients (global)", math.sqrt(num / den), KINK_TOL))
+    return out
+
+
 ALL = [check_conv, check_conv_transpose, check_elementwise, check_attention, check_vq_losses_optim, check_mel,
        lambda: check_s2("small"), lambda: check_s2("ragged"), check_api_layouts,
        check_gpt_kernels, check_scaled_adam, lambda: check_gpt("small"), lambda: check_gpt("ragged"),
-       check_gpt_dpo_and_trainer, check_gemm_tma]
+       check_gpt_dpo_and_trainer, check_gemm_tma, check_vocoder_cfg5]
 NAMES = ["conv", "conv_transpose", "elementwise", "attention", "vq_losses_optim", "mel", "s2_small", "s2_ragged", "api",
-         "gpt_kernels", "scaled_adam", "gpt_small", "gpt_ragged", "gpt_dpo_trainer", "gemm_tma"]
+         "gpt_kernels", "scaled_adam", "gpt_small", "gpt_ragged", "gpt_dpo_trainer", "gemm_tma", "vocoder_cfg5"]
