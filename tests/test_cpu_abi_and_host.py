@@ -219,3 +219,21 @@ def test_gpt_dataset_collate_and_sampler(tmp_path):
     assert set(parts[0]) | set(parts[1]) == set(range(len(ds)))    # every sample visited; ranks take alternating slots
     sp0 = data_gpt.DistributedBucketSampler(ds, 2, 0, batch_size=4); sp0.set_epoch(3)
     assert list(sp0) == parts[0]                                   # deterministic in (seed, epoch)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs next to ours) must emit exactly one JSON line on stdout with the
+    contract keys, without touching a GPU or /root/reference."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                        "--cpu-batch", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["higher_is_better"] is True and d["n_gpus"] == 1
+    assert d["metric"].startswith("s2 SoVITS+HiFiGAN") and d["unit"] == "audio-s/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["e2e"]["h2d_bytes_per_step"] == 0
