@@ -132,11 +132,13 @@ class SynthesizerTrn(ParamTree):
 
     def _wn(self, pfx, k, n_layers):
         H, gin = self.hidden_channels, self.gin_channels
-        self._conv(pfx + ".cond_layer", 2 * H * n_layers, gin, 1, wn=True)
+        # registration order = the reference's named_parameters() order (modules.py:153-185: in/res_skip ModuleLists are
+        # assigned before cond_layer), so optimizer state indices line up with torch.optim.AdamW checkpoints
         for i in range(n_layers):
             self._conv(f"{pfx}.in_layers.{i}", 2 * H, H, k, wn=True)
         for i in range(n_layers):
             self._conv(f"{pfx}.res_skip_layers.{i}", 2 * H if i < n_layers - 1 else H, H, 1, wn=True)
+        self._conv(pfx + ".cond_layer", 2 * H * n_layers, gin, 1, wn=True)
 
     def _build(self):
         H, I, gin = self.hidden_channels, self.inter_channels, self.gin_channels

@@ -93,11 +93,18 @@ class FlatScaledAdam:
             off, k = self.slots[n]
             self.flat_delta[off:off + k].copy_(st["delta"].reshape(-1))
             self.flat_v[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
-            if k > 1:
+            if k > 1 and "param_rms" in st:
                 self.rms[i] = st["param_rms"]; self.sv[i] = st["scale_exp_avg_sq"]; self.sg[:, i] = st["scale_grads"]
             self.stepbuf.fill_(int(st["step"]))
-        self.norms.copy_(sd["model_norms"]); self.thr.copy_(sd["model_norm_threshold"])
-        self.set_lr(sd["param_groups"][0]["lr"])
+        # the clipping history is optional: states written by other ScaledAdam implementations (the reference keeps
+        # `model_norms` inside the per-batch state, optim.py:330-346) simply restart the median-of-1000 window
+        if "model_norms" in sd:
+            self.norms.copy_(sd["model_norms"])
+        if "model_norm_threshold" in sd:
+            self.thr.copy_(sd["model_norm_threshold"])
+        groups = sd.get("param_groups") or [{}]
+        if "lr" in groups[0]:
+            self.set_lr(groups[0]["lr"])
 
 
 class GptStep:

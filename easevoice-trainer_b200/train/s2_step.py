@@ -25,51 +25,78 @@ class FlatAdamW:
     """AdamW (torch.optim.AdamW semantics, sovits.py:294-319) over per-group flat fp32 arenas.
 
     Parameters are re-pointed into one contiguous buffer per lr group, so the update is one kernel per group and the
-    data-parallel all-reduce is one collective per network."""
+    data-parallel all-reduce is one collective per network.
 
-    def __init__(self, named_params, groups, betas, eps, weight_decay=0.01):
+    `frozen` names parameters that never receive a gradient (the reference's `p.grad is None` case: torch.optim.AdamW
+    skips them entirely -- no weight decay, no state).  They live in a tail region of the arena that no update kernel
+    touches, keep their index in `param_groups` (so optimizer state indices line up with a torch.optim.AdamW built over
+    the reference modules, whose named_parameters() order models.py reproduces) and have no entry in `state`."""
+
+    def __init__(self, named_params, groups, betas, eps, weight_decay=0.01, frozen=()):
         # groups: list of (lr_scale, [names]) ; every param must appear exactly once
         self.betas, self.eps, self.wd = betas, eps, weight_decay
         named = dict(named_params)
+        self.frozen = set(frozen)
         self.groups = []
         dev = next(iter(named.values())).device
         total = sum(named[n].numel() for _, names in groups for n in names)
         self.flat_p = torch.empty(total, device=dev, dtype=torch.float32)
         self.flat_g = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.flat_m = torch.zeros(total, device=dev, dtype=torch.float32)
-        self.flat_v = torch.zeros(total, device=dev, dtype=torch.float32)
         off = 0
         self.slots = {}
+
+        def place(n):
+            nonlocal off
+            p = named[n]
+            k = p.numel()
+            self.flat_p[off:off + k].copy_(p.data.reshape(-1))
+            p.data = self.flat_p[off:off + k].view_as(p)
+            self.slots[n] = (off, k)
+            off += k
         for lr_scale, names in groups:
             beg = off
             for n in names:
-                p = named[n]
-                k = p.numel()
-                self.flat_p[off:off + k].copy_(p.data.reshape(-1))
-                p.data = self.flat_p[off:off + k].view_as(p)
-                self.slots[n] = (off, k)
-                off += k
+                if n not in self.frozen:
+                    place(n)
             self.groups.append(dict(lr_scale=lr_scale, beg=beg, end=off, names=list(names)))
+        self.n_active = off                                   # [0, n_active): updated + all-reduced; the rest is frozen
+        for _, names in groups:
+            for n in names:
+                if n in self.frozen:
+                    place(n)
+        self.flat_m = torch.zeros(self.n_active, device=dev, dtype=torch.float32)
+        self.flat_v = torch.zeros(self.n_active, device=dev, dtype=torch.float32)
         self.params = [named[n] for _, names in groups for n in names]
         self.names = [n for _, names in groups for n in names]
         self.hyper = torch.zeros(2, device=dev, dtype=torch.float32)        # [lr, step] lives on the device
         self.gnorm_sq = torch.zeros(1, device=dev, dtype=torch.float32)
+        self.lr_host = 0.0
 
     @property
     def step_count(self):
         return int(self.hyper[1].item())
 
+    @property
+    def reduce_view(self):
+        """what the data-parallel exchange sums: the gradients of the parameters that are actually updated"""
+        return self.flat_g[:self.n_active]
+
     def set_lr(self, lr):
         """host-side (outside any captured graph): the lr only changes at epoch boundaries (ExponentialLR)."""
+        self.lr_host = float(lr)
         self.hyper[0] = float(lr)
 
     def set_grads(self, grads):
-        """copy autograd's per-parameter gradients into the flat buffer (unused parameters get zeros)."""
+        """copy autograd's per-parameter gradients into the flat buffer.  A parameter without a gradient must have been
+        declared `frozen` (it is then skipped like torch.optim.AdamW skips `p.grad is None`); anything else is a bug."""
         views, srcs = [], []
         for n, g in zip(self.names, grads):
             off, k = self.slots[n]
             if g is None:
-                self.flat_g[off:off + k].zero_()
+                if n not in self.frozen:
+                    raise RuntimeError(f"parameter {n} received no gradient but is not declared frozen")
+            elif n in self.frozen:
+                raise RuntimeError(f"frozen parameter {n} received a gradient")
             else:
                 views.append(self.flat_g[off:off + k].view_as(g))
                 srcs.append(g)
@@ -81,14 +108,18 @@ class FlatAdamW:
         self.gnorm_sq.zero_()
         for g in self.groups:
             s, e = g["beg"], g["end"]
-            ops.adamw_flat(self.flat_p[s:e], self.flat_g[s:e], self.flat_m[s:e], self.flat_v[s:e], self.hyper, g["lr_scale"],
-                           self.betas, self.eps, self.wd, grad_scale, self.gnorm_sq)
+            if e > s:
+                ops.adamw_flat(self.flat_p[s:e], self.flat_g[s:e], self.flat_m[s:e], self.flat_v[s:e], self.hyper,
+                               g["lr_scale"], self.betas, self.eps, self.wd, grad_scale, self.gnorm_sq)
 
-    # torch.optim-compatible state for checkpoints (ckpt.py:78-93 stores optimizer.state_dict())
+    # torch.optim.AdamW-compatible state (ckpt.py:78-93 stores optimizer.state_dict(); the reference resumes from it with
+    # torch.optim.AdamW.load_state_dict followed by ExponentialLR, which needs 'lr' / 'initial_lr' in every group)
     def state_dict(self):
         state = {}
         sc = self.step_count
         for i, n in enumerate(self.names):
+            if n in self.frozen:
+                continue
             off, k = self.slots[n]
             shape = self.params[i].shape
             state[i] = dict(step=torch.tensor(float(sc)), exp_avg=self.flat_m[off:off + k].view(shape).clone(),
@@ -96,19 +127,34 @@ class FlatAdamW:
         pg, idx = [], 0
         for g in self.groups:
             n = len(g["names"])
-            pg.append(dict(lr_scale=g["lr_scale"], betas=self.betas, eps=self.eps, weight_decay=self.wd,
-                           params=list(range(idx, idx + n))))
+            lr = self.lr_host * g["lr_scale"]
+            pg.append(dict(lr=lr, betas=tuple(self.betas), eps=self.eps, weight_decay=self.wd, amsgrad=False, foreach=None,
+                           maximize=False, capturable=False, differentiable=False, fused=None,
+                           initial_lr=g.get("initial_lr", lr), params=list(range(idx, idx + n))))
             idx += n
         return dict(state=state, param_groups=pg)
 
     def load_state_dict(self, sd):
+        """accepts this class's own checkpoints and torch.optim.AdamW's (same param order)."""
+        groups = sd.get("param_groups", [])
+        assert not groups or [len(g["params"]) for g in groups] == [len(g["names"]) for g in self.groups], \
+            "optimizer state has a different parameter-group structure"
         for i, n in enumerate(self.names):
-            if i in sd["state"]:
-                off, k = self.slots[n]
-                st = sd["state"][i]
-                self.flat_m[off:off + k].copy_(st["exp_avg"].reshape(-1))
-                self.flat_v[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
-                self.hyper[1] = float(st["step"])
+            st = sd["state"].get(i)
+            if st is None or n in self.frozen:
+                continue
+            off, k = self.slots[n]
+            self.flat_m[off:off + k].copy_(st["exp_avg"].reshape(-1))
+            self.flat_v[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+            self.hyper[1] = float(st["step"])
+        if groups and "lr" in groups[0]:
+            self.set_lr(float(groups[0]["lr"]) / (self.groups[0]["lr_scale"] or 1.0))
+            for mine, g in zip(self.groups, groups):
+                if "initial_lr" in g:
+                    mine["initial_lr"] = float(g["initial_lr"])
+
+
+FROZEN_G = ("ssl_proj.weight", "ssl_proj.bias")     # models.py:911-921: the quantizer front end runs under no_grad
 
 
 def g_param_groups(net_g, text_low_lr_rate):
@@ -126,8 +172,31 @@ def g_param_groups(net_g, text_low_lr_rate):
     return [(1.0, base), (text_low_lr_rate, te), (text_low_lr_rate, et), (text_low_lr_rate, mr)]
 
 
+def quantize_shape(T, X, t_q=32, x_q=32):
+    """Pad targets for a batch whose longest item has T frames / X phonemes: CUDA graphs are captured per shape, so
+    shapes are rounded up to a coarse grid (the length masks already make padding inert)."""
+    return (T + t_q - 1) // t_q * t_q, (X + x_q - 1) // x_q * x_q
+
+
+def pad_host_batch(host, Tq, Xq, hop):
+    """zero-pad a collated host batch (data.TextAudioSpeakerCollate layout) to Tq frames / Xq phonemes."""
+    B, _, T = host["ssl"].shape
+    X = host["text"].shape[1]
+    if T == Tq and X == Xq:
+        return host
+    assert Tq >= T and Xq >= X
+    out = dict(host)
+    F = torch.nn.functional
+    out["ssl"] = F.pad(host["ssl"], (0, Tq - T))
+    out["wav"] = F.pad(host["wav"], (0, Tq * hop - host["wav"].shape[2]))
+    out["text"] = F.pad(host["text"], (0, Xq - X))
+    return out
+
+
 class S2Step:
     """Holds the two networks, both optimisers and runs `sovits.py:459-525` for one batch."""
+    MAX_GRAPHS = 12          # LRU bound on captured shapes (all graphs share one memory pool)
+    CAPTURE_AFTER = 2        # a shape is captured the 2nd time it is seen; rare shapes run the eager step
 
     def __init__(self, net_g, net_d, hps_train, hps_data, world_size=1):
         self.net_g, self.net_d = net_g, net_d
@@ -136,7 +205,7 @@ class S2Step:
         self.seg_frames = hps_train["segment_size"] // hps_data["hop_length"]
         betas = tuple(hps_train["betas"])
         self.opt_g = FlatAdamW(net_g.named_parameters(), g_param_groups(net_g, hps_train["text_low_lr_rate"]), betas,
-                               hps_train["eps"])
+                               hps_train["eps"], frozen=FROZEN_G)
         self.opt_d = FlatAdamW(net_d.named_parameters(), [(1.0, [n for n, _ in net_d.named_parameters()])], betas,
                                hps_train["eps"])
         self.lr = hps_train["learning_rate"]
@@ -145,7 +214,10 @@ class S2Step:
         dev = next(net_g.parameters()).device
         self.bank = get_bank(hps_data["sampling_rate"], hps_data["filter_length"], hps_data["n_mel_channels"],
                              hps_data["mel_fmin"], hps_data["mel_fmax"], dev)
-        self._graphs = {}
+        self._graphs = {}            # shape key -> (graphs, static inputs, static outputs); insertion order = LRU order
+        self._seen = {}              # shape key -> sightings
+        self._pool = None            # one private memory pool shared by every captured graph
+        self._shape_group = None     # gloo group for the host-side shape agreement (world > 1)
 
     def losses(self, batch, noise=None, ids_slice=None):
         """Forward + both losses (no optimiser).  batch: dict of channels-last device tensors:
@@ -187,7 +259,7 @@ class S2Step:
 
     def _allreduce(self, opt):
         if self.world > 1:
-            dist.all_reduce(opt.flat_g)
+            dist.all_reduce(opt.reduce_view)
 
     # The step in three segments, split where the data-parallel gradient exchanges happen:
     #   A: G forward, features, D forward, D backward -> flat D grads          | all-reduce(D grads)
@@ -215,28 +287,62 @@ class S2Step:
         out.update({k: v.detach() for k, v in parts.items()})
         return out
 
-    def step(self, batch, noise=None, ids_slice=None):
-        """Eager step (every kernel launched from Python).  No host synchronisation anywhere."""
+    def step(self, batch, noise=None, ids_slice=None, collectives=True):
+        """Eager step (every kernel launched from Python).  No host synchronisation anywhere.
+        collectives=False runs the rank-local math only (graph warm-up: a warm-up must never pair with another rank's
+        real gradient exchange)."""
         r, loss_d = self._seg_a(batch, noise, ids_slice)
-        self._allreduce(self.opt_d)
+        if collectives:
+            self._allreduce(self.opt_d)
         loss_g, parts = self._seg_b(r)
-        self._allreduce(self.opt_g)
+        if collectives:
+            self._allreduce(self.opt_g)
         self._seg_c()
         return self._outputs(loss_d, loss_g, parts, self.opt_d, self.opt_g)
 
-    # ---- CUDA-graph path: the ~3000 launches of one step are captured once per batch shape and replayed --------
-    def graph_step(self, batch):
-        """Copy `batch` into the static input buffers of the graph captured for its shape, replay, return the static
-        loss tensors.  Shapes are bucketed by the sampler (sovits.py:233-252), so a handful of graphs covers a run."""
+    # ---- shape agreement + CUDA-graph path ----------------------------------------------------------------------
+    def agree_shape(self, T, X):
+        """-> (Tq, Xq): the padded shape EVERY rank uses for this iteration.  Each rank's collate pads to its own batch
+        maximum (data_utils.py:185-188), so the local maxima are first rounded up to a coarse grid and then MAX-reduced
+        over a gloo (host-side) group: no GPU synchronisation, and all ranks capture / replay / fall back to the eager
+        step at the same iterations, so their NCCL all-reduces always pair up."""
+        Tq, Xq = quantize_shape(T, X)
+        if self.world > 1:
+            if self._shape_group is None:
+                self._shape_group = dist.new_group(backend="gloo")
+            t = torch.tensor([Tq, Xq], dtype=torch.int64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self._shape_group)
+            Tq, Xq = int(t[0]), int(t[1])
+        return Tq, Xq
+
+    def train_step(self, batch):
+        """What the trainer calls: replay the graph of this (already agreed / quantised) shape, capturing it the
+        CAPTURE_AFTER-th time the shape shows up; before that the eager step runs."""
         key = (tuple(batch["ssl"].shape), tuple(batch["text"].shape))
-        g = self._graphs.get(key)
+        n = self._seen[key] = self._seen.get(key, 0) + 1
+        if key in self._graphs or n >= self.CAPTURE_AFTER:
+            return self.graph_step(batch)
+        return self.step(batch)
+
+    def graph_step(self, batch, noise=None, ids_slice=None, keep=False):
+        """Copy `batch` into the static input buffers of the graph captured for its shape, replay, return the static
+        loss tensors.  noise / ids_slice (parity tests) become static inputs of a separately keyed graph; keep=True also
+        returns the captured forward tensors (they stay valid until the next replay)."""
+        key = (tuple(batch["ssl"].shape), tuple(batch["text"].shape), noise is not None, bool(keep))
+        g = self._graphs.pop(key, None)
         if g is None:
-            g = self._capture(batch)
-            self._graphs[key] = g
+            while len(self._graphs) >= self.MAX_GRAPHS:                  # evict the least recently used shape
+                self._graphs.pop(next(iter(self._graphs)))
+            inputs = dict(batch)
+            if noise is not None:
+                inputs["noise"], inputs["ids_slice"] = noise, ids_slice
+            g = self._capture(inputs, keep)
+        self._graphs[key] = g                                            # (re)insert as most recently used
         graphs, static, out = g
         for k in static:
-            if static[k] is not batch[k]:
-                static[k].copy_(batch[k], non_blocking=True)
+            src = noise if k == "noise" else ids_slice if k == "ids_slice" else batch[k]
+            if static[k] is not src:
+                static[k].copy_(src, non_blocking=True)
         if len(graphs) == 1:
             graphs[0].replay()
         else:                               # data parallel: NCCL all-reduces run between the captured segments
@@ -247,42 +353,52 @@ class S2Step:
             graphs[2].replay()
         return out
 
-    def _capture(self, batch):
+    def _capture(self, batch, keep=False):
         static = {k: (v.clone() if k != "spec" else v) for k, v in batch.items()}
         # `spec` keeps its padded row pitch (a view of a wider buffer): clone the parent storage explicitly
         sp = batch["spec"]
         wide = torch.empty((sp.shape[0], sp.shape[1], sp.stride(1)), device=sp.device, dtype=sp.dtype)
         static["spec"] = wide[:, :, :sp.shape[2]]
         static["spec"].copy_(sp)
-        # warm-up (allocator, smem attributes, NCCL) must not count as training: snapshot and restore all mutable state
-        snap = [t.clone() for t in (self.opt_g.flat_p, self.opt_g.flat_m, self.opt_g.flat_v, self.opt_g.hyper,
-                                    self.opt_d.flat_p, self.opt_d.flat_m, self.opt_d.flat_v, self.opt_d.hyper,
-                                    ops.rng_state(sp.device))]
+        inj = dict(noise=static.get("noise"), ids_slice=static.get("ids_slice"))
+        feed = {k: v for k, v in static.items() if k not in ("noise", "ids_slice")}
+        # warm-up (allocator, smem attributes) must not count as training: snapshot and restore all mutable state.
+        # It runs WITHOUT collectives -- another rank may be replaying a real step right now.
+        state = (self.opt_g.flat_p, self.opt_g.flat_m, self.opt_g.flat_v, self.opt_g.hyper, self.opt_d.flat_p, self.opt_d.flat_m,
+                 self.opt_d.flat_v, self.opt_d.hyper, ops.rng_state(sp.device))
+        snap = [t.clone() for t in state]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):
-                self.step(static)
+                self.step(feed, collectives=False, **inj)
         torch.cuda.current_stream().wait_stream(side)
-        for dst, src in zip((self.opt_g.flat_p, self.opt_g.flat_m, self.opt_g.flat_v, self.opt_g.hyper, self.opt_d.flat_p,
-                             self.opt_d.flat_m, self.opt_d.flat_v, self.opt_d.hyper, ops.rng_state(sp.device)), snap):
+        for dst, src in zip(state, snap):
             dst.copy_(src)
         torch.cuda.synchronize()
+        if self._pool is None:
+            self._pool = torch.cuda.graph_pool_handle()
         if self.world == 1:
             graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                out = self.step(static)
-            return [graph], static, out
-        # world > 1: three graphs sharing one memory pool (replayed in capture order), collectives in between
-        ga, gb, gc = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-        with torch.cuda.graph(ga):
-            r, loss_d = self._seg_a(static)
-        with torch.cuda.graph(gb, pool=ga.pool()):
-            loss_g, parts = self._seg_b(r)
-        with torch.cuda.graph(gc, pool=ga.pool()):
-            self._seg_c()
+            with torch.cuda.graph(graph, pool=self._pool):
+                r, loss_d = self._seg_a(feed, **inj)
+                loss_g, parts = self._seg_b(r)
+                self._seg_c()
+            graphs = [graph]
+        else:
+            # world > 1: three graphs sharing the pool (replayed in capture order), collectives in between
+            ga, gb, gc = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga, pool=self._pool):
+                r, loss_d = self._seg_a(feed, **inj)
+            with torch.cuda.graph(gb, pool=self._pool):
+                loss_g, parts = self._seg_b(r)
+            with torch.cuda.graph(gc, pool=self._pool):
+                self._seg_c()
+            graphs = [ga, gb, gc]
         out = self._outputs(loss_d, loss_g, parts, self.opt_d, self.opt_g)
-        return [ga, gb, gc], static, out
+        if keep:
+            out["forward"] = {k: v for k, v in r.items() if torch.is_tensor(v)}
+        return graphs, static, out
 
     def set_lr(self, lr):
         self.lr = lr

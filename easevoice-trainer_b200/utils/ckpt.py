@@ -14,7 +14,7 @@ import torch
 
 
 def save_with_torch(obj, path):
-    tmp = f"{time.time()}.pth"
+    tmp = os.path.join(os.path.dirname(os.path.abspath(path)), f".{time.time()}.pth.tmp")   # next to the target, not in the CWD
     torch.save(obj, tmp)
     shutil.move(tmp, path)
 

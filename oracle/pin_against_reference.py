@@ -84,9 +84,17 @@ def pin_mel(mp):
     return out
 
 
-def pin_s2(models, losses, commons):
+S2_CASES = {"small": (2, 48, 12, False), "ragged": (3, 56, 17, True)}
+# BASELINE config 3 at the shapes bench.py times (T = 346 frames, 120 phonemes); B = 8 keeps every launch on the same
+# kernel family as the benchmarked B = 16 (the dispatch thresholds are in rows = B * T) while the CPU oracle still
+# finishes in about a minute on the GPU box's host cores.
+S2_FULL_CASES = {"cfg3": (8, 346, 120, False), "cfg3r": (8, 346, 120, True)}
+
+
+def pin_s2(models, losses, commons, cases=None):
     """Reference SynthesizerTrn/MPD (eval => dropout off, frozen VQ) vs oracle, fwd + grads."""
     res = {}
+    cases = cases or S2_CASES
     m = dict(s2_oracle.S2_MODEL)
     net_g = models.SynthesizerTrn(1025, 32, n_speakers=300, **m)
     net_d = models.MultiPeriodDiscriminator(False)
@@ -108,7 +116,7 @@ def pin_s2(models, losses, commons):
     net_g.load_state_dict(PG); net_d.load_state_dict(PD)
     net_g.eval(); net_d.eval()
 
-    for tag, (B, T, X, ragged) in {"small": (2, 48, 12, False), "ragged": (3, 56, 17, True)}.items():
+    for tag, (B, T, X, ragged) in cases.items():
         wav, ssl, text, spec_len, text_len = s2_oracle.synthetic_batch(B, T, X, 99, ragged)
         spec = mel_oracle.spectrogram(wav.squeeze(1), 2048, 640, 2048)
         g = torch.Generator().manual_seed(5)
@@ -202,11 +210,23 @@ def pin_s2(models, losses, commons):
                              ("discriminators.0.convs.3.weight_v", "discriminators.0.conv_post.weight_g",
                               "discriminators.3.convs.0.weight_v", "discriminators.5.convs.4.weight_v")},
         }
+        if tag in S2_FULL_CASES:       # full-size cases: the reference's norm of EVERY parameter gradient + forward slices
+            gold["grad_norms_g"] = {k: float(v.norm()) for k, v in gg_ref.items() if v is not None}
+            gold["grad_norms_d"] = {k: float(v.norm()) for k, v in gd_ref.items()}
+            for nm, t in (("z", z), ("z_p", z_p), ("m_p", m_p), ("logs_p", logs_p), ("m_q", m_q), ("logs_q", logs_q)):
+                gold[nm + "_norm"] = float(t.norm())
+                gold[nm + "_b0_c5_t100_108"] = t[0, 5, 100:108].tolist()
+            gold["y_hat_b1_0_4000_4008"] = y_hat[1, 0, 4000:4008].tolist()
         with open(os.path.join(GOLD, f"s2_{tag}.json"), "w") as f:
             json.dump(gold, f, indent=1)
     return res
 
-def pin_gpt():
+GPT_CASES = (("small", 3, 3, 12, 20, False), ("ragged", 2, 4, 9, 17, True))
+# BASELINE config 2 at the benchmarked model size: 24 layers, X = 256 phonemes, Y = 1024 semantic tokens, ragged 512..1024
+GPT_FULL_CASES = (("cfg2", 24, 4, 256, 1024, True),)
+
+
+def pin_gpt(cases=None, adam=True):
     """Stage-1 AR GPT: forward_old loss/acc/grads and ScaledAdam trajectories vs the reference classes.
 
     torchmetrics is absent from this image: MulticlassAccuracy(top_k=3, average="micro", ignore_index=EOS) is stubbed
@@ -233,7 +253,7 @@ def pin_gpt():
     from src.easevoice.soundstorm.auto_reg.models.t2s_model import Text2SemanticDecoder
     from src.easevoice.soundstorm.auto_reg.modules.optim import ScaledAdam
     res = {}
-    for tag, nl, B, X, Y, ragged in (("small", 3, 3, 12, 20, False), ("ragged", 2, 4, 9, 17, True)):
+    for tag, nl, B, X, Y, ragged in cases or GPT_CASES:
         m = dict(gpt_oracle.GPT_MODEL, n_layer=nl)
         ref = Text2SemanticDecoder({"model": m}).eval()        # eval: dropout off (parity configuration)
         spec = gpt_oracle.gpt_param_spec(m)
@@ -251,8 +271,14 @@ def pin_gpt():
         loss_o.backward()
         dl = abs(float(loss_r) - float(loss_o)) / abs(float(loss_r))
         da = abs(float(acc_r) - float(acc_o))
-        dg = max(maxdiff(g_ref[k], Pq[k].grad) / (float(g_ref[k].abs().max()) + 1e-12) for k in g_ref)
-        assert dl < 1e-5 and da < 1e-6 and dg < 2e-4, (tag, dl, da, dg)
+        per = {k: maxdiff(g_ref[k], Pq[k].grad) / (float(g_ref[k].abs().max()) + 1e-12) for k in g_ref}
+        dg = max(per.values())
+        if os.environ.get("PIN_VERBOSE"):
+            for k, v in sorted(per.items(), key=lambda kv: -kv[1])[:8]:
+                print("gpt", tag, k, v, float(g_ref[k].abs().max()))
+        # 24 layers deep the two fp32 evaluation orders (fused F.multi_head_attention_forward path vs the restated one)
+        # differ by up to ~1e-3 of a tensor's max on the tiny-gradient tensors; 3 layers: < 2e-4
+        assert dl < 1e-5 and da < 1e-6 and dg < (3e-3 if nl > 8 else 2e-4), (tag, dl, da, dg)
         res[tag] = {"loss_rel": dl, "acc_abs": da, "grad_rel_max": dg}
         gold = {"model": m, "B": B, "X": X, "Y": Y, "ragged": ragged, "param_seed": 11 + nl, "batch_seed": 5,
                 "alpha_text": 0.8, "alpha_audio": 1.3, "loss": float(loss_r), "acc": float(acc_r),
@@ -278,12 +304,16 @@ def pin_gpt():
         dl_o.backward()
         ddl = abs(float(dl_r) - float(dl_o)) / abs(float(dl_r))
         ddg = max(maxdiff(p.grad, Pd[k].grad) / (float(p.grad.abs().max()) + 1e-12) for k, p in ref.named_parameters())
-        assert ddl < 1e-5 and ddg < 2e-4, (tag, ddl, ddg)
+        assert ddl < 1e-5 and ddg < (3e-3 if nl > 8 else 2e-4), (tag, ddl, ddg)
         res[tag].update(dpo_loss_rel=ddl, dpo_grad_rel_max=ddg)
         gold.update(dpo=dict(spans=spans, loss=float(dl_r), loss_1=float(l1_o), loss_2=float(l2_o), acc=float(dacc_r),
                              grad_norms={k: float(p.grad.norm()) for k, p in ref.named_parameters() if k in gold["grad_norms"]}))
+        if tag == "cfg2":
+            gold["grad_norms"] = {k: float(v.norm()) for k, v in g_ref.items()}
         with open(os.path.join(GOLD, f"gpt_{tag}.json"), "w") as f:
             json.dump(gold, f, indent=1)
+    if not adam:
+        return res
     # ---- ScaledAdam: 14 steps on a small mixed set (matrix, vector, scalar, tiny-rms tensor), lr 0.01 then 0.002
     g = torch.Generator().manual_seed(3)
     shapes = [(6, 5), (7,), (1,), (4, 3), (2, 3, 2)]
@@ -319,6 +349,13 @@ def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     mp, models, losses, commons = import_reference()
+    if "--full" in sys.argv:          # the benchmarked shapes (minutes of CPU time): python oracle/pin_against_reference.py --full
+        mp.mel_basis.clear()
+        report = {"s2": pin_s2(models, losses, commons, S2_FULL_CASES), "gpt": pin_gpt(GPT_FULL_CASES, adam=False)}
+        with open(os.path.join(GOLD, "pin_report_full.json"), "w") as f:
+            json.dump(report, f, indent=1)
+        print("PIN OK (full-size cases)")
+        return
     report = {"mel": pin_mel(mp)}
     print(json.dumps(report, indent=1))
     mp.mel_basis.clear()  # see pin_mel: the reference's filterbank cache is not keyed by sampling rate
