@@ -19,6 +19,7 @@ int check_launch(const char* what) {
   return EVK_OK;
 }
 int mel_init_tables();
+double g_disp_flops[EVK_DISPATCH_SLOTS] = {0};
 }  // namespace evk
 using namespace evk;
 
@@ -45,5 +46,18 @@ extern "C" int evk_sync_check(evk_stream_t stream) {
   cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("evk_sync_check: %s", cudaGetErrorString(e)); return EVK_ERR_CUDA; }
+  return EVK_OK;
+}
+
+// Host-side dispatch accounting (parity tests / bench.py): algorithmic flops of every contraction launch since the last
+// reset, by the kernel family that served it.  Counted when the launch is enqueued -- a CUDA-graph replay adds nothing,
+// so callers account one eager step of the shape they replay.
+extern "C" int evk_dispatch_stats(double* out, int32_t n) {
+  EVK_REQUIRE(out && n >= 1, EVK_ERR_ARG, "dispatch_stats: null output");
+  for (int i = 0; i < n && i < EVK_DISPATCH_SLOTS; ++i) out[i] = g_disp_flops[i];
+  return EVK_OK;
+}
+extern "C" int evk_dispatch_stats_reset(void) {
+  for (int i = 0; i < EVK_DISPATCH_SLOTS; ++i) g_disp_flops[i] = 0.0;
   return EVK_OK;
 }

@@ -183,6 +183,7 @@ extern "C" int evk_conv_direct_fwd(const evk_gconv_desc* d, evk_stream_t stream)
     dim3 grid(cdiv(total, 256), 1, p.Z);
     direct_fwd_thread<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   }
+  g_disp_flops[3] += desc_flops(d);
   return check_launch("conv_direct_fwd");
 }
 
@@ -194,6 +195,7 @@ extern "C" int evk_conv_direct_dgrad(const evk_gconv_desc* d, evk_stream_t strea
   if (total == 0) return EVK_OK;
   dim3 grid(cdiv(total, 256), 1, p.Z);
   direct_dgrad<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  g_disp_flops[3] += desc_flops(d);
   return check_launch("conv_direct_dgrad");
 }
 
@@ -212,5 +214,6 @@ extern "C" int evk_conv_direct_wgrad(const evk_gconv_desc* d, evk_stream_t strea
   dim3 grid(cdiv(npos, chunk), wblocks, p.Z);
   EVK_REQUIRE(grid.y <= 65535, EVK_ERR_ARG, "conv_direct_wgrad: too many weights");
   direct_wgrad<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  g_disp_flops[6] += desc_flops(d);
   return check_launch("conv_direct_wgrad");
 }

@@ -21,6 +21,12 @@ int check_launch(const char* what);   // cudaGetLastError -> EVK_ERR_CUDA
     }                                       \
   } while (0)
 
+// dispatch accounting slots (evk_dispatch_stats)
+extern double g_disp_flops[EVK_DISPATCH_SLOTS];
+static inline double desc_flops(const evk_gconv_desc* d) {
+  return 2.0 * d->Z * (double)d->J * d->P * d->N * (d->C / (d->G > 0 ? d->G : 1)) * d->Q;
+}
+
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---- device helpers -----------------------------------------------------------------------

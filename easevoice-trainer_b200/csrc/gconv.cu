@@ -448,11 +448,12 @@ extern "C" int evk_gconv_fwd(const evk_gconv_desc* d, evk_stream_t stream) {
   EVK_REQUIRE(d->y != nullptr && d->x != nullptr && d->w != nullptr, EVK_ERR_ARG, "gconv_fwd: null tensor");
   cudaStream_t st = (cudaStream_t)stream;
   if (g_backend_tc && !g_precise && (d->ldx % 4) == 0) {
-    rc = gemm_tma_try(d, st);          // tap-free dense contractions: TMA-fed persistent tcgen05 GEMM
-    if (rc <= 0) return rc;
+    rc = gemm_tma_try(d, st);          // TMA-fed persistent tcgen05 GEMM / implicit-GEMM conv
+    if (rc <= 0) { if (rc == 0) g_disp_flops[0] += desc_flops(d); return rc; }
     rc = gconv_tc_try(d, st);
-    if (rc <= 0) return rc;
+    if (rc <= 0) { if (rc == 0) g_disp_flops[1] += desc_flops(d); return rc; }
   }
+  g_disp_flops[2] += desc_flops(d);
   // pick the N tile with the least padding (prefer wide)
   const int N = p.N;
   auto waste = [&](int bn) { return (long long)cdiv(N, bn) * bn; };
@@ -513,6 +514,7 @@ extern "C" int evk_gconv_wgrad(const evk_gconv_desc* d, evk_stream_t stream) {
               "gconv_wgrad: batch strides must be multiples of 4");
   EVK_REQUIRE(d->y != nullptr && d->x != nullptr && d->w != nullptr, EVK_ERR_ARG, "gconv_wgrad: null tensor");
   cudaStream_t st = (cudaStream_t)stream;
+  g_disp_flops[5] += desc_flops(d);
   const long long ncols = (long long)p.Q * ((p.C + 3) & ~3);
 #define EVK_W(...) (g_precise ? launch_w<__VA_ARGS__, true>(p, st) : launch_w<__VA_ARGS__, false>(p, st))
   if (p.N <= 16) {

@@ -436,6 +436,7 @@ extern "C" int evk_gconv_fwd_phased(const evk_gconv_desc* d, int32_t phases, int
   EVK_REQUIRE(d && src, EVK_ERR_ARG, "gconv_fwd_phased: null argument");
   int rc = gemm_tma_run(d, phases, x_ps, src, st);
   EVK_REQUIRE(rc != 1, EVK_ERR_UNSUPPORTED, "gconv_fwd_phased: launch not eligible for the TMA kernel");
+  if (rc == 0) g_disp_flops[0] += desc_flops(d);
   return rc;
 }
 
@@ -454,6 +455,7 @@ extern "C" int evk_gemm_tf32(const float* A, int32_t lda, const float* B, int32_
   p.os = 1; p.o0 = 0;
   int rc = run_gemm(o, p, splits, st);
   EVK_REQUIRE(rc != 1, EVK_ERR_UNSUPPORTED, "gemm_tf32: cuTensorMapEncodeTiled unavailable or rejected the operand");
+  if (rc == 0) g_disp_flops[7] += 2.0 * M * (double)N * K;
   return rc;
 }
 
@@ -479,5 +481,6 @@ extern "C" int evk_conv_wgrad_tma(const float* dyt, int32_t ld_dy, int64_t dy_sb
   Operands o{dyt, ld_dy, dy_sb, in_rows, xt, ld_x, x_sb, x_rs, 1, 0};
   int rc = run_gemm(o, p, splits < 1 ? 1 : splits, st);
   EVK_REQUIRE(rc != 1, EVK_ERR_UNSUPPORTED, "conv_wgrad_tma: cuTensorMapEncodeTiled unavailable or rejected the operand");
+  if (rc == 0) g_disp_flops[4] += 2.0 * B * (double)out_rows * N * C * Q;
   return rc;
 }

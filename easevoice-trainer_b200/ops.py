@@ -62,6 +62,21 @@ def profile_end():
     return agg
 
 
+DISPATCH_SLOTS = ("fwd_gemm_tma", "fwd_gconv_tc", "fwd_mma_sync", "fwd_direct", "wgrad_gemm_tma", "wgrad_mma_sync", "wgrad_direct",
+                  "gemm_tf32")
+
+
+def dispatch_reset():
+    L.check(_lib().evk_dispatch_stats_reset())
+
+
+def dispatch_stats():
+    """-> {kernel family: algorithmic flops enqueued since dispatch_reset()} (host-side accounting in the library)."""
+    buf = (ctypes.c_double * len(DISPATCH_SLOTS))()
+    L.check(_lib().evk_dispatch_stats(buf, len(DISPATCH_SLOTS)))
+    return dict(zip(DISPATCH_SLOTS, [float(v) for v in buf]))
+
+
 def _timed(name, fn, flops=0.0, nbytes=0.0):
     if _prof is None:
         return fn()

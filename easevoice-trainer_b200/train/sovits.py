@@ -91,7 +91,7 @@ class SovitsTrain:
             import torch.multiprocessing as mp
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
             os.environ.setdefault("MASTER_PORT", str(randint(30000, 55555)))
-            mp.spawn(_spawn_entry, nprocs=len(gpus), args=(len(gpus), self.params, [int(g) for g in gpus]))
+            mp.spawn(_spawn_entry, nprocs=len(gpus), args=(len(gpus), self.params, [int(g) for g in gpus], self.dataset))
         return TrainOutput(model_path=self.hps["train"]["output_dir"])
 
     def _build(self, device):
@@ -197,6 +197,6 @@ class SovitsTrain:
                                 self.global_step, t["save_weight_dir"])
 
 
-def _spawn_entry(local_rank, world, params, gpu_ids):
+def _spawn_entry(local_rank, world, params, gpu_ids, dataset=None):
     os.environ.update(RANK=str(local_rank), WORLD_SIZE=str(world), LOCAL_RANK=str(gpu_ids[local_rank]))
-    SovitsTrain(params).train()
+    SovitsTrain(params, dataset=dataset).train()

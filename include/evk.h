@@ -69,6 +69,15 @@ int evk_set_precise(int32_t on);
 int evk_get_precise(void);
 /* 1 (default): stride-1 launches run on the tcgen05/TMEM kernel (gconv_tc.cu); 0: mma.sync kernels only. */
 int evk_set_backend(int32_t tcgen05);
+/* Dispatch accounting: algorithmic flops enqueued since the last reset, per kernel family (host-side counters; graph
+ * replays add nothing).  out[i], i < EVK_DISPATCH_SLOTS:
+ *   0 conv/linear fwd-like on gemm_tma_kernel (TMA + tcgen05)   1 ... on gconv_tc_kernel (tcgen05, staged slab)
+ *   2 ... on gconv_f_kernel (mma.sync)                          3 ... on the direct CUDA-core kernels
+ *   4 weight gradients on gemm_tma_kernel                        5 ... on gconv_w_kernel (mma.sync)
+ *   6 ... on the direct kernels                                  7 plain evk_gemm_tf32 calls */
+#define EVK_DISPATCH_SLOTS 8
+int evk_dispatch_stats(double* out, int32_t n);
+int evk_dispatch_stats_reset(void);
 /* Weight gradient of the same operator:  W[z][q][n][c] += sum_{j,w} Yg[z][orow][n] * X[z][irow][c]
  * (d->y is read as the output gradient, d->w is accumulated with atomics; when w_sb == w_sh == 0 the
  * sum also runs over z).  Replaces autograd's conv weight-gradient kernels for the call sites above. */

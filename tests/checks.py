@@ -4,11 +4,20 @@
 Each check returns a list of (name, error, tolerance) triples; tests/test_gpu_parity.py asserts them,
 tests/run_gpu_checks.py prints all of them without stopping (used for blind debugging through gpurun).
 
-Tolerances (stated once, used everywhere):
-  TOL_TC   = 3e-3  relative-L2 for anything that passes through the TF32 tensor-core kernels
-                   (10-bit operand mantissa, fp32 accumulate; same class as the reference's allow_tf32=True path)
-  TOL_F32  = 2e-5  relative-L2 for pure fp32 CUDA-core kernels
-  integer results (VQ codes, slice ids, masks) must be bit-exact.
+Tolerance table (stated once, used everywhere; relative L2 unless noted -- measured worst cases of the round-2 B200 runs
+are kept next to the goldens in profiles/r2_parity_table.md):
+  TOL_F32   = 2e-5   pure fp32 CUDA-core kernels
+  TOL_TC    = 1e-3   "TF32-class" gate of BASELINE.md: the result of ONE tensor-core contraction on a linear path
+                     (y, dx, dW, dbias of a conv / linear / attention forward; 10-bit operand mantissa, fp32 accumulate)
+  TOL_TC2   = 2e-3   the result of TWO chained contractions inside one op (attention dq/dk/dv: S is recomputed, then
+                     dS.K; weight-norm dv/dg: dW then the norm projection)
+  TOL_NET   = 3e-3   activations / losses at the END of an assembled network (10-100 tensor-core launches deep)
+  KINK_TOL  = 2.5e-2 any gradient that crossed a (leaky-)ReLU: compared across two forward roundings, pre-activations
+                     within rounding distance of 0 flip their derivative (slope 0.1 <-> 1); 3xTF32 mode collapses it
+                     (test_precise_mode_tightens_*), i.e. it is rounding, not indexing
+  NET_GRAD  = 1e-2 global / 5e-2 worst single tensor: parameter gradients of the assembled stage-2 networks
+                     ("BF16-class" gate of BASELINE.md for the global number); the GPT uses KINK_TOL global
+  integer results (VQ codes, slice ids, masks, targets) must be bit-exact.
 """
 import json
 import math
@@ -23,9 +32,12 @@ sys.path.insert(0, ROOT)
 
 from oracle import mel_oracle, s2_oracle, gpt_oracle  # noqa: E402  (checker only)
 
-TOL_TC = 3e-3
+TOL_TC = 1e-3
+TOL_TC2 = 2e-3
+TOL_NET = 3e-3
 TOL_F32 = 2e-5
 KINK_TOL = 2.5e-2          # gradients through ReLU-type kinks under TF32 forward rounding (see check_conv)
+NET_GRAD_GLOBAL, NET_GRAD_TENSOR = 1e-2, 5e-2
 PRECISE_MODE = [False]     # set by the caller when the library runs in 3xTF32 mode
 DEV = "cuda"
 
@@ -172,7 +184,7 @@ def check_conv_transpose():
         yo.backward(cl(gy))
         n = f"convT[{cin}->{cout} k{k} s{s}]"
         out += [(n + " y", rel(cf(yo), y), TOL_TC), (n + " dx", rel(cf(xd.grad), xr.grad), TOL_TC),
-                (n + " dv", rel(vd.grad.cpu(), vr.grad), TOL_TC * 2), (n + " dg", rel(gd.grad.cpu(), gr.grad), TOL_TC * 2),
+                (n + " dv", rel(vd.grad.cpu(), vr.grad), TOL_TC2), (n + " dg", rel(gd.grad.cpu(), gr.grad), TOL_TC2),
                 (n + " dbias", rel(bd.grad.cpu(), br.grad), TOL_TC)]
     return out
 
@@ -298,11 +310,11 @@ def check_attention():
         qmd = cl(qm)
         (yo * qmd).backward(cl(gy))
         n = f"attn[{name}]"
-        out += [(n + " y", rel(cf(yo * qmd), yr * qm), TOL_TC), (n + " dq", rel(cf(qd.grad), leaves[0].grad), TOL_TC * 2),
-                (n + " dk(+v path)", rel(cf(kd.grad), leaves[1].grad), TOL_TC * 2)]
+        out += [(n + " y", rel(cf(yo * qmd), yr * qm), TOL_TC), (n + " dq", rel(cf(qd.grad), leaves[0].grad), TOL_TC2),
+                (n + " dk(+v path)", rel(cf(kd.grad), leaves[1].grad), TOL_TC2)]
         if win is not None:
-            out += [(n + " dEk", rel(Ekd.grad, P["a.emb_rel_k"].grad), TOL_TC * 2),
-                    (n + " dEv", rel(Evd.grad, P["a.emb_rel_v"].grad), TOL_TC * 2)]
+            out += [(n + " dEk", rel(Ekd.grad, P["a.emb_rel_k"].grad), TOL_TC2),
+                    (n + " dEv", rel(Evd.grad, P["a.emb_rel_v"].grad), TOL_TC2)]
     return out
 
 
@@ -448,17 +460,17 @@ def check_s2(tag="small"):
     r = stepper.losses(batch, noise=cl(noise), ids_slice=ids.to(DEV))
     out.append((f"s2[{tag}] VQ codes mismatches", float((r["codes"].cpu() != o["codes"]).sum()), 0.5))
     for k in ("z", "z_p", "m_p", "logs_p", "m_q", "logs_q", "y_hat"):
-        out.append((f"s2[{tag}] {k}", rel(cf(r[k]), o[k]), TOL_TC * (3 if k == "y_hat" else 1)))
-    out.append((f"s2[{tag}] y_hat_mel", rel(cf(r["y_hat_mel"]), o["y_hat_mel"]), TOL_TC * 3))
+        out.append((f"s2[{tag}] {k}", rel(cf(r[k]), o[k]), TOL_NET))
+    out.append((f"s2[{tag}] y_hat_mel", rel(cf(r["y_hat_mel"]), o["y_hat_mel"]), TOL_NET))
     out.append((f"s2[{tag}] y_mel", rel(cf(r["y_mel"]), o["y_mel"]), 1e-5))
     out.append((f"s2[{tag}] y slice", rel(cf(r["y"]), o["y"]), 1e-12))
     ld = stepper.d_loss(r)
     lg, parts = stepper.g_loss(r)
-    out.append((f"s2[{tag}] loss_disc", abs(float(ld) - float(o["loss_disc"])) / float(o["loss_disc"]), TOL_TC))
-    out.append((f"s2[{tag}] loss_gen_all", abs(float(lg) - float(o["loss_gen_all"])) / float(o["loss_gen_all"]), TOL_TC))
+    out.append((f"s2[{tag}] loss_disc", abs(float(ld) - float(o["loss_disc"])) / float(o["loss_disc"]), TOL_NET))
+    out.append((f"s2[{tag}] loss_gen_all", abs(float(lg) - float(o["loss_gen_all"])) / float(o["loss_gen_all"]), TOL_NET))
     for k in ("loss_gen", "loss_fm", "loss_mel", "loss_kl"):
-        out.append((f"s2[{tag}] {k}", abs(float(parts[k]) - float(o[k])) / abs(float(o[k])), TOL_TC * 2))
-        out.append((f"s2[{tag}] {k} vs reference golden", abs(float(parts[k]) - gold[k]) / abs(gold[k]), TOL_TC * 2))
+        out.append((f"s2[{tag}] {k}", abs(float(parts[k]) - float(o[k])) / abs(float(o[k])), TOL_NET))
+        out.append((f"s2[{tag}] {k} vs reference golden", abs(float(parts[k]) - gold[k]) / abs(gold[k]), TOL_NET))
     dnames = [n for n, _ in net_d.named_parameters()]
     gd = torch.autograd.grad(ld, [p for _, p in net_d.named_parameters()], retain_graph=True, allow_unused=True)
     worst, wname, num, den = 0.0, "", 0.0, 0.0
@@ -469,8 +481,8 @@ def check_s2(tag="small"):
         if e > worst:
             worst, wname = e, n
     # per-tensor worst case is dominated by leaky-ReLU derivative flips in the 1->32 / 1->16 first layers (KINK_TOL x2)
-    out.append((f"s2[{tag}] D param grads worst rel-L2 ({wname})", worst, 5e-2))
-    out.append((f"s2[{tag}] D param grads global rel-L2", math.sqrt(num / den), 1e-2))
+    out.append((f"s2[{tag}] D param grads worst rel-L2 ({wname})", worst, NET_GRAD_TENSOR))
+    out.append((f"s2[{tag}] D param grads global rel-L2", math.sqrt(num / den), NET_GRAD_GLOBAL))
     gnames = [n for n, _ in net_g.named_parameters()]
     gg = torch.autograd.grad(lg, [p for _, p in net_g.named_parameters()], allow_unused=True)
     worst, wname, unused = 0.0, "", []
@@ -486,8 +498,8 @@ def check_s2(tag="small"):
         tot_den += float(gg_ref[n].double().pow(2).sum())
         if e > worst:
             worst, wname = e, n
-    out.append((f"s2[{tag}] G param grads worst rel-L2 ({wname})", worst, 5e-2))
-    out.append((f"s2[{tag}] G param grads global rel-L2", math.sqrt(tot_num / tot_den), 1e-2))
+    out.append((f"s2[{tag}] G param grads worst rel-L2 ({wname})", worst, NET_GRAD_TENSOR))
+    out.append((f"s2[{tag}] G param grads global rel-L2", math.sqrt(tot_num / tot_den), NET_GRAD_GLOBAL))
     out.append((f"s2[{tag}] unused G params == {{ssl_proj.weight, ssl_proj.bias}}",
                 0.0 if sorted(unused) == ["ssl_proj.bias", "ssl_proj.weight"] else 1.0, 0.5))
     for k, v in gold["grad_norms_g"].items():
@@ -509,20 +521,20 @@ def check_api_layouts():
     o = s2_oracle.synthesizer_forward(PG, ssl, spec, spec_len, text, text_len, noise, ids)
     y_hat, commit, ids_r, m1, m2, lat, quant = net_g(ssl.to(DEV), spec.to(DEV), spec_len.to(DEV), text.to(DEV),
                                                      text_len.to(DEV), noise=noise.to(DEV), ids_slice=ids.to(DEV))
-    out.append(("api G y_hat [B,1,T]", rel(y_hat, o["y_hat"]), TOL_TC * 3))
+    out.append(("api G y_hat [B,1,T]", rel(y_hat, o["y_hat"]), TOL_NET))
     out.append(("api G quantized", rel(quant, o["quantized"]), 1e-12))
     out.append(("api G mask", rel(m1, o["y_mask"]), 1e-12))
     for t, k in zip(lat, ("z", "z_p", "m_p", "logs_p", "m_q", "logs_q")):
-        out.append((f"api G {k}", rel(t, o[k]), TOL_TC))
+        out.append((f"api G {k}", rel(t, o[k]), TOL_NET))
     y = torch.rand(2, 1, 20480, generator=g) - 0.5
     yh = torch.rand(2, 1, 20480, generator=g) - 0.5
     rs, gs, frs, fgs = s2_oracle.mpd(PD, y, yh)
     ors, ogs, ofrs, ofgs = net_d(y.to(DEV), yh.to(DEV))
     for d in range(6):
-        out.append((f"api D[{d}] logits real", rel(ors[d], rs[d]), TOL_TC * 2))
-        out.append((f"api D[{d}] logits gen", rel(ogs[d], gs[d]), TOL_TC * 2))
+        out.append((f"api D[{d}] logits real", rel(ors[d], rs[d]), TOL_NET))
+        out.append((f"api D[{d}] logits gen", rel(ogs[d], gs[d]), TOL_NET))
         for i in range(len(frs[d])):
-            out.append((f"api D[{d}] fmap{i}", rel(ofgs[d][i], fgs[d][i]), TOL_TC * 2))
+            out.append((f"api D[{d}] fmap{i}", rel(ofgs[d][i], fgs[d][i]), TOL_NET))
     return out
 
 
@@ -563,9 +575,9 @@ def check_gpt_kernels():
         out.append((f"flash {tag} out", rel(o, o_ref), TOL_TC))
         gq, gk, gv = qd.grad.cpu().split(D, dim=-1)
         rq, rk, rv = qr.grad.split(D, dim=-1)
-        out.append((f"flash {tag} dq", rel(gq, rq), TOL_TC * 2))
-        out.append((f"flash {tag} dk", rel(gk, rk), TOL_TC * 2))
-        out.append((f"flash {tag} dv", rel(gv, rv), TOL_TC * 2))
+        out.append((f"flash {tag} dq", rel(gq, rq), TOL_TC2))
+        out.append((f"flash {tag} dk", rel(gk, rk), TOL_TC2))
+        out.append((f"flash {tag} dv", rel(gv, rv), TOL_TC2))
     # ---- dropout: recover the keep mask with V = I (L = 32 keys, dk = 32), then check fwd/bwd against the oracle given it
     B, H, X, Y, p = 2, 2, 12, 20, 0.25
     L, D = 32, 64
@@ -591,7 +603,7 @@ def check_gpt_kernels():
     o = ops.flash_attention(qd, heads=H, prefix=X, xlen=xl.to(DEV), ylen=yl.to(DEV), p_drop=p, tag="chk.drop")
     o.backward(go.to(DEV))
     out.append(("flash dropout out (same mask)", rel(o, o_ref), TOL_TC))
-    out.append(("flash dropout dqkv (mask regenerated in bwd)", rel(qd.grad, qr.grad), TOL_TC * 2))
+    out.append(("flash dropout dqkv (mask regenerated in bwd)", rel(qd.grad, qr.grad), TOL_TC2))
     # ---- sinusoid + alpha + concat
     from easevoice_trainer_b200.models_gpt import sine_table
     B, X, Y, D = 3, 5, 9, 64
@@ -691,9 +703,9 @@ def check_gpt(tag="small"):
     y_in, tg = net.make_targets(y.to(DEV), yl.to(DEV))
     out.append((f"gpt {tag} targets (pad_y_eos) exact", float((tg.cpu() != tg_o).sum()), 0.0))
     out.append((f"gpt {tag} targets checksum == reference golden", abs(int(tg.sum()) - gold["targets_sum"]), 0))
-    out.append((f"gpt {tag} logits", rel(net.last_logits[..., :m["vocab_size"]].reshape(logits_o.shape), logits_o), TOL_TC * 3))
-    out.append((f"gpt {tag} loss vs oracle", abs(float(loss.detach()) - float(loss_o)) / abs(float(loss_o)), TOL_TC))
-    out.append((f"gpt {tag} loss vs reference golden", abs(float(loss.detach()) - gold["loss"]) / abs(gold["loss"]), TOL_TC))
+    out.append((f"gpt {tag} logits", rel(net.last_logits[..., :m["vocab_size"]].reshape(logits_o.shape), logits_o), TOL_NET))
+    out.append((f"gpt {tag} loss vs oracle", abs(float(loss.detach()) - float(loss_o)) / abs(float(loss_o)), TOL_NET))
+    out.append((f"gpt {tag} loss vs reference golden", abs(float(loss.detach()) - gold["loss"]) / abs(gold["loss"]), TOL_NET))
     out.append((f"gpt {tag} top-3 acc vs reference golden", abs(float(acc) - gold["acc"]), 2.0 / (gold["B"] * gold["Y"])))
     worst, gl = 0.0, 0.0
     num = den = 0.0
@@ -738,7 +750,7 @@ def check_gpt(tag="small"):
             l_d, _ = step.step(dict(phoneme_ids=xb.to(DEV), phoneme_ids_len=xlb.to(DEV), semantic_ids=yb.to(DEV),
                                     semantic_ids_len=ylb.to(DEV), bert_feature=bb.to(DEV)))
             lo.append(abs(float(l_d) - float(l_o)) / abs(float(l_o)))
-        out.append(("gpt 6 training_steps: loss track", max(lo), TOL_TC * 2))
+        out.append(("gpt 6 training_steps: loss track", max(lo), TOL_NET))
         out.append(("gpt 6 training_steps: exactly one optimizer step", abs(step.opt.step_count - 1), 0))
         pw = max(rel(p.data, Po[keys.index(n)]) for n, p in net.named_parameters())
         out.append(("gpt 6 training_steps: params vs oracle loop", pw, 2e-3))
@@ -768,8 +780,8 @@ def check_gpt_dpo_and_trainer():
     loss, acc = net.forward(x.to(DEV), xl.to(DEV), y.to(DEV), yl.to(DEV), bert.to(DEV), reject=(ry.to(DEV), ryl.to(DEV)))
     named = list(net.named_parameters())
     grads = torch.autograd.grad(loss, [p for _, p in named])
-    out.append(("dpo loss vs oracle", abs(float(loss.detach()) - float(lo)) / abs(float(lo)), TOL_TC))
-    out.append(("dpo loss vs reference golden", abs(float(loss.detach()) - gold["dpo"]["loss"]) / abs(gold["dpo"]["loss"]), TOL_TC))
+    out.append(("dpo loss vs oracle", abs(float(loss.detach()) - float(lo)) / abs(float(lo)), TOL_NET))
+    out.append(("dpo loss vs reference golden", abs(float(loss.detach()) - gold["dpo"]["loss"]) / abs(gold["dpo"]["loss"]), TOL_NET))
     out.append(("dpo loss_2 term vs oracle", abs(float(net.last_dpo[1]) - float(l2o)) / (abs(float(l2o)) + 1e-6), 5e-2))
     out.append(("dpo acc vs reference golden", abs(float(acc) - gold["dpo"]["acc"]), 2.0 / (gold["B"] * gold["Y"])))
     num = den = 0.0
@@ -896,13 +908,13 @@ def check_vocoder_cfg5():
     loss_o.backward()
     zd = cl(z).requires_grad_(True)
     yh = net_g._generator(zd, cl(ge))                                    # [B, 48000, 1]
-    out.append(("cfg5 generator y_hat [B, 48000]", rel(yh.reshape(B, -1), yh_o.reshape(B, -1)), TOL_TC * 3))
+    out.append(("cfg5 generator y_hat [B, 48000]", rel(yh.reshape(B, -1), yh_o.reshape(B, -1)), TOL_NET))
     outs = net_d.forward_cl(cl(y), yh)
     lg = lf = ld = 0.0
     for d_i, (logit, fmap) in enumerate(outs):
         # logits of a random-init discriminator on a 0.06-amplitude waveform are small differences of large terms: the
         # relative error of the 6-layer chain is amplified (measured 5e-4 .. 1.1e-2), the loss below pins the absolute scale
-        out.append((f"cfg5 D[{d_i}] logits", rel(logit[B:].reshape(B, -1), gs[d_i]), TOL_TC * 8))
+        out.append((f"cfg5 D[{d_i}] logits", rel(logit[B:].reshape(B, -1), gs[d_i]), KINK_TOL))
         lg = lg + ops.mean_sq_one_minus(logit[B:])
         ld = ld + ops.mean_sq_one_minus(logit[:B]) + ops.mean_sq(logit[B:])
         for f in fmap:
@@ -910,10 +922,10 @@ def check_vocoder_cfg5():
     loss = lg + 2.0 * lf + ld
     names = [n for n, _ in net_d.named_parameters()]
     grads = torch.autograd.grad(loss, [zd] + [p for _, p in net_d.named_parameters()])
-    out.append(("cfg5 loss (gen + fm + disc)", abs(float(loss.detach()) - float(loss_o)) / abs(float(loss_o)), TOL_TC))
+    out.append(("cfg5 loss (gen + fm + disc)", abs(float(loss.detach()) - float(loss_o)) / abs(float(loss_o)), TOL_NET))
     # dz crosses ~60 leaky-ReLU layers at 48 000 positions: kink flips accumulate (measured 4.7e-2; an indexing error in any
     # data-gradient path would give O(1))
-    out.append(("cfg5 dz (through D and the whole generator)", rel(cf(grads[0]), zr.grad), 4 * KINK_TOL))
+    out.append(("cfg5 dz (through D and the whole generator)", rel(cf(grads[0]), zr.grad), NET_GRAD_TENSOR))
     num = den = 0.0
     for n, gk in zip(names, grads[1:]):
         r = PDr[n].grad
@@ -922,9 +934,297 @@ def check_vocoder_cfg5():
     return out
 
 
+# ------------------------------------------------------------------------------------------------
+# Full-size parity: the benchmarked shapes, through the SAME captured CUDA graph bench.py replays
+# ------------------------------------------------------------------------------------------------
+REPORT = {}          # tag -> per-tensor error table (run_gpu_checks.py dumps it to gpurun_out/parity_table.json)
+
+
+def _oracle_threads():
+    """torch's intra-op pool stops scaling (and then collapses) on these conv shapes well before the host's core count."""
+    n = max(1, min(os.cpu_count() or 1, 16))
+    torch.set_num_threads(n)
+    return n
+
+
+def check_s2_full(tag="cfg3"):
+    """BASELINE config 3 shapes (T = 346 frames, 120 phonemes, B = 8: every launch takes the same kernel family as the
+    benchmarked B = 16).  Losses, forward tensors and EVERY parameter gradient of the graph-replayed step (lr forced to 0 so
+    the D update inside the step leaves the weights the oracle sees) vs the CPU oracle, plus the reference's own numbers
+    from tests/golden/s2_<tag>.json (written by oracle/pin_against_reference.py --full from the imported reference)."""
+    from easevoice_trainer_b200 import ops
+    from easevoice_trainer_b200.train import s2_step
+    out = []
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", f"s2_{tag}.json")))
+    c = gold["cfg"]
+    B, T, X = c["B"], c["T"], c["X"]
+    net_g, net_d, PG, PD = _load_models(c["g_seed"], c["d_seed"])                # eval(): dropout off, like the pin
+    wav, ssl, text, spec_len, text_len = s2_oracle.synthetic_batch(B, T, X, c["batch_seed"], c["ragged"])
+    spec = mel_oracle.spectrogram(wav.squeeze(1), 2048, 640, 2048)
+    g = _gen(c["noise_seed"])
+    noise = torch.randn(B, 192, T, generator=g)
+    ids = (torch.rand(B, generator=g) * (spec_len - 32 + 1)).long()
+    assert ids.tolist() == gold["ids_slice"] and spec_len.tolist() == gold["spec_len"]
+    # ---- ours first (GPU work overlaps nothing; keeps the CPU oracle's memory high-water mark out of the way)
+    stepper = s2_step.S2Step(net_g, net_d, dict(s2_oracle.S2_TRAIN), dict(s2_oracle.S2_DATA))
+    stepper.set_lr(0.0)
+    batch = dict(ssl=cl(ssl), spec=ops.to_channels_last(spec.to(DEV), pad_to=4), lengths=spec_len.to(DEV).to(torch.int32),
+                 wav=wav.reshape(B, -1, 1).to(DEV), text=text.to(DEV), text_lengths=text_len.to(DEV).to(torch.int32))
+    noise_d, ids_d = cl(noise), ids.to(DEV)
+    ops.dispatch_reset()
+    stepper.step(batch, noise=noise_d, ids_slice=ids_d)                             # eager: host-side dispatch accounting
+    disp = ops.dispatch_stats()
+    res = stepper.graph_step(batch, noise=noise_d, ids_slice=ids_d, keep=True)    # capture (+2 warm-ups) + replay
+    res = stepper.graph_step(batch, noise=noise_d, ids_slice=ids_d, keep=True)    # pure replay: what bench.py times
+    torch.cuda.synchronize()
+    fw = {k: cf(v) for k, v in res["forward"].items() if k in ("z", "z_p", "m_p", "logs_p", "m_q", "logs_q", "y_hat", "y_hat_mel", "y_mel", "y")}
+    codes = res["forward"]["codes"].cpu()
+    ours = {k: float(res[k]) for k in ("loss_disc", "loss_gen_all", "loss_gen", "loss_fm", "loss_mel", "loss_kl")}
+    gd = {n: stepper.opt_d.flat_g[o:o + k].view(p.shape).cpu().clone() for n, p, (o, k) in
+          ((n, p, stepper.opt_d.slots[n]) for n, p in net_d.named_parameters())}
+    gg = {n: stepper.opt_g.flat_g[o:o + k].view(p.shape).cpu().clone() for n, p, (o, k) in
+          ((n, p, stepper.opt_g.slots[n]) for n, p in net_g.named_parameters())}
+    tot = sum(disp.values())
+    tma = disp["fwd_gemm_tma"] + disp["wgrad_gemm_tma"] + disp["gemm_tf32"]
+    out.append((f"s2[{tag}] share of contraction flops NOT on gemm_tma_kernel", 1.0 - tma / tot, 0.20))
+    # ---- oracle (CPU, fp32)
+    nthr = _oracle_threads()
+    OG = {k: (v.clone().requires_grad_(True) if k not in s2_oracle.GEN_BUFFERS else v.clone()) for k, v in PG.items()}
+    OD = {k: v.clone().requires_grad_(True) for k, v in PD.items()}
+    o = s2_oracle.s2_losses(OG, OD, (ssl, spec, spec_len, wav, text, text_len), noise, ids)
+    gd_ref = dict(zip(OD.keys(), torch.autograd.grad(o["loss_disc"], list(OD.values()), retain_graph=True)))
+    gn = [k for k in OG if k not in s2_oracle.GEN_BUFFERS]
+    gg_ref = dict(zip(gn, torch.autograd.grad(o["loss_gen_all"], [OG[k] for k in gn], allow_unused=True)))
+    table = dict(cfg=c, oracle_threads=nthr, dispatch_flops=disp, forward={}, losses={}, grad_d={}, grad_g={})
+    for k in ("loss_disc", "loss_gen_all", "loss_gen", "loss_fm", "loss_mel", "loss_kl"):
+        e_o, e_g = abs(float(o[k]) - gold[k]) / abs(gold[k]), abs(ours[k] - gold[k]) / abs(gold[k])
+        out.append((f"s2[{tag}] oracle {k} vs reference golden", e_o, 1e-4))
+        out.append((f"s2[{tag}] {k} vs reference golden", e_g, TOL_NET))
+        out.append((f"s2[{tag}] {k} vs oracle", abs(ours[k] - float(o[k])) / abs(float(o[k])), TOL_NET))
+        table["losses"][k] = dict(ours=ours[k], oracle=float(o[k]), reference=gold[k])
+    out.append((f"s2[{tag}] VQ codes mismatches", float((codes != o["codes"]).sum()), 0.5))
+    out.append((f"s2[{tag}] VQ codes checksum == reference golden", abs(int(codes.sum()) - gold["codes_sum"]), 0))
+    for k in ("z", "z_p", "m_p", "logs_p", "m_q", "logs_q", "y_hat", "y_hat_mel"):
+        e = rel(fw[k], o[k])
+        table["forward"][k] = e
+        out.append((f"s2[{tag}] {k}", e, TOL_NET))
+    out.append((f"s2[{tag}] y_mel", rel(fw["y_mel"], o["y_mel"]), 1e-5))
+    out.append((f"s2[{tag}] y slice", rel(fw["y"], o["y"]), 1e-12))
+    for k in ("z", "z_p", "m_p", "logs_p", "m_q", "logs_q"):                        # the REFERENCE's values, not the oracle's
+        gk = torch.tensor(gold[k + "_b0_c5_t100_108"])
+        out.append((f"s2[{tag}] {k}[0,5,100:108] vs reference golden", float((fw[k][0, 5, 100:108] - gk).norm() / (gk.norm() + 1e-12)), 3 * TOL_NET))
+        out.append((f"s2[{tag}] |{k}| vs reference golden", abs(float(fw[k].norm()) - gold[k + "_norm"]) / gold[k + "_norm"], TOL_NET))
+    gk = torch.tensor(gold["y_hat_b1_0_4000_4008"])
+    out.append((f"s2[{tag}] y_hat[1,0,4000:4008] vs reference golden", float((fw["y_hat"][1, 0, 4000:4008] - gk).norm() / (gk.norm() + 1e-12)), 10 * TOL_NET))
+    for nm, ours_g, ref_g, gold_n, unused_ok in (("D", gd, gd_ref, gold["grad_norms_d"], ()), ("G", gg, gg_ref, gold["grad_norms_g"], s2_step.FROZEN_G)):
+        worst, wname, num, den, worst_gold, wg_name = 0.0, "", 0.0, 0.0, 0.0, ""
+        for n, gr in ours_g.items():
+            if n in unused_ok:
+                assert ref_g[n] is None
+                continue
+            if n.endswith(("conv_k.bias", "w_ks.bias")):       # analytically zero gradients (see pin_against_reference.py)
+                continue
+            e = rel(gr, ref_g[n])
+            table["grad_" + nm.lower()][n] = dict(rel_l2=e, norm=float(gr.norm()), norm_reference=gold_n[n])
+            num += float((gr.double() - ref_g[n].double()).pow(2).sum())
+            den += float(ref_g[n].double().pow(2).sum())
+            if e > worst:
+                worst, wname = e, n
+            eg = abs(float(gr.norm()) - gold_n[n]) / (gold_n[n] + 1e-30)
+            if eg > worst_gold:
+                worst_gold, wg_name = eg, n
+        out.append((f"s2[{tag}] {nm} param grads worst rel-L2 ({wname})", worst, NET_GRAD_TENSOR))
+        out.append((f"s2[{tag}] {nm} param grads global rel-L2", math.sqrt(num / den), NET_GRAD_GLOBAL))
+        out.append((f"s2[{tag}] {nm} |grad| of every tensor vs reference golden, worst ({wg_name})", worst_gold, NET_GRAD_TENSOR))
+    REPORT[f"s2_{tag}"] = table
+    return out
+
+
+def check_gpt_full(tag="cfg2"):
+    """BASELINE config 2 at the benchmarked model size (24 layers, X = 256, Y = 1024, ragged lengths 512..1024, B = 4):
+    loss / targets / logits / every parameter gradient of the GRAPH-REPLAYED micro-batch vs the CPU oracle and the
+    reference's numbers (tests/golden/gpt_cfg2.json)."""
+    from easevoice_trainer_b200 import ops
+    from easevoice_trainer_b200.models_gpt import Text2SemanticDecoder
+    from easevoice_trainer_b200.train.gpt_step import GptStep
+    out = []
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", f"gpt_{tag}.json")))
+    m = gold["model"]
+    spec = gpt_oracle.gpt_param_spec(m)
+    P = gpt_oracle.init_params(spec, gold["param_seed"])
+    P["ar_text_position.alpha"].fill_(gold["alpha_text"]); P["ar_audio_position.alpha"].fill_(gold["alpha_audio"])
+    net = Text2SemanticDecoder({"model": m}, layer_dropout=0.0)
+    net.load_state_dict(P)
+    net = net.to(DEV).eval()
+    x, xl, y, yl, bert = gpt_oracle.synthetic_gpt_batch(gold["B"], gold["X"], gold["Y"], gold["batch_seed"], gold["ragged"])
+    step = GptStep(net)
+    step.batch_idx = 1                                   # a micro-batch without optimizer update: flat_g = its gradients
+    batch = dict(phoneme_ids=x.to(DEV), phoneme_ids_len=xl.to(DEV), semantic_ids=y.to(DEV), semantic_ids_len=yl.to(DEV),
+                 bert_feature=bert.to(DEV))
+    ops.dispatch_reset()
+    loss, acc = step.graph_step(batch)                   # capture (its warm-ups leave flat_g untouched) + replay
+    disp = ops.dispatch_stats()
+    torch.cuda.synchronize()
+    loss, acc = float(loss), float(acc)
+    logits = net.last_logits[..., :m["vocab_size"]].detach().cpu()
+    names = [n for n, _ in net.named_parameters()]
+    grads = {n: step.opt.flat_g[o:o + k].view(p.shape).cpu().clone() for n, p, (o, k) in
+             ((n, p, step.opt.slots[n]) for n, p in net.named_parameters())}
+    y_in, tg = net.make_targets(y.to(DEV), yl.to(DEV))
+    tot = sum(disp.values())
+    out.append((f"gpt[{tag}] share of contraction flops NOT on gemm_tma_kernel", 1.0 - (disp["fwd_gemm_tma"] + disp["wgrad_gemm_tma"] + disp["gemm_tf32"]) / tot, 0.05))
+    nthr = _oracle_threads()
+    Pq = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    taps = {}
+    loss_o, acc_o, logits_o, tg_o = gpt_oracle.forward_old(Pq, x, xl, y, yl, bert, m, taps)
+    loss_o.backward()
+    out.append((f"gpt[{tag}] targets (pad_y_eos) exact", float((tg.cpu() != tg_o).sum()), 0.0))
+    out.append((f"gpt[{tag}] targets checksum == reference golden", abs(int(tg.sum()) - gold["targets_sum"]), 0))
+    out.append((f"gpt[{tag}] logits", rel(logits.reshape(logits_o.shape), logits_o), TOL_NET))
+    out.append((f"gpt[{tag}] loss vs oracle", abs(loss - float(loss_o)) / abs(float(loss_o)), TOL_NET))
+    out.append((f"gpt[{tag}] loss vs reference golden", abs(loss - gold["loss"]) / abs(gold["loss"]), TOL_NET))
+    out.append((f"gpt[{tag}] top-3 acc vs reference golden", abs(acc - gold["acc"]), 8.0 / float(yl.sum())))
+    table = dict(B=gold["B"], X=gold["X"], Y=gold["Y"], oracle_threads=nthr, dispatch_flops=disp, loss=dict(ours=loss, oracle=float(loss_o), reference=gold["loss"]), grad={})
+    worst, wname, num, den, gl, gl_name = 0.0, "", 0.0, 0.0, 0.0, ""
+    alpha_rows = []
+    for n in names:
+        gk, gr = grads[n], Pq[n].grad
+        if n.endswith(".alpha"):
+            alpha_rows.append((n, abs(float(gk) - float(gr))))
+            continue
+        r = rel(gk, gr)
+        table["grad"][n] = dict(rel_l2=r, norm=float(gk.norm()), norm_reference=gold["grad_norms"][n])
+        if r > worst:
+            worst, wname = r, n
+        num += float((gk.double() - gr.double()).pow(2).sum()); den += float(gr.double().pow(2).sum())
+        e = abs(float(gk.norm()) - gold["grad_norms"][n]) / (gold["grad_norms"][n] + 1e-12)
+        if e > gl:
+            gl, gl_name = e, n
+    alpha_tol = 4.0 * max(math.sqrt(num / den), 1e-4) * float(taps["h0"].grad.norm()) * math.sqrt(0.5)
+    for n, e in alpha_rows:
+        out.append((f"gpt[{tag}] d{n} (abs, projection-noise bound)", e, alpha_tol))
+    out.append((f"gpt[{tag}] grads worst tensor ({wname})", worst, 2 * KINK_TOL))
+    out.append((f"gpt[{tag}] grads global", math.sqrt(num / den), KINK_TOL))
+    out.append((f"gpt[{tag}] |grad| of every tensor vs reference golden, worst ({gl_name})", gl, 2 * KINK_TOL))
+    REPORT[f"gpt_{tag}"] = table
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# the trainer, end to end, on files (SURVEY 8b: class API, files in / out, stdout protocol, TB scalars, resume)
+# ------------------------------------------------------------------------------------------------
+def make_s2_dataset_dir(root, n_utt=8, seed=0, min_s=1.0, max_s=3.2):
+    """Synthetic <train_input_dir> in the layout Normalize writes (normalize.py:65-211): 2-name2text.txt,
+    4-cnhubert/<name>.pt f32 [1,768,T50Hz], 5-wav32k/<name> int16 mono 32 kHz."""
+    import wave
+    import numpy as np
+    g = _gen(seed)
+    os.makedirs(os.path.join(root, "4-cnhubert"), exist_ok=True)
+    os.makedirs(os.path.join(root, "5-wav32k"), exist_ok=True)
+    table = {f"p{i}": i for i in range(732)}
+    lines = []
+    for u in range(n_utt):
+        name = f"utt{u:02d}.wav"
+        n = int((min_s + (max_s - min_s) * float(torch.rand(1, generator=g))) * 32000)
+        pcm = ((torch.rand(n, generator=g) - 0.5) * 20000).to(torch.int16).numpy()
+        with wave.open(os.path.join(root, "5-wav32k", name), "wb") as w:
+            w.setnchannels(1); w.setsampwidth(2); w.setframerate(32000); w.writeframes(pcm.astype(np.int16).tobytes())
+        T = n // 640
+        torch.save(torch.randn(1, 768, T, generator=g), os.path.join(root, "4-cnhubert", name + ".pt"))
+        nph = 6 + int(torch.randint(0, 30, (1,), generator=g))
+        phones = " ".join(f"p{int(i)}" for i in torch.randint(0, 732, (nph,), generator=g))
+        lines.append(f"{name}\t{phones}\t1\ttext")
+    with open(os.path.join(root, "2-name2text.txt"), "w", encoding="utf8") as f:
+        f.write("\n".join(lines) + "\n")
+    return table
+
+
+def check_sovits_train_e2e(gpu_ids="0"):
+    """SovitsTrain(params, dataset).train() on files: loss lines every 10 steps, G_/D_latest.pth, export without enc_q,
+    TensorBoard scalars of sovits.py:539-568, frozen ssl_proj bit-identical, resume continues from the stored epoch."""
+    import contextlib
+    import io
+    import tempfile
+    from easevoice_trainer_b200.train import data as s2data
+    from easevoice_trainer_b200.train import s2_step
+    from easevoice_trainer_b200.train.sovits import SovitsTrain, SovitsTrainParams
+    from easevoice_trainer_b200 import models, configs
+    out = []
+    tmp = tempfile.mkdtemp(prefix="evk_e2e_")
+    old_base = os.environ.get("EASEVOICE_BASE_PATH")
+    os.environ["EASEVOICE_BASE_PATH"] = tmp
+    try:
+        table = make_s2_dataset_dir(os.path.join(tmp, "in"))
+        ds = s2data.TextAudioSpeakerLoader(os.path.join(tmp, "in"), phoneme_table=table)
+        nb = len(ds) // 4                                                    # 100 replicated items / batch 4 -> 25 steps / epoch
+        params = SovitsTrainParams(batch_size=4, total_epochs=2, save_every_epoch=1, gpu_ids=gpu_ids, train_input_dir=os.path.join(tmp, "in"),
+                                   output_model_name="e2e", project_dir=tmp)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            res = SovitsTrain(params, dataset=ds).train()
+        lines = [json.loads(l.split(" ", 1)[1]) for l in buf.getvalue().splitlines() if l.startswith("loss-of-easevoice")]
+        world = len(gpu_ids.split(","))
+        steps = 2 * (nb // world)
+        if world == 1:                  # spawned ranks write to their own stdout: the line protocol is checked single-process
+            out.append(("e2e loss lines every 10 steps", abs(len(lines) - len(range(0, steps, 10))), 0))
+            out.append(("e2e loss line keys", 0.0 if all({"step", "loss", "loss/g/total", "loss/d/total", "learning_rate"} <= set(l) for l in lines) else 1.0, 0.0))
+            fin = all(math.isfinite(float(l["loss"])) for l in lines)
+            out.append(("e2e losses finite", 0.0 if fin else 1.0, 0.0))
+        logs = os.path.join(res.model_path, "logs")
+        for f in ("G_latest.pth", "D_latest.pth"):
+            out.append((f"e2e {f} written", 0.0 if os.path.isfile(os.path.join(logs, f)) else 1.0, 0.0))
+        exp = os.path.join(res.model_path, f"e2e_e2_s{steps}.pth")
+        out.append(("e2e export written", 0.0 if os.path.isfile(exp) else 1.0, 0.0))
+        ex = torch.load(exp, map_location="cpu")
+        out.append(("e2e export: fp16, no enc_q, config + info", 0.0 if (all(v.dtype == torch.float16 for v in ex["weight"].values()) and
+                    not any("enc_q" in k for k in ex["weight"]) and ex["info"] == f"2epoch_{steps}iteration" and "model" in ex["config"]) else 1.0, 0.0))
+        ck = torch.load(os.path.join(logs, "G_latest.pth"), map_location="cpu")
+        out.append(("e2e checkpoint iteration == epoch", abs(ck["iteration"] - 2), 0))
+        hps = configs.load_s2_config()
+        torch.manual_seed(hps["train"]["seed"])
+        fresh = models.SynthesizerTrn(hps["data"]["filter_length"] // 2 + 1, hps["train"]["segment_size"] // hps["data"]["hop_length"],
+                                      n_speakers=hps["data"]["n_speakers"], **hps["model"]).state_dict()
+        for n in s2_step.FROZEN_G:
+            out.append((f"e2e frozen {n} bit-identical after {steps} steps", float((ck["model"][n] != fresh[n]).sum()), 0.0))
+        moved = float((ck["model"]["dec.conv_pre.weight"] - fresh["dec.conv_pre.weight"]).abs().max())
+        out.append(("e2e trained weights moved", 0.0 if moved > 0 else 1.0, 0.0))
+        out.append(("e2e optimizer state torch-style (lr in every group)", 0.0 if all("lr" in g and "initial_lr" in g for g in ck["optimizer"]["param_groups"]) else 1.0, 0.0))
+        # TensorBoard scalars (sovits.py:539-568: every 5 steps)
+        from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+        ea = EventAccumulator(os.path.join(tmp, "tb_logs", "e2e"))
+        ea.Reload()
+        tags = set(ea.Tags()["scalars"])
+        want = {"loss/g/total", "loss/d/total", "learning_rate", "grad_norm_d", "grad_norm_g", "loss/g/fm", "loss/g/mel", "loss/g/kl_ssl", "loss/g/kl"}
+        out.append(("e2e TensorBoard scalar tags", float(len(want - tags)), 0.0))
+        n_tb = len(ea.Scalars("loss/g/total")) if "loss/g/total" in tags else 0
+        out.append(("e2e TensorBoard points every 5 steps", abs(n_tb - len(range(0, steps, 5))), 0))
+        # resume: the stored epoch is re-entered (sovits.py:327-343,378), global_step continues from (epoch-1)*len(loader)
+        params3 = SovitsTrainParams(batch_size=4, total_epochs=3, save_every_epoch=1, gpu_ids=gpu_ids, train_input_dir=os.path.join(tmp, "in"),
+                                    output_model_name="e2e", project_dir=tmp)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            SovitsTrain(params3, dataset=ds).train()
+        lines2 = [json.loads(l.split(" ", 1)[1]) for l in buf.getvalue().splitlines() if l.startswith("loss-of-easevoice")]
+        if world == 1:
+            first = min(int(l["step"]) for l in lines2)
+            out.append(("e2e resume continues at the stored epoch's first step", abs(first - ((nb // world + 9) // 10 * 10)), 0))
+        ck3 = torch.load(os.path.join(logs, "G_latest.pth"), map_location="cpu")
+        out.append(("e2e resumed run saved epoch 3", abs(ck3["iteration"] - 3), 0))
+        out.append(("e2e resumed optimizer step count", abs(float(ck3["optimizer"]["state"][0]["step"]) - 4 * (nb // world)), 0))
+    finally:
+        if old_base is None:
+            os.environ.pop("EASEVOICE_BASE_PATH", None)
+        else:
+            os.environ["EASEVOICE_BASE_PATH"] = old_base
+    return out
+
+
 ALL = [check_conv, check_conv_transpose, check_elementwise, check_attention, check_vq_losses_optim, check_mel,
        lambda: check_s2("small"), lambda: check_s2("ragged"), check_api_layouts,
        check_gpt_kernels, check_scaled_adam, lambda: check_gpt("small"), lambda: check_gpt("ragged"),
-       check_gpt_dpo_and_trainer, check_gemm_tma, check_vocoder_cfg5]
+       check_gpt_dpo_and_trainer, check_gemm_tma, check_vocoder_cfg5,
+       lambda: check_s2_full("cfg3"), lambda: check_s2_full("cfg3r"), lambda: check_gpt_full("cfg2"),
+       check_sovits_train_e2e]
 NAMES = ["conv", "conv_transpose", "elementwise", "attention", "vq_losses_optim", "mel", "s2_small", "s2_ragged", "api",
-         "gpt_kernels", "scaled_adam", "gpt_small", "gpt_ragged", "gpt_dpo_trainer", "gemm_tma", "vocoder_cfg5"]
+         "gpt_kernels", "scaled_adam", "gpt_small", "gpt_ragged", "gpt_dpo_trainer", "gemm_tma", "vocoder_cfg5",
+         "s2_cfg3", "s2_cfg3r", "gpt_cfg2", "sovits_train_e2e"]

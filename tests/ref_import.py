@@ -34,6 +34,11 @@ def import_hot_path():
     """-> (mel_processing, models, losses, commons) of the reference (see oracle/pin_against_reference.py)."""
     from oracle import pin_against_reference as pin
     mods = pin.import_reference()
+    # the reference has its own top-level `tests` package: keep it BEHIND this repo on sys.path (spawned workers of
+    # later tests re-import `tests.*` by name)
+    while REF in sys.path:
+        sys.path.remove(REF)
+    sys.path.append(REF)
     for n in ("librosa", "librosa.filters"):
         sys.modules[n].__spec__ = importlib.machinery.ModuleSpec(n, None)
     return mods

@@ -55,6 +55,9 @@ def main():
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     with open(args.out, "w") as f:
         json.dump(dict(precise=args.precise, failed=failed, results=results), f, indent=1)
+    if checks.REPORT:
+        with open(os.path.join(os.path.dirname(args.out), "parity_table.json"), "w") as f:
+            json.dump(checks.REPORT, f, indent=1)
     print(f"TOTAL {len(results)} checks, {failed} failed (precise={args.precise})")
     return 1 if failed else 0
 

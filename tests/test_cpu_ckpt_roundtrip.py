@@ -26,6 +26,7 @@ def test_s2_export_loads_through_reference_tts(tmp_path):
     hps = configs.load_s2_config()
     net_g = models.SynthesizerTrn(hps["data"]["filter_length"] // 2 + 1, hps["train"]["segment_size"] // hps["data"]["hop_length"],
                                   n_speakers=hps["data"]["n_speakers"], **hps["model"])
+    before = set(os.listdir("."))
     path = ckpt.export_weights(net_g.state_dict(), hps, "rt_e1_s10", 1, 10, str(tmp_path))
     fake = _fake_tts()
     tts.TTS.init_vits_weights(fake, path)                        # the reference's own loader, unmodified
@@ -35,7 +36,7 @@ def test_s2_export_loads_through_reference_tts(tmp_path):
     for k, v in ref_sd.items():
         assert torch.equal(v, ours[k].float()), k                # strict=False in the loader: prove nothing was skipped
     assert fake.configs.sampling_rate == 32000 and fake.configs.hop_length == 640
-    assert not [n for n in os.listdir(".") if n.endswith(".pth")], "temp file must not be left in / written to the CWD"
+    assert set(os.listdir(".")) == before, "the temp file of save_with_torch must live next to its target, not in the CWD"
 
 
 def test_gpt_export_loads_through_reference_tts(tmp_path):

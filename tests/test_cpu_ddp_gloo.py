@@ -89,3 +89,40 @@ def test_two_rank_gpt_accumulate_then_single_allreduce():
     mp.spawn(_gpt_worker, nprocs=2, args=(2, 29514, ret), join=True)
     assert ret["chunks_cover"]
     assert ret["gpt_err"] < 1e-5, ret["gpt_err"]
+
+
+def _shape_worker(rank, world, port, ret):
+    """ranks collate batches of different lengths; every rank must end up with the SAME padded shape each
+    iteration (otherwise they would capture CUDA graphs at different iterations and mis-pair their all-reduces)."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from easevoice_trainer_b200.train import s2_step
+    from easevoice_trainer_b200.train.data import TextAudioSpeakerCollate
+
+    class Host:                                               # the two attributes S2Step.agree_shape uses
+        world, _shape_group = 2, None
+    host = Host()
+    g = torch.Generator().manual_seed(100 + rank)             # different data per rank
+    shapes = []
+    for it in range(6):
+        items = []
+        for _ in range(3):
+            T = int(torch.randint(40, 200, (1,), generator=g))
+            X = int(torch.randint(5, 90, (1,), generator=g))
+            items.append((torch.randn(1, 768, T), torch.rand(1, T * 640 + 17) - 0.5, torch.randint(0, 732, (X,))))
+        b = TextAudioSpeakerCollate(640)(items)
+        Tq, Xq = s2_step.S2Step.agree_shape(host, b["ssl"].shape[2], b["text"].shape[1])
+        p = s2_step.pad_host_batch(b, Tq, Xq, 640)
+        assert p["ssl"].shape[2] == Tq and p["wav"].shape[2] == Tq * 640 and p["text"].shape[1] == Xq
+        assert Tq % 32 == 0 and Xq % 32 == 0 and Tq >= b["ssl"].shape[2]
+        assert torch.equal(p["ssl"][:, :, :b["ssl"].shape[2]], b["ssl"]) and float(p["ssl"][:, :, b["ssl"].shape[2]:].abs().sum()) == 0.0
+        shapes.append((Tq, Xq))
+    ret[rank] = shapes
+    dist.destroy_process_group()
+
+
+def test_two_ranks_agree_on_padded_shapes():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_shape_worker, nprocs=2, args=(2, 29516, ret), join=True)
+    assert ret[0] == ret[1] and len(set(ret[0])) > 1, (ret[0], ret[1])

@@ -5,7 +5,8 @@ import torch
 pytestmark = pytest.mark.gpu
 
 GROUPS = ["conv", "conv_transpose", "elementwise", "attention", "vq_losses_optim", "mel", "s2_small", "s2_ragged", "api",
-          "gpt_kernels", "scaled_adam", "gpt_small", "gpt_ragged", "gpt_dpo_trainer", "gemm_tma", "vocoder_cfg5"]
+          "gpt_kernels", "scaled_adam", "gpt_small", "gpt_ragged", "gpt_dpo_trainer", "gemm_tma", "vocoder_cfg5",
+          "s2_cfg3", "s2_cfg3r", "gpt_cfg2", "sovits_train_e2e"]          # the last three: BASELINE configs 3 / 2 at the benchmarked shapes
 
 
 @pytest.fixture(scope="module")
@@ -61,3 +62,14 @@ def test_precise_mode_tightens_gpt(evk):
     assert not bad, bad
     glob = [e for n, e, t in g_rows if "grads global" in n][0]
     assert glob <= 5e-3, glob
+
+
+def test_sovits_train_two_ranks_ragged_shapes(evk):
+    """ranks whose batches have different lengths must still capture / replay / all-reduce in lock-step
+    (shapes agreed over the gloo side group, no collectives in warm-up).  Needs 2 GPUs: `gpurun --gpus 2`."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from tests import checks
+    rows = checks.check_sovits_train_e2e(gpu_ids="0,1")
+    bad = [(n, e, t) for n, e, t in rows if not (e == e and e <= t)]
+    assert not bad, bad
