@@ -38,3 +38,13 @@ def generator_loss(disc_outputs):
 def kl_loss(z_p, logs_q, m_p, logs_p, lengths):
     """losses.py:46-61 on channels-last tensors with an int32 length vector instead of a dense mask."""
     return ops.kl_loss(z_p, logs_q, m_p, logs_p, lengths)
+
+
+def multi_resolution_stft_loss(y_hat, y, window_sizes=(4096, 2048, 1024, 512, 256), hop_size=147, n_fft=2048):
+    """The only multi-resolution STFT loss defined in the reference tree (audiokit/uvr5/.../bs_roformer.py:565-581): sum over
+    window sizes of F.l1_loss between the complex torch.stft(n_fft=max(win, 2048), hop=147, win_length=win, Hann, center=True)
+    of the generated and the target waveform, computed by the general STFT kernel and its adjoint.  y_hat, y: [B, L] or
+    [B, 1, L].  BASELINE.json lists it for config 5; SovitsTrain's own loss has no such term (sovits.py:513-518), so
+    S2Step only adds it when hps.train["c_mrstft"] > 0 (off by default)."""
+    B = y_hat.shape[0]
+    return ops.mrstft_loss(y_hat.reshape(B, -1), y.reshape(B, -1), tuple(window_sizes), hop_size, n_fft)

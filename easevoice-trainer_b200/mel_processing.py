@@ -47,16 +47,18 @@ def get_bank(sr, n_fft, n_mels, fmin, fmax, device):
 
 
 def _check(n_fft, win_size, center):
-    if n_fft != 2048 or win_size != 2048 or center:
-        raise NotImplementedError("the fused kernel implements the reference's training configuration: "
-                                  "n_fft = win = 2048, center=False (configs/s2.json:26-28)")
+    if center:
+        raise NotImplementedError("center=True on top of the manual reflect padding (a double reflection) is not a configuration "
+                                  "the reference uses; ops.stft(center=True) gives torch.stft's own centred transform")
+    if n_fft < 256 or n_fft > 4096 or n_fft & (n_fft - 1) or win_size > n_fft or win_size & (win_size - 1):
+        raise NotImplementedError("n_fft must be a power of two in [256, 4096] and win_size a power of two <= n_fft")
 
 
-def spectrogram_torch(y, n_fft, sampling_rate, hop_size, win_size, center=False):
-    """mel_processing.py:40-74: y [B, L] -> |X| [B, n_fft//2+1, T]."""
+def spectrogram_torch(y, n_fft, sampling_rate, hop_size, win_size, center=False, lengths=None):
+    """mel_processing.py:40-74: y [B, L] -> |X| [B, n_fft//2+1, T].  lengths (optional int32 [B]): per-row valid samples."""
     _check(n_fft, win_size, center)
     bank = get_bank(sampling_rate, n_fft, 128, 0.0, None, y.device)
-    spec, _ = ops.mel_frontend(y, bank, hop_size, want_spec=True, want_mel=False)
+    spec, _ = ops.mel_frontend(y, bank, hop_size, want_spec=True, want_mel=False, lens=lengths, n_fft=n_fft, win=win_size)
     return ops.to_channels_first(spec)
 
 
@@ -70,7 +72,7 @@ def mel_spectrogram_torch(y, n_fft, num_mels, sampling_rate, hop_size, win_size,
     """mel_processing.py:93-142: y [B, L] -> log-mel [B, num_mels, T]; differentiable wrt y."""
     _check(n_fft, win_size, center)
     bank = get_bank(sampling_rate, n_fft, num_mels, fmin, fmax, y.device)
-    _, mel = ops.mel_frontend(y, bank, hop_size, want_spec=False, want_mel=True)
+    _, mel = ops.mel_frontend(y, bank, hop_size, want_spec=False, want_mel=True, n_fft=n_fft, win=win_size)
     return ops.to_channels_first(mel) if not mel.requires_grad else _CFirst.apply(mel)
 
 

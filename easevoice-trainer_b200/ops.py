@@ -80,10 +80,16 @@ def dispatch_stats():
 def _timed(name, fn, flops=0.0, nbytes=0.0):
     if _prof is None:
         return fn()
+    before = dispatch_stats() if flops else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     r = fn()
     e1.record()
+    if before is not None:                      # which kernel family served this contraction (library-side accounting)
+        after = dispatch_stats()
+        grown = [k for k in DISPATCH_SLOTS if after[k] > before[k]]
+        if grown:
+            name = f"{name}:{grown[0]}"
     _prof.append((name, e0, e1, flops, nbytes))
     return r
 
@@ -92,6 +98,13 @@ def _call(name, *args):
     global _launches
     _launches += 1
     _timed(name, lambda: L.check(getattr(_lib(), name)(*args, _st())))
+
+
+def _call_f(name, flops, *args):
+    """_call with an algorithmic flop count attached (contractions: shows up in profile_end / the bench roofline)."""
+    global _launches
+    _launches += 1
+    _timed(name, lambda: L.check(getattr(_lib(), name)(*args, _st())), flops)
 
 
 def _rows(t):
@@ -431,8 +444,8 @@ class _ConvFn(torch.autograd.Function):
                     kblocks = B * ((Ro + 31) // 32)
                     splits = max(1, min(64, 148 // tiles, kblocks // 8))        # one full wave of (tile, split) CTAs
                     offa = (ctypes.c_int32 * nq)(*shifts)
-                    _call("evk_conv_wgrad_tma", _p(dyt), ldo, N * ldo, _p(xt), ldi, C * ldi, B * C * ldi,
-                          dpa.data_ptr() + 4 * qs[0] * N * lda, lda, qstep * N * lda, B, N, C, Ro, Ri, nq, P, offa, splits)
+                    _call_f("evk_conv_wgrad_tma", 2.0 * B * Ro * N * C * nq, _p(dyt), ldo, N * ldo, _p(xt), ldi, C * ldi, B * C * ldi,
+                            dpa.data_ptr() + 4 * qs[0] * N * lda, lda, qstep * N * lda, B, N, C, Ro, Ri, nq, P, offa, splits)
             elif mma:
                 d = _desc(x=x, w=dpa, y=dy, res=None, bias=None, in_len=in_len, out_len=None,
                           x_sb=Tin * P * ldx, x_sh=Cg if G > 1 else 0, w_sb=0, w_sh=Ng * lda if G > 1 else 0, w_sq=N * lda,
@@ -1303,21 +1316,33 @@ class MelBank:
         self.val = torch.tensor(val, dtype=torch.float32, device=device)
 
 
+def stft_frames(L, n_fft, hop, pad):
+    return (L + 2 * pad - n_fft) // hop + 1
+
+
 class _MelFn(torch.autograd.Function):
+    """|X| / log-mel of reflect-padded frames.  geo = (n_fft, hop, win, pad): the training configuration (2048, hop, 2048,
+    (2048 - hop) / 2) runs on the warp-per-frame register-FFT kernel, everything else on the general kernel of stft.cu."""
+
     @staticmethod
-    def forward(ctx, wav, bank, hop, want_spec, want_mel):
+    def forward(ctx, wav, bank, geo, want_spec, want_mel, lens):
+        n_fft, hop, win, pad = geo
         wav = wav.contiguous()
         B, Lw = wav.shape
-        n_fft = 2 * (bank.n_bins - 1)
-        T = (Lw + 2 * ((n_fft - hop) // 2) - n_fft) // hop + 1
+        assert bank.n_bins == n_fft // 2 + 1
+        T = stft_frames(Lw, n_fft, hop, pad)
         need_grad = ctx.needs_input_grad[0]
         ld_spec = (bank.n_bins + 3) // 4 * 4          # 16-byte row pitch so |X| can feed the tensor-core GEMMs directly
         spec = torch.empty((B, T, ld_spec), device=wav.device, dtype=torch.float32) if want_spec else None
         mel = torch.empty((B, T, bank.n_mels), device=wav.device, dtype=torch.float32) if want_mel else None
         cplx = torch.empty((B, T, bank.n_bins, 2), device=wav.device, dtype=torch.float32) if need_grad else None
-        _call("evk_mel_fwd", _p(wav), B, Lw, Lw, hop, bank.n_mels, _p(bank.ptr), _p(bank.idx), _p(bank.val), _p(spec),
-              ld_spec, _p(mel), bank.n_mels, _p(cplx))
-        ctx.k = (bank, hop, B, Lw)
+        if n_fft == 2048 and win == 2048 and pad == (2048 - hop) // 2:
+            _call("evk_mel_fwd", _p(wav), _p(lens), B, Lw, Lw, hop, bank.n_mels, _p(bank.ptr), _p(bank.idx), _p(bank.val), _p(spec),
+                  ld_spec, _p(mel), bank.n_mels, _p(cplx))
+        else:
+            _call("evk_stft_fwd", _p(wav), _p(lens), B, Lw, Lw, n_fft, hop, win, pad, T, ctypes.c_float(1e-6), _p(cplx), _p(spec), ld_spec,
+                  bank.n_mels, _p(bank.ptr), _p(bank.idx), _p(bank.val), ctypes.c_float(1e-5), _p(mel), bank.n_mels)
+        ctx.k = (bank, geo, B, Lw, T, lens)
         ctx.save_for_backward(cplx, mel)
         if spec is None:
             spec = torch.empty(0, device=wav.device)
@@ -1330,19 +1355,87 @@ class _MelFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, _dspec, dmel):
-        bank, hop, B, Lw = ctx.k
+        bank, (n_fft, hop, win, pad), B, Lw, T, lens = ctx.k
         cplx, mel = ctx.saved_tensors
         dmel = dmel.contiguous()
         dwav = torch.zeros((B, Lw), device=dmel.device, dtype=torch.float32)
-        _call("evk_mel_bwd", _p(dmel), bank.n_mels, _p(cplx), _p(mel), bank.n_mels, B, Lw, Lw, hop, bank.n_mels, _p(bank.ptr),
-              _p(bank.idx), _p(bank.val), _p(dwav))
+        _call("evk_stft_bwd", None, _p(dmel), bank.n_mels, _p(cplx), _p(mel), bank.n_mels, ctypes.c_float(1e-6), ctypes.c_float(1e-5),
+              bank.n_mels, _p(bank.ptr), _p(bank.idx), _p(bank.val), _p(lens), B, Lw, Lw, n_fft, hop, win, pad, T, _p(dwav))
+        return dwav, None, None, None, None, None
+
+
+def mel_frontend(wav, bank, hop, want_spec=False, want_mel=True, lens=None, n_fft=2048, win=None, pad=None):
+    """wav [B, L] -> (spec [B,T,n_fft/2+1] or None, log-mel [B,T,n_mels] or None), channels-last; differentiable wrt wav via mel.
+    lens (int32 [B], optional): per-row valid length (reflection at each row's own end, zero frames past it)."""
+    win = n_fft if win is None else win
+    pad = (n_fft - hop) // 2 if pad is None else pad
+    spec, mel = _MelFn.apply(wav, bank, (n_fft, hop, win, pad), want_spec, want_mel, lens)
+    return (spec if want_spec else None), (mel if want_mel else None)
+
+
+class _StftFn(torch.autograd.Function):
+    """complex STFT [B, T, n_fft/2+1, 2] of reflect-padded frames (torch.stft(return_complex=True) semantics when
+    pad = n_fft / 2), differentiable wrt wav."""
+
+    @staticmethod
+    def forward(ctx, wav, n_fft, hop, win, pad):
+        wav = wav.contiguous()
+        B, Lw = wav.shape
+        T = stft_frames(Lw, n_fft, hop, pad)
+        out = torch.empty((B, T, n_fft // 2 + 1, 2), device=wav.device, dtype=torch.float32)
+        _call("evk_stft_fwd", _p(wav), None, B, Lw, Lw, n_fft, hop, win, pad, T, ctypes.c_float(0.0), _p(out), None, 0, 0, None, None, None,
+              ctypes.c_float(0.0), None, 0)
+        ctx.k = (n_fft, hop, win, pad, B, Lw, T)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        n_fft, hop, win, pad, B, Lw, T = ctx.k
+        g = g.contiguous()
+        dwav = torch.zeros((B, Lw), device=g.device, dtype=torch.float32)
+        _call("evk_stft_bwd", _p(g), None, 0, None, None, 0, ctypes.c_float(0.0), ctypes.c_float(0.0), 0, None, None, None, None, B, Lw, Lw,
+              n_fft, hop, win, pad, T, _p(dwav))
         return dwav, None, None, None, None
 
 
-def mel_frontend(wav, bank, hop, want_spec=False, want_mel=True):
-    """wav [B, L] -> (spec [B,T,1025] or None, log-mel [B,T,128] or None), channels-last; differentiable wrt wav via mel."""
-    spec, mel = _MelFn.apply(wav, bank, hop, want_spec, want_mel)
-    return (spec if want_spec else None), (mel if want_mel else None)
+def stft(wav, n_fft, hop, win=None, center=True):
+    """wav [B, L] -> [B, T, n_fft/2+1, 2] (re, im).  center=True: torch.stft defaults (reflect pad n_fft/2, T = 1 + L // hop);
+    center=False: no padding.  Window: periodic Hann(win) centred in the n_fft frame."""
+    win = n_fft if win is None else win
+    return _StftFn.apply(wav, n_fft, hop, win, n_fft // 2 if center else 0)
+
+
+class _CplxL1Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        a, b = a.contiguous(), b.contiguous()
+        n = a.numel() // 2
+        loss = torch.zeros(1, device=a.device, dtype=torch.float32)
+        grad = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        _call("evk_cplx_l1", _p(a), _p(b), n, ctypes.c_float(1.0 / n), _p(loss), _p(grad))
+        ctx.save_for_backward(grad)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad * g, None
+
+
+def complex_l1(a, b):
+    """F.l1_loss(a, b) for complex tensors stored as [..., 2]: mean modulus of the difference; gradient wrt a only."""
+    return _CplxL1Fn.apply(a, b.detach())
+
+
+def mrstft_loss(y_hat, y, windows=(4096, 2048, 1024, 512, 256), hop=147, n_fft_min=2048):
+    """Multi-resolution STFT loss exactly as the reference defines it (bs_roformer.py:565-581): sum over window sizes of the
+    complex L1 between torch.stft(n_fft=max(win, 2048), hop=147, win_length=win, hann, center=True) of both signals.
+    y_hat, y: [B, L].  An opt-in extension of the stage-2 generator loss (BASELINE config 5); not part of SovitsTrain parity."""
+    total = 0
+    for w in windows:
+        n_fft = max(w, n_fft_min)
+        total = total + complex_l1(stft(y_hat, n_fft, hop, w), stft(y.detach(), n_fft, hop, w))
+    return total
 
 
 def spec_to_mel(spec, bank):
@@ -1550,6 +1643,6 @@ def gemm_tf32(a, b, out=None, bias=None, res=None, act=ACT_NONE, slope=0.0, spli
     assert b.shape[1] == K and a.stride(1) == 1 and b.stride(1) == 1
     if out is None:
         out = (torch.zeros if splits > 1 else torch.empty)((M, N), device=a.device, dtype=torch.float32)
-    _call("evk_gemm_tf32", _p(a), a.stride(0), _p(b), b.stride(0), _p(out), out.stride(0), M, N, K, _p(bias), _p(res),
-          res.stride(0) if res is not None else 0, act, ctypes.c_float(slope), splits)
+    _call_f("evk_gemm_tf32", 2.0 * M * N * K, _p(a), a.stride(0), _p(b), b.stride(0), _p(out), out.stride(0), M, N, K, _p(bias),
+            _p(res), res.stride(0) if res is not None else 0, act, ctypes.c_float(slope), splits)
     return out

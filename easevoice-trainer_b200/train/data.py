@@ -2,7 +2,8 @@
 sampler (reference: src/easevoice/module/data_utils.py:14-324).  Differences: the wav files under 5-wav32k are read
 directly (they are already 32 kHz mono int16; the reference pipes each one through an ffmpeg subprocess), and |X| is
 NOT computed per item on CPU workers -- the trainer computes it for the whole batch on the GPU with the fused mel
-kernel (s2_step.to_device_batch).
+kernel (s2_step.to_device_batch), which takes the per-item sample counts (`wav_lengths`) so that every row is
+reflect-padded at its own end and zero beyond its own last frame, exactly like the reference's per-item features.
 """
 import math
 import os
@@ -92,6 +93,7 @@ class TextAudioSpeakerCollate:
         wav = torch.zeros(B, 1, L)
         text = torch.zeros(B, X, dtype=torch.long)
         lengths = torch.zeros(B, dtype=torch.long)
+        wav_lengths = torch.zeros(B, dtype=torch.long)
         text_lengths = torch.zeros(B, dtype=torch.long)
         for k, i in enumerate(order):
             s, w, t = batch[i]
@@ -99,8 +101,8 @@ class TextAudioSpeakerCollate:
             ssl[k, :, :min(s.shape[-1], Tp)] = s[0, :, :Tp]
             wav[k, :, :w.shape[1]] = w
             text[k, :t.shape[0]] = t
-            lengths[k], text_lengths[k] = n, t.shape[0]
-        return dict(ssl=ssl, wav=wav, text=text, lengths=lengths, text_lengths=text_lengths)
+            lengths[k], text_lengths[k], wav_lengths[k] = n, t.shape[0], w.shape[1]
+        return dict(ssl=ssl, wav=wav, text=text, lengths=lengths, text_lengths=text_lengths, wav_lengths=wav_lengths)
 
 
 class DistributedBucketSampler(torch.utils.data.Sampler):

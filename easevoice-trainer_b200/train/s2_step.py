@@ -255,7 +255,12 @@ class S2Step:
             loss_gen = loss_gen + ops.mean_sq_one_minus(logit[B:])
         loss_fm = loss_fm * 2
         total = loss_gen + loss_fm + loss_mel + loss_kl                            # + kl_ssl == 0 (frozen quantizer)
-        return total, dict(loss_gen=loss_gen, loss_fm=loss_fm, loss_mel=loss_mel, loss_kl=loss_kl)
+        parts = dict(loss_gen=loss_gen, loss_fm=loss_fm, loss_mel=loss_mel, loss_kl=loss_kl)
+        c_mr = float(self.t.get("c_mrstft", 0.0))
+        if c_mr > 0.0:          # opt-in extension (BASELINE config 5): the MR-STFT term of bs_roformer.py:565-581 on the fused STFT kernel
+            parts["loss_mrstft"] = ops.mrstft_loss(r["y_hat"].reshape(B, -1), r["y"].reshape(B, -1)) * c_mr
+            total = total + parts["loss_mrstft"]
+        return total, parts
 
     def _allreduce(self, opt):
         if self.world > 1:
@@ -438,6 +443,8 @@ def to_device_batch(host, device, bank, hop=640):
     lengths = host["lengths"].to(device, non_blocking=True).to(torch.int32)
     text_lengths = host["text_lengths"].to(device, non_blocking=True).to(torch.int32)
     B, _, L = wav.shape
-    spec, _ = ops.mel_frontend(wav.reshape(B, L), bank, hop, want_spec=True, want_mel=False)   # [B,T,1025], pitch 1028
+    # per-row sample counts (when the collate provides them): reflection at each utterance's own end (data_utils.py:119-128)
+    lens = host["wav_lengths"].to(device, non_blocking=True).to(torch.int32) if "wav_lengths" in host else None
+    spec, _ = ops.mel_frontend(wav.reshape(B, L), bank, hop, want_spec=True, want_mel=False, lens=lens)   # [B,T,1025], pitch 1028
     return dict(ssl=ops.to_channels_last(ssl), spec=spec, lengths=lengths, wav=wav.reshape(B, L, 1), text=text,
                 text_lengths=text_lengths)

@@ -114,16 +114,37 @@ int evk_weight_pack_bwd(const float* dpa, int32_t lda, const float* v, const flo
  * wav [B][L] (pitch ldw); outputs channels-last: spec [B*T][n_fft/2+1] (pitch ld_spec, nullable),
  * mel [B*T][n_mels] (pitch ld_mel, nullable), cplx [B*T][n_fft/2+1][2] (nullable, saved for bwd).
  * Filterbank is CSR by mel row: fb_ptr[n_mels+1], fb_idx[nnz], fb_val[nnz].
+ * lens (nullable, int32 [B]): per-row valid length; the reflection sits at each row's own end and frames past the row's
+ * own count are written as zeros / log(1e-5) (what the reference's per-utterance features + zero-padding collate give).
  * ------------------------------------------------------------------------------------------ */
-int evk_mel_fwd(const float* wav, int32_t B, int32_t L, int32_t ldw, int32_t hop, int32_t n_mels,
+int evk_mel_fwd(const float* wav, const int32_t* lens, int32_t B, int32_t L, int32_t ldw, int32_t hop, int32_t n_mels,
                 const int32_t* fb_ptr, const int32_t* fb_idx, const float* fb_val, float* spec, int32_t ld_spec,
                 float* mel, int32_t ld_mel, float* cplx, evk_stream_t stream);
-/* 1 (default): warp-per-frame register FFT; 0: the first CTA-per-frame shared-memory FFT (kept for A/B parity). */
+/* 1 (default): warp-per-frame register FFT; 0: the general block-per-frame kernel (evk_stft_fwd), kept for A/B parity. */
 int evk_set_mel_variant(int32_t v);
 /* gradient wrt wav of sum(dmel * mel): dwav [B][L] must be zero-initialised (overlap-add). */
-int evk_mel_bwd(const float* dmel, int32_t ld_dmel, const float* cplx, const float* mel, int32_t ld_mel, int32_t B,
-                int32_t L, int32_t ldw, int32_t hop, int32_t n_mels, const int32_t* fb_ptr, const int32_t* fb_idx,
+int evk_mel_bwd(const float* dmel, int32_t ld_dmel, const float* cplx, const float* mel, int32_t ld_mel, const int32_t* lens,
+                int32_t B, int32_t L, int32_t ldw, int32_t hop, int32_t n_mels, const int32_t* fb_ptr, const int32_t* fb_idx,
                 const float* fb_val, float* dwav, evk_stream_t stream);
+/* General STFT (stft.cu): n_fft in {256..4096} (power of two), any hop, power-of-two win <= n_fft (periodic Hann, centred in
+ * the frame as torch.stft does), reflect padding `pad` on both sides, T frames per row starting at f*hop - pad:
+ *   mel_processing.py:40-74  -> pad = (n_fft - hop) / 2, T = (L + 2 pad - n_fft) / hop + 1
+ *   torch.stft(center=True)  -> pad = n_fft / 2,         T = 1 + L / hop        (bs_roformer.py:565-581, the MR-STFT loss)
+ * Outputs (each nullable): cplx [B*T][n_fft/2+1][2]; spec [B*T][ld_spec] = sqrt(re^2+im^2+mag_eps); mel [B*T][ld_mel] =
+ * log(max(fb . spec, clip)), filterbank in CSR-by-mel form. */
+int evk_stft_fwd(const float* wav, const int32_t* lens, int32_t B, int32_t L, int32_t ldw, int32_t n_fft, int32_t hop, int32_t win,
+                 int32_t pad, int32_t T, float mag_eps, float* cplx, float* spec, int32_t ld_spec, int32_t n_mels,
+                 const int32_t* fb_ptr, const int32_t* fb_idx, const float* fb_val, float clip, float* mel, int32_t ld_mel,
+                 evk_stream_t stream);
+/* Adjoint: dwav [B][ldw] (zero-initialised by the caller) += d/dwav, from either gcplx [B*T][n_fft/2+1][2] (dL/dRe, dL/dIm) or,
+ * when gcplx is null, from dmel with the forward's saved cplx and mel. */
+int evk_stft_bwd(const float* gcplx, const float* dmel, int32_t ld_dmel, const float* cplx, const float* mel, int32_t ld_mel,
+                 float mag_eps, float clip, int32_t n_mels, const int32_t* fb_ptr, const int32_t* fb_idx, const float* fb_val,
+                 const int32_t* lens, int32_t B, int32_t L, int32_t ldw, int32_t n_fft, int32_t hop, int32_t win, int32_t pad,
+                 int32_t T, float* dwav, evk_stream_t stream);
+/* loss[0] += scale * sum_i |a_i - b_i| over n complex elements (F.l1_loss on complex tensors); grad (nullable, [n][2]) =
+ * scale * (a - b) / |a - b|. */
+int evk_cplx_l1(const float* a, const float* b, int64_t n, float scale, float* loss, float* grad, evk_stream_t stream);
 /* spec_to_mel_torch (mel_processing.py:77-90): spec [rows][F] -> log-mel [rows][n_mels] */
 int evk_spec_to_mel(const float* spec, int64_t rows, int32_t ld_spec, int32_t n_mels, const int32_t* fb_ptr,
                     const int32_t* fb_idx, const float* fb_val, float* mel, int32_t ld_mel, evk_stream_t stream);

@@ -278,7 +278,7 @@ def relpos_attention(P, pfx, x, c, attn_mask, n_heads, window):
             i0 = max(0, -r)
             idx = torch.arange(i0, i0 + n, device=p.device)
             contrib = p[:, :, idx, idx + r].unsqueeze(-1) * Ev[r + window]
-            out = out.index_add(2, idx, contrib)
+            out = out.index_add(2, idx, contrib.to(out.dtype))      # .to(): no-op in fp32; keeps the autocast comparator of bench.py running
     out = out.transpose(2, 3).contiguous().view(B, C, Tt)
     return conv1d(P, pfx + ".conv_o", out)
 

@@ -416,6 +416,71 @@ def check_mel():
     return out
 
 
+def check_stft():
+    """General STFT kernel + adjoint (stft.cu) vs torch.stft on the CPU: every (n_fft, hop, win) of the MR-STFT loss, the
+    per-row-length front end, the block-per-frame variant of the training configuration, and the MR-STFT loss with its gradient."""
+    from easevoice_trainer_b200 import ops, lib
+    from easevoice_trainer_b200 import mel_processing as mp
+    out = []
+    g = _gen(21)
+    y = torch.rand(3, 6000, generator=g) - 0.5
+    for n_fft, hop, win, center in ((2048, 147, 2048, True), (4096, 147, 4096, True), (2048, 147, 1024, True), (2048, 147, 512, True),
+                                    (2048, 147, 256, True), (1024, 256, 1024, True), (512, 128, 512, False), (256, 64, 256, True)):
+        yr = y.clone().requires_grad_(True)
+        ref = torch.view_as_real(torch.stft(yr, n_fft, hop_length=hop, win_length=win, window=torch.hann_window(win), center=center,
+                                            pad_mode="reflect", normalized=False, onesided=True, return_complex=True)).permute(0, 2, 1, 3)
+        gy = torch.randn(ref.shape, generator=g)
+        (ref * gy).sum().backward()
+        yd = y.to(DEV).requires_grad_(True)
+        o = ops.stft(yd, n_fft, hop, win, center=center)
+        (o * gy.to(DEV)).sum().backward()
+        tag = f"stft n_fft={n_fft} hop={hop} win={win} center={center}"
+        out.append((tag + " X", rel(o, ref), 2e-6))
+        out.append((tag + " d wav (adjoint)", rel(yd.grad, yr.grad), 5e-6))
+    # MR-STFT loss of bs_roformer.py:565-581 (complex L1 over five windows) and its gradient
+    yh = (torch.rand(2, 12000, generator=g) - 0.5)
+    yt = (torch.rand(2, 12000, generator=g) - 0.5)
+    yhr = yh.clone().requires_grad_(True)
+    tot = 0
+    for w in (4096, 2048, 1024, 512, 256):
+        kw = dict(n_fft=max(w, 2048), hop_length=147, win_length=w, window=torch.hann_window(w), return_complex=True, normalized=False)
+        tot = tot + F.l1_loss(torch.stft(yhr, **kw), torch.stft(yt, **kw))
+    tot.backward()
+    yhd = yh.to(DEV).requires_grad_(True)
+    lo = ops.mrstft_loss(yhd, yt.to(DEV))
+    lo.backward()
+    out.append(("mrstft loss", abs(float(lo) - float(tot)) / float(tot), 1e-5))
+    out.append(("mrstft d y_hat", rel(yhd.grad, yhr.grad), 2e-5))
+    # per-row lengths: |X| of a zero-padded batch == the reference's per-utterance spectrogram + zero-padding collate
+    L = 640 * 40
+    wav = torch.zeros(3, L)
+    lens = [L, 640 * 33 + 17, 640 * 21]
+    for b, n in enumerate(lens):
+        wav[b, :n] = torch.rand(n, generator=g) - 0.5
+    ref = torch.zeros(3, 1025, 40)
+    for b, n in enumerate(lens):
+        sp = mel_oracle.spectrogram(wav[b:b + 1, :n], 2048, 640, 2048)
+        ref[b, :, :sp.shape[2]] = sp[0]
+    ln = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    got = mp.spectrogram_torch(wav.to(DEV), 2048, 32000, 640, 2048, lengths=ln)
+    out.append(("spectrogram with per-row lengths (warp kernel)", rel(got, ref), 2e-5))
+    L_ = lib.init()
+    L_.evk_set_mel_variant(0)
+    try:
+        got0 = mp.spectrogram_torch(wav.to(DEV), 2048, 32000, 640, 2048, lengths=ln)
+        m0 = mp.mel_spectrogram_torch(wav.to(DEV), 2048, 128, 32000, 640, 2048, 0.0, None)
+    finally:
+        L_.evk_set_mel_variant(1)
+    m1 = mp.mel_spectrogram_torch(wav.to(DEV), 2048, 128, 32000, 640, 2048, 0.0, None)
+    out.append(("spectrogram with per-row lengths (general kernel)", rel(got0, ref), 2e-5))
+    out.append(("log-mel: general kernel vs warp kernel, max |d|", float((m0 - m1).abs().max()), 2e-4))
+    # a non-default transform size through the reference-named API (n_fft 1024 / win 512 / hop 160)
+    y2 = torch.rand(2, 8000, generator=g) - 0.5
+    ref2 = mel_oracle.spectrogram(y2, 1024, 160, 512)
+    out.append(("spectrogram_torch n_fft=1024 hop=160 win=512", rel(mp.spectrogram_torch(y2.to(DEV), 1024, 32000, 160, 512), ref2), 2e-5))
+    return out
+
+
 def _load_models(seed_g=1234, seed_d=4321):
     from easevoice_trainer_b200 import models
     net_g = models.SynthesizerTrn(1025, 32, n_speakers=300, **s2_oracle.S2_MODEL)
@@ -1224,7 +1289,7 @@ ALL = [check_conv, check_conv_transpose, check_elementwise, check_attention, che
        check_gpt_kernels, check_scaled_adam, lambda: check_gpt("small"), lambda: check_gpt("ragged"),
        check_gpt_dpo_and_trainer, check_gemm_tma, check_vocoder_cfg5,
        lambda: check_s2_full("cfg3"), lambda: check_s2_full("cfg3r"), lambda: check_gpt_full("cfg2"),
-       check_sovits_train_e2e]
+       check_sovits_train_e2e, check_stft]
 NAMES = ["conv", "conv_transpose", "elementwise", "attention", "vq_losses_optim", "mel", "s2_small", "s2_ragged", "api",
          "gpt_kernels", "scaled_adam", "gpt_small", "gpt_ragged", "gpt_dpo_trainer", "gemm_tma", "vocoder_cfg5",
-         "s2_cfg3", "s2_cfg3r", "gpt_cfg2", "sovits_train_e2e"]
+         "s2_cfg3", "s2_cfg3r", "gpt_cfg2", "sovits_train_e2e", "stft_mrstft"]
