@@ -41,6 +41,10 @@ struct GemmP {
   long long y_sb, r_sb;
   const int* out_len;
   int off[EVK_MAX_TAPS];
+  // staging geometry (host-chosen): SA / SB ring depths, a_stage = shared-memory pitch of an A stage (multiple of 1024),
+  // a_bytes = bytes the TMA loads of one A stage deliver (expect_tx), slab mode: off_min, span rows after the MT*128-row box
+  int SA, SB, a_stage, a_bytes, slab, off_min;
+  float comp;                                        // accumulator scale compensating the tensor core's operand TRUNCATION (see run_gemm)
 };
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -99,25 +103,38 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 struct MapB4 { CUtensorMap m[4]; };                  // B: mode 1 uses one map per delayed copy of X^T, mode 0 only m[0]
-                                                     // A: mode 0 uses one map per stride phase of the input, mode 1 only m[0]
-template <int BN, int STAGES>
+                                                     // A: mode 0 uses one map per stride phase of the input, mode 1 only m[0];
+                                                     //    slab mode: m[1] = the same tensor with a `span`-row box (the slab tail)
+constexpr int MAX_RING = 8;
+
+// One CTA per SM, persistent over the tile list.  Tile = (MT x 128) output rows x BN output channels.
+//   MT = 2 : two 128-row accumulators share every weight (B) tile -> half the L2->SM weight traffic per flop.
+//   slab   : stride-1 tap sums stage ONE input slab of MT*128 + span rows per channel block and run every tap from it
+//            (tap q = the A descriptor advanced by (off[q] - off_min) * P rows; the 128-byte swizzle is a function of the
+//            shared-memory ADDRESS, so any row offset is a valid descriptor start -- tools/exp/slab_desc.cu measured
+//            all 24 shifts exact with base_offset = 0).  The round-1 kernel re-fetched the A box for every tap from L2
+//            (21x operand re-read on the k = 11 layers, 25 % tensor-pipe, L2->SM bandwidth bound at 46.6 B/clk/SM).
+template <int BN, int MT>
 __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_constant__ MapB4 mapA4,
                                                                  const __grid_constant__ MapB4 mapB4,
                                                                  const __grid_constant__ GemmP p) {
   const CUtensorMap& mapA = mapA4.m[0];
   const CUtensorMap& mapB = mapB4.m[0];
-  constexpr int A_BYTES = BM * BK * 4, B_BYTES = BN * BK * 4, STAGE_BYTES = A_BYTES + B_BYTES;
-  constexpr int TCOLS = 2 * BN;
-  static_assert(TCOLS <= 512 && (TCOLS & (TCOLS - 1)) == 0, "TMEM columns");
+  constexpr int B_BYTES = BN * BK * 4;
+  constexpr int NACC = (2 * MT * BN <= 512) ? 2 : 1;
+  constexpr int TCOLS_RAW = NACC * MT * BN;
+  constexpr int TCOLS = TCOLS_RAW <= 32 ? 32 : TCOLS_RAW <= 64 ? 64 : TCOLS_RAW <= 128 ? 128 : TCOLS_RAW <= 256 ? 256 : 512;
+  static_assert(TCOLS_RAW <= 512, "TMEM columns");
   extern __shared__ uint8_t gsm_raw[];
   uint8_t* gsm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gsm_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2];
+  uint8_t* gsmB = gsm + (size_t)p.SA * p.a_stage;           // B ring behind the A ring (a_stage is a multiple of 1024)
+  __shared__ __align__(8) uint64_t fullA[MAX_RING], emptyA[MAX_RING], fullB[MAX_RING], emptyB[MAX_RING], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float epi_s[4 * 32 * 33];                          // per-epilogue-warp transpose tile
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < MAX_RING; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;\n");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&mapA4.m[0])));
@@ -142,33 +159,53 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
     else if (p.splits > 1) { k0 = outer * p.kb_per_split; k1 = min(kb_total, k0 + p.kb_per_split); }
     else { k0 = 0; k1 = p.Q * kb_total; }
   };
+  const int slab = p.slab;
 
   if (warp == 0) {
     if (lane == 0) {
-      int it = 0;
+      int itA = 0, itB = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int outer = tile / tiles_mn, mn = tile - outer * tiles_mn;
         const int tm = mn / p.tiles_n, tn = mn - tm * p.tiles_n;
         const int z = (p.splits > 1 || p.mode) ? 0 : outer;
         int k0, k1;
         k_range(outer, k0, k1);
-        for (int ki = k0; ki < k1; ++ki, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
-          mbar_expect_tx(&full[s], STAGE_BYTES);
-          uint8_t* sa = gsm + (size_t)s * STAGE_BYTES;
+        for (int ki = k0; ki < k1; ++ki) {
+          int q, kb;
+          if (slab) { kb = ki / p.Q; q = ki - kb * p.Q; }
+          else if (p.mode) { q = outer / p.splits; kb = ki; }
+          else { q = ki / kb_total; kb = ki - q * kb_total; }
+          if (!slab || q == 0) {                                 // a new A stage
+            const int s = itA % p.SA;
+            mbar_wait(&emptyA[s], ((itA / p.SA) & 1) ^ 1);
+            uint8_t* sa = gsm + (size_t)s * p.a_stage;
+            mbar_expect_tx(&fullA[s], (uint32_t)p.a_bytes);
+            if (p.mode) {
+              const int b = kb / p.kbs, kk = kb - b * p.kbs;
+              tma_load_3d(sa, &mapA, kk * BK, tm * BM, b, &fullA[s]);
+            } else if (slab) {
+              const int row0 = tm * (MT * BM) + p.off_min * p.P;
+              tma_load_3d(sa, &mapA, kb * BK, row0, z, &fullA[s]);
+              tma_load_3d(sa + MT * BM * BK * 4, &mapA4.m[1], kb * BK, row0 + MT * BM, z, &fullA[s]);
+            } else {
+              tma_load_3d(sa, &mapA4.m[p.src[q]], kb * BK, tm * (MT * BM) + p.off[q] * p.P, z, &fullA[s]);
+            }
+            ++itA;
+          }
+          const int s = itB % p.SB;
+          mbar_wait(&emptyB[s], ((itB / p.SB) & 1) ^ 1);
+          mbar_expect_tx(&fullB[s], B_BYTES);
+          uint8_t* sb = gsmB + (size_t)s * B_BYTES;
           if (p.mode) {
-            const int b = ki / p.kbs, kb = ki - b * p.kbs, q = outer / p.splits;
-            tma_load_3d(sa, &mapA, kb * BK, tm * BM, b, &full[s]);
+            const int b = kb / p.kbs, kk = kb - b * p.kbs;
             // TMA needs the inner coordinate 16-byte aligned: X[t + sh] is read from the copy delayed by r = (-sh) mod 4
             // (xt_r[u] = X[u - r]) at the aligned coordinate t + sh + r
             const int sh = p.off[q] * p.P, r = (((-sh) % 4) + 4) % 4;
-            tma_load_3d(sa + A_BYTES, &mapB4.m[r], kb * BK + (sh + r), tn * BN, b, &full[s]);
+            tma_load_3d(sb, &mapB4.m[r], kk * BK + (sh + r), tn * BN, b, &fullB[s]);
           } else {
-            const int q = ki / kb_total, kb = ki - q * kb_total;
-            tma_load_3d(sa, &mapA4.m[p.src[q]], kb * BK, tm * BM + p.off[q] * p.P, z, &full[s]);
-            tma_load_3d(sa + A_BYTES, &mapB, kb * BK, tn * BN, q, &full[s]);
+            tma_load_3d(sb, &mapB, kb * BK, tn * BN, q, &fullB[s]);
           }
+          ++itB;
         }
       }
     }
@@ -176,24 +213,41 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
     if (lane == 0) {
       // instruction descriptor: D = f32, A = B = tf32, both K-major, N = BN, M = 128
       constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      int it = 0, tcount = 0;
+      int itA = 0, itB = 0, tcount = 0, sA = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
-        int kb0, kb1;
-        k_range(tile / tiles_mn, kb0, kb1);
-        const int a = tcount & 1;
-        mbar_wait(&acc_empty[a], ((tcount >> 1) & 1) ^ 1);
+        const int outer = tile / tiles_mn;
+        int k0, k1;
+        k_range(outer, k0, k1);
+        const int a = tcount % NACC;
+        mbar_wait(&acc_empty[a], ((tcount / NACC) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;\n");
-        const uint32_t tacc = tmem_base + (uint32_t)(a * BN);
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&full[s], (it / STAGES) & 1);
+        const uint32_t tacc = tmem_base + (uint32_t)(a * MT * BN);
+        for (int ki = k0; ki < k1; ++ki) {
+          int q = 0;
+          if (slab) q = ki % p.Q;
+          const bool newA = !slab || q == 0;
+          if (newA) {
+            sA = itA % p.SA;
+            mbar_wait(&fullA[sA], (itA / p.SA) & 1);
+            ++itA;
+          }
+          const int sB = itB % p.SB;
+          mbar_wait(&fullB[sB], (itB / p.SB) & 1);
+          ++itB;
           asm volatile("tcgen05.fence::after_thread_sync;\n");
-          const uint32_t sa = smem_u32(gsm + (size_t)s * STAGE_BYTES);
-          const uint64_t da = sw128_desc(sa), db = sw128_desc(sa + A_BYTES);
+          uint32_t a_addr = smem_u32(gsm + (size_t)sA * p.a_stage);
+          if (slab) a_addr += (uint32_t)((p.off[q] - p.off_min) * p.P) * (BK * 4);
+          uint64_t da[MT];
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) da[mt] = sw128_desc(a_addr + (uint32_t)(mt * BM * BK * 4));
+          const uint64_t db = sw128_desc(smem_u32(gsmB + (size_t)sB * B_BYTES));
 #pragma unroll
           for (int k = 0; k < BK / 8; ++k)
-            umma_tf32(tacc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty[s]);
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt)
+              umma_tf32(tacc + (uint32_t)(mt * BN), da[mt] + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (ki > k0 || k > 0) ? 1u : 0u);
+          umma_commit(&emptyB[sB]);
+          if (!slab || q == p.Q - 1) umma_commit(&emptyA[sA]);
         }
         umma_commit(&acc_full[a]);
       }
@@ -208,21 +262,25 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
       float* dz = p.mode ? p.d + (size_t)(outer / p.splits) * p.d_sq : p.d + (size_t)z * p.y_sb;
       const float* rz = p.res ? p.res + (size_t)z * p.r_sb : nullptr;
       const int olen = p.out_len ? p.out_len[z] : 0x7fffffff;
-      const int a = tcount & 1;
-      mbar_wait(&acc_full[a], (tcount >> 1) & 1);
+      const int a = tcount % NACC;
+      mbar_wait(&acc_full[a], (tcount / NACC) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n");
       // TMEM gives each lane one ROW (32 consecutive columns); a direct store would touch 32 different rows per
       // instruction.  Transpose through a padded per-warp smem tile so that every store instruction writes four full
       // 128-byte row segments (and bias / residual loads are coalesced the same way).
       float* tr = epi_s + (warp - 2) * (32 * 33);
       const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
-      const int row_base = tm * BM + lq * 32;
+      const float comp = p.comp;
+#pragma unroll 1
+      for (int mt = 0; mt < MT; ++mt) {
+      const int row_base = tm * (MT * BM) + mt * BM + lq * 32;
+      if (row_base >= p.M) continue;                             // warp-uniform: nothing of this quadrant is inside the problem
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * BN + c0), v);
         const int n = tn * BN + c0;
-        if (n >= p.N) continue;                                  // warp-uniform
+        if (n >= p.N) break;                                     // warp-uniform
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * MT * BN + mt * BN + c0), v);
 #pragma unroll
         for (int e = 0; e < 32; ++e) tr[lane * 33 + e] = v[e];
         __syncwarp();
@@ -237,7 +295,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
         for (int i = 0; i < 8; ++i) {
           const int rl = i * 4 + r_sub, row = row_base + rl;
           if (row >= p.M || nn >= p.N) continue;
-          float t[4] = {tr[rl * 33 + c4], tr[rl * 33 + c4 + 1], tr[rl * 33 + c4 + 2], tr[rl * 33 + c4 + 3]};
+          float t[4] = {tr[rl * 33 + c4] * comp, tr[rl * 33 + c4 + 1] * comp, tr[rl * 33 + c4 + 2] * comp, tr[rl * 33 + c4 + 3] * comp};
           const int jo = p.o0 + (row / p.P) * p.os;
           const size_t orow = (size_t)jo * p.P + (row % p.P);
           float* dp = dz + orow * p.ldd + nn;
@@ -276,6 +334,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
           }
         }
         __syncwarp();
+      }
       }
       asm volatile("tcgen05.fence::before_thread_sync;\n");
       __syncwarp();
@@ -321,17 +380,45 @@ bool make_map(CUtensorMap* m, const float* base, long long outer, long long sb, 
 }
 
 int g_sm_count = 0;
+int g_opt_slab = 1, g_opt_mt2 = 1;          // A/B switches (evk_set_tma_options)
+// The tensor core reads fp32 operands as TF32 by DROPPING the low 13 mantissa bits (truncation towards zero): every product
+// is biased by -2^-11 * E[1/m] = -3.5e-4 relative per truncated operand (m = mantissa in [1,2), log-uniform).  Weights are
+// rounded to nearest once when they are packed, activations arrive raw through TMA.  The bias is systematic -- it adds up
+// along a 24-layer residual stream and shows in LayerNorm's 1/sigma (measured on the 24-layer GPT: gradient norms drift by
+// +1 % over 16 layers, d alpha off by 3x the noise bound) -- so the epilogue multiplies the accumulator by
+// (1 + 3.52e-4)^(number of raw operands).  The variance of the per-element error is the same as round-to-nearest's.
+float g_trunc_comp = 3.52e-4f;
 
 struct Operands {
   const float* A; int lda; long long a_sb, a_rows;     // activations: [Z][a_rows][K]
   const float* B; int ldb; long long b_sq;             // weights:     [Q][N][K]
   long long b_rs;                                      // mode 1: pitch between the four residue copies of X^T
   int a_phases; long long a_ps;                        // mode 0: stride phases of the input and their pitch
+  int raw_operands;                                    // how many of the two operands are un-rounded fp32 (truncated by the MMA)
 };
 
-template <int BN, int STAGES>
+constexpr int SMEM_BUDGET = 200 * 1024;
+
+template <int BN, int MT>
 int launch_gemm(const Operands& o, GemmP& p, int splits, cudaStream_t st) {
+  constexpr int B_BYTES = BN * BK * 4;
   MapB4 ma, mb;
+  p.slab = 0;
+  int span = 0;
+  if (!p.mode && g_opt_slab && o.a_phases == 1 && p.Q >= 2 && splits <= 1) {
+    int mn = p.off[0], mx = p.off[0];
+    for (int i = 1; i < p.Q; ++i) { mn = min(mn, p.off[i]); mx = max(mx, p.off[i]); }
+    span = (mx - mn) * p.P;
+    const long long a_stage = ((long long)(MT * BM + span + 7) / 8 * 8) * BK * 4;
+    if (span >= 1 && span <= 256 && (SMEM_BUDGET - 2 * a_stage) / B_BYTES >= 3) {
+      p.slab = 1; p.off_min = mn; p.SA = 2; p.a_stage = (int)a_stage; p.a_bytes = (MT * BM + span) * BK * 4;
+      { const long long nb = (SMEM_BUDGET - 2 * a_stage) / B_BYTES; p.SB = (int)(nb < MAX_RING ? nb : MAX_RING); }
+    }
+  }
+  if (!p.slab) {
+    p.a_stage = p.a_bytes = MT * BM * BK * 4;
+    p.SA = p.SB = min(MAX_RING, SMEM_BUDGET / (p.a_stage + B_BYTES));
+  }
   if (p.mode) {            // A = dY^T [Z][M = N_out][K = rows], B = residue copies of X^T [Z][N = C_in][in_rows - r]
     if (!make_map(&ma.m[0], o.A, p.Z, o.a_sb, p.M, p.K, o.lda, BM)) return 1;
     ma.m[1] = ma.m[2] = ma.m[3] = ma.m[0];
@@ -339,26 +426,23 @@ int launch_gemm(const Operands& o, GemmP& p, int splits, cudaStream_t st) {
       if (!make_map(&mb.m[r], o.B + r * o.b_rs, p.Z, o.b_sq, p.N, o.a_rows + r, o.ldb, BN)) return 1;
   } else {
     for (int ph = 0; ph < 4; ++ph) {
-      if (ph < o.a_phases) { if (!make_map(&ma.m[ph], o.A + ph * o.a_ps, p.Z, o.a_sb, o.a_rows, p.K, o.lda, BM)) return 1; }
+      if (ph < o.a_phases) { if (!make_map(&ma.m[ph], o.A + ph * o.a_ps, p.Z, o.a_sb, o.a_rows, p.K, o.lda, MT * BM)) return 1; }
       else ma.m[ph] = ma.m[0];
     }
+    if (p.slab && !make_map(&ma.m[1], o.A, p.Z, o.a_sb, o.a_rows, p.K, o.lda, span)) return 1;
     if (!make_map(&mb.m[0], o.B, p.Q, o.b_sq, p.N, p.K, o.ldb, BN)) return 1;
     mb.m[1] = mb.m[2] = mb.m[3] = mb.m[0];
   }
-  constexpr int STAGE_BYTES = (BM + BN) * BK * 4;
-  constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024;
-  auto kern = gemm_tma_kernel<BN, STAGES>;
+  const size_t SMEM = (size_t)p.SA * p.a_stage + (size_t)p.SB * B_BYTES + 1024;
+  auto kern = gemm_tma_kernel<BN, MT>;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM) != cudaSuccess) return 1;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 1024) != cudaSuccess) return 1;
     attr_set = true;
   }
-  if (!g_sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-  }
-  p.tiles_m = cdiv(p.M, BM);
+  p.comp = 1.f;
+  for (int i = 0; i < o.raw_operands; ++i) p.comp *= 1.f + g_trunc_comp;
+  p.tiles_m = cdiv(p.M, MT * BM);
   p.tiles_n = cdiv(p.N, BN);
   const int kb_total = p.mode ? p.Z * p.kbs : cdiv(p.K, BK);
   splits = max(1, min(splits, kb_total));
@@ -372,11 +456,30 @@ int launch_gemm(const Operands& o, GemmP& p, int splits, cudaStream_t st) {
   return check_launch("gemm_tma_kernel");
 }
 
+// MT = 2 halves the weight-tile traffic per flop but doubles the tile: take it when the wave quantisation of the persistent
+// grid does not eat the gain (cost in units of 128-row tile-times; 0.65 = measured relative cost of a row in a 256-row tile)
+template <int BN>
+int launch_bn(const Operands& o, GemmP& p, int splits, cudaStream_t st) {
+  if (!g_sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  bool mt2 = false;
+  if (g_opt_mt2 && !p.mode && splits <= 1 && p.M >= 2 * BM) {
+    const long long per = (long long)cdiv(p.N, BN) * p.Z;
+    const long long t1 = per * cdiv(p.M, BM), t2 = per * cdiv(p.M, 2 * BM);
+    const double c1 = (double)cdiv(t1, g_sm_count), c2 = (double)cdiv(t2, g_sm_count) * 2.0 * 0.65;
+    mt2 = c2 < c1;
+  }
+  return mt2 ? launch_gemm<BN, 2>(o, p, splits, st) : launch_gemm<BN, 1>(o, p, splits, st);
+}
+
 int run_gemm(const Operands& o, GemmP& p, int splits, cudaStream_t st) {
-  if (p.N > 128) return launch_gemm<256, 4>(o, p, splits, st);
-  if (p.N > 64) return launch_gemm<128, 6>(o, p, splits, st);
-  if (p.N > 32) return launch_gemm<64, 8>(o, p, splits, st);
-  return launch_gemm<32, 8>(o, p, splits, st);
+  if (p.N > 128) return launch_bn<256>(o, p, splits, st);
+  if (p.N > 64) return launch_bn<128>(o, p, splits, st);
+  if (p.N > 32) return launch_bn<64>(o, p, splits, st);
+  return launch_bn<32>(o, p, splits, st);
 }
 
 }  // namespace
@@ -405,6 +508,7 @@ int gemm_tma_run(const evk_gconv_desc* d, int phases, long long x_ps, const int*
   }
   Operands o{};
   o.B = d->w; o.ldb = d->ldw; o.b_sq = d->w_sq; o.a_phases = phases; o.a_ps = x_ps;
+  o.raw_operands = 1;                                       // A = activations (raw fp32), B = packed weights (already TF32, rounded to nearest)
   const bool flat = phases == 1 && d->Q == 1 && d->off[0] == 0 && d->P == 1 && !d->out_len && d->J == d->Tin && d->os == 1 && d->o0 == 0 &&
                     (d->Z == 1 || (d->x_sb == in_rows * d->ldx && d->y_sb == npos * d->ldy && (!d->res || d->r_sb == npos * d->ldr)));
   if (flat) {                                               // Linear / 1x1 conv: batch folds into the row dimension
@@ -427,6 +531,12 @@ int gemm_tma_try(const evk_gconv_desc* d, cudaStream_t st) { return gemm_tma_run
 using namespace evk;
 
 extern "C" int evk_set_backend_tma(int32_t on) { g_backend_tma = on ? 1 : 0; return EVK_OK; }
+// A/B switches of the TMA kernel (tests / bench): slab = one staged input slab per channel block shared by all taps,
+// mt2 = 256-row tiles, trunc_comp = relative accumulator compensation per raw (truncated) operand (0 disables it).
+extern "C" int evk_set_tma_options(int32_t slab, int32_t mt2, float trunc_comp) {
+  g_opt_slab = slab ? 1 : 0; g_opt_mt2 = mt2 ? 1 : 0; g_trunc_comp = trunc_comp;
+  return EVK_OK;
+}
 
 // Strided convolution forward on the TMA/tcgen05 kernel.  d describes the conv as a STRIDE-1 tap sum over `phases` (= the
 // conv stride, <= 4) phase copies of the input produced by evk_phase_split: d->x = copy 0, copies x_ps floats apart, each
@@ -451,7 +561,7 @@ extern "C" int evk_gemm_tf32(const float* A, int32_t lda, const float* B, int32_
   p.d = D; p.ldd = ldd; p.bias = bias; p.res = res; p.ldr = ldr; p.M = M; p.N = N; p.K = K; p.act = act; p.slope = slope;
   p.atomic = splits > 1 ? 1 : 0;
   p.Z = 1; p.Q = 1; p.P = 1;
-  Operands o{A, lda, 0, M, B, ldb, 0, 0, 1, 0};
+  Operands o{A, lda, 0, M, B, ldb, 0, 0, 1, 0, 2};
   p.os = 1; p.o0 = 0;
   int rc = run_gemm(o, p, splits, st);
   EVK_REQUIRE(rc != 1, EVK_ERR_UNSUPPORTED, "gemm_tf32: cuTensorMapEncodeTiled unavailable or rejected the operand");
@@ -478,7 +588,7 @@ extern "C" int evk_conv_wgrad_tma(const float* dyt, int32_t ld_dy, int64_t dy_sb
   p.d = dW; p.ldd = ldw; p.d_sq = w_sq; p.M = N; p.N = C; p.K = out_rows; p.atomic = 1; p.mode = 1;
   p.Z = B; p.Q = Q; p.P = P; p.kbs = cdiv(out_rows, BK); p.os = 1; p.o0 = 0;
   for (int i = 0; i < EVK_MAX_TAPS; ++i) p.off[i] = i < Q ? off[i] : 0;
-  Operands o{dyt, ld_dy, dy_sb, in_rows, xt, ld_x, x_sb, x_rs, 1, 0};
+  Operands o{dyt, ld_dy, dy_sb, in_rows, xt, ld_x, x_sb, x_rs, 1, 0, 2};     // both operands are raw activations / gradients
   int rc = run_gemm(o, p, splits < 1 ? 1 : splits, st);
   EVK_REQUIRE(rc != 1, EVK_ERR_UNSUPPORTED, "conv_wgrad_tma: cuTensorMapEncodeTiled unavailable or rejected the operand");
   if (rc == 0) g_disp_flops[4] += 2.0 * B * (double)out_rows * N * C * Q;

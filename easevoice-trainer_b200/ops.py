@@ -468,9 +468,18 @@ class _ConvFn(torch.autograd.Function):
 
 
 def conv(x, w: PackedW, bias=None, *, stride=1, pad=0, dil=1, P=1, groups=1, act=ACT_NONE, slope=0.0, res=None,
-         in_len=None, out_len=None):
-    """Conv1d (P == 1) / Conv2d with (k,1) kernels over a period-folded view (P == period)."""
+         in_len=None, out_len=None, precise=False):
+    """Conv1d (P == 1) / Conv2d with (k,1) kernels over a period-folded view (P == period).
+    precise=True: this launch uses 3xTF32 error-compensated products (fp32-class accuracy; forward-only call sites)."""
     cfg = (w.Q, stride, pad, dil, P, groups, act, slope, in_len, out_len)
+    if precise:
+        lib = _lib()
+        was = lib.evk_get_precise()
+        lib.evk_set_precise(1)           # read when the launch is enqueued (also at graph capture): a per-call switch
+        try:
+            return _ConvFn.apply(x, w.pa, w.pb, bias, res, cfg)
+        finally:
+            lib.evk_set_precise(was)
     return _ConvFn.apply(x, w.pa, w.pb, bias, res, cfg)
 
 
@@ -940,12 +949,22 @@ def reflect_pad_right(x, Tp):
     return x if Tp == x.shape[1] else _ReflectPadFn.apply(x, Tp)
 
 
+def widen_to_pitch(x):
+    """[B, T, C] view whose row pitch is wider than C (|X| from mel_frontend, to_channels_last(pad_to=4)) -> the [B, T, pitch]
+    view over the same memory.  The producers zero the pitch columns, so the wide view is a valid 16-byte tileable operand."""
+    if x.dim() != 3 or x.stride(2) != 1 or x.stride(1) == x.shape[2]:
+        return x
+    ld = x.stride(1)
+    assert ld > x.shape[2] and ld % 4 == 0 and x.stride(0) == x.shape[1] * ld
+    return torch.as_strided(x, (x.shape[0], x.shape[1], ld), x.stride(), x.storage_offset())
+
+
 def to_channels_last(x, pad_to=None):
     """[B, C, T] -> [B, T, C] (new memory; pitch rounded up to `pad_to` channels, returned as a view)."""
     x = x.contiguous()
     B, C, T = x.shape
     ld = C if pad_to is None else (C + pad_to - 1) // pad_to * pad_to
-    buf = torch.empty((B, T, ld), device=x.device, dtype=torch.float32)
+    buf = (torch.zeros if ld != C else torch.empty)((B, T, ld), device=x.device, dtype=torch.float32)   # pitch columns stay zero
     _call("evk_transpose_bct_btc", _p(x), _p(buf), B, C, T, ld, 1)
     return buf[:, :, :C] if ld != C else buf
 
@@ -1333,7 +1352,7 @@ class _MelFn(torch.autograd.Function):
         T = stft_frames(Lw, n_fft, hop, pad)
         need_grad = ctx.needs_input_grad[0]
         ld_spec = (bank.n_bins + 3) // 4 * 4          # 16-byte row pitch so |X| can feed the tensor-core GEMMs directly
-        spec = torch.empty((B, T, ld_spec), device=wav.device, dtype=torch.float32) if want_spec else None
+        spec = (torch.zeros if ld_spec != bank.n_bins else torch.empty)((B, T, ld_spec), device=wav.device, dtype=torch.float32) if want_spec else None
         mel = torch.empty((B, T, bank.n_mels), device=wav.device, dtype=torch.float32) if want_mel else None
         cplx = torch.empty((B, T, bank.n_bins, 2), device=wav.device, dtype=torch.float32) if need_grad else None
         if n_fft == 2048 and win == 2048 and pad == (2048 - hop) // 2:

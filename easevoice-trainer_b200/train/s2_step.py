@@ -362,7 +362,7 @@ class S2Step:
         static = {k: (v.clone() if k != "spec" else v) for k, v in batch.items()}
         # `spec` keeps its padded row pitch (a view of a wider buffer): clone the parent storage explicitly
         sp = batch["spec"]
-        wide = torch.empty((sp.shape[0], sp.shape[1], sp.stride(1)), device=sp.device, dtype=sp.dtype)
+        wide = torch.zeros((sp.shape[0], sp.shape[1], sp.stride(1)), device=sp.device, dtype=sp.dtype)   # pitch columns must stay zero (ops.widen_to_pitch)
         static["spec"] = wide[:, :, :sp.shape[2]]
         static["spec"].copy_(sp)
         inj = dict(noise=static.get("noise"), ids_slice=static.get("ids_slice"))

@@ -75,6 +75,10 @@ int evk_set_backend(int32_t tcgen05);
  *   2 ... on gconv_f_kernel (mma.sync)                          3 ... on the direct CUDA-core kernels
  *   4 weight gradients on gemm_tma_kernel                        5 ... on gconv_w_kernel (mma.sync)
  *   6 ... on the direct kernels                                  7 plain evk_gemm_tf32 calls */
+/* A/B switches of gemm_tma_kernel: slab (default 1) = stride-1 tap sums stage one input slab per channel block and run every
+ * tap from it; mt2 (default 1) = 256-row tiles where the persistent grid's wave quantisation allows; trunc_comp (default
+ * 3.52e-4) = accumulator compensation per raw fp32 operand for the tensor core's TF32 operand truncation (0 disables). */
+int evk_set_tma_options(int32_t slab, int32_t mt2, float trunc_comp);
 #define EVK_DISPATCH_SLOTS 8
 int evk_dispatch_stats(double* out, int32_t n);
 int evk_dispatch_stats_reset(void);
