@@ -161,51 +161,83 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
   };
   const int slab = p.slab;
 
+  // Both single-thread loops below run once per (tap, channel block) step and must stay well under the 128..256 cycles the
+  // MMAs of a step take: ring positions and the (tap, block) decomposition are carried incrementally -- no integer
+  // division or modulo by run-time values inside the step loops.
+  const int SA = p.SA, SB = p.SB, Q = p.Q;
   if (warp == 0) {
     if (lane == 0) {
-      int itA = 0, itB = 0;
+      int sA = 0, phA = 1, sB = 0, phB = 1;                      // empty barriers: the first pass over a ring passes immediately
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int outer = tile / tiles_mn, mn = tile - outer * tiles_mn;
         const int tm = mn / p.tiles_n, tn = mn - tm * p.tiles_n;
         const int z = (p.splits > 1 || p.mode) ? 0 : outer;
-        int k0, k1;
-        k_range(outer, k0, k1);
-        for (int ki = k0; ki < k1; ++ki) {
-          int q, kb;
-          if (slab) { kb = ki / p.Q; q = ki - kb * p.Q; }
-          else if (p.mode) { q = outer / p.splits; kb = ki; }
-          else { q = ki / kb_total; kb = ki - q * kb_total; }
-          if (!slab || q == 0) {                                 // a new A stage
-            const int s = itA % p.SA;
-            mbar_wait(&emptyA[s], ((itA / p.SA) & 1) ^ 1);
-            uint8_t* sa = gsm + (size_t)s * p.a_stage;
-            mbar_expect_tx(&fullA[s], (uint32_t)p.a_bytes);
-            if (p.mode) {
-              const int b = kb / p.kbs, kk = kb - b * p.kbs;
-              tma_load_3d(sa, &mapA, kk * BK, tm * BM, b, &fullA[s]);
-            } else if (slab) {
-              const int row0 = tm * (MT * BM) + p.off_min * p.P;
-              tma_load_3d(sa, &mapA, kb * BK, row0, z, &fullA[s]);
-              tma_load_3d(sa + MT * BM * BK * 4, &mapA4.m[1], kb * BK, row0 + MT * BM, z, &fullA[s]);
-            } else {
-              tma_load_3d(sa, &mapA4.m[p.src[q]], kb * BK, tm * (MT * BM) + p.off[q] * p.P, z, &fullA[s]);
+        auto next_a = [&]() -> uint8_t* {
+          mbar_wait(&emptyA[sA], phA);
+          mbar_expect_tx(&fullA[sA], (uint32_t)p.a_bytes);
+          return gsm + (size_t)sA * p.a_stage;
+        };
+        auto done_a = [&]() { if (++sA == SA) { sA = 0; phA ^= 1; } };
+        auto next_b = [&]() -> uint8_t* {
+          mbar_wait(&emptyB[sB], phB);
+          mbar_expect_tx(&fullB[sB], B_BYTES);
+          return gsmB + (size_t)sB * B_BYTES;
+        };
+        auto done_b = [&]() { if (++sB == SB) { sB = 0; phB ^= 1; } };
+        if (slab) {
+          const int row0 = tm * (MT * BM) + p.off_min * p.P;
+          for (int kb = 0; kb < kb_total; ++kb) {
+            uint8_t* sa = next_a();
+            tma_load_3d(sa, &mapA, kb * BK, row0, z, &fullA[sA]);
+            tma_load_3d(sa + MT * BM * BK * 4, &mapA4.m[1], kb * BK, row0 + MT * BM, z, &fullA[sA]);
+            done_a();
+            for (int q = 0; q < Q; ++q) {
+              uint8_t* sb = next_b();
+              tma_load_3d(sb, &mapB, kb * BK, tn * BN, q, &fullB[sB]);
+              done_b();
             }
-            ++itA;
           }
-          const int s = itB % p.SB;
-          mbar_wait(&emptyB[s], ((itB / p.SB) & 1) ^ 1);
-          mbar_expect_tx(&fullB[s], B_BYTES);
-          uint8_t* sb = gsmB + (size_t)s * B_BYTES;
+        } else if (!p.mode && p.splits == 1) {
+          for (int q = 0; q < Q; ++q) {
+            const CUtensorMap* am = &mapA4.m[p.src[q]];
+            const int arow = tm * (MT * BM) + p.off[q] * p.P;
+            for (int kb = 0; kb < kb_total; ++kb) {
+              uint8_t* sa = next_a();
+              tma_load_3d(sa, am, kb * BK, arow, z, &fullA[sA]);
+              done_a();
+              uint8_t* sb = next_b();
+              tma_load_3d(sb, &mapB, kb * BK, tn * BN, q, &fullB[sB]);
+              done_b();
+            }
+          }
+        } else {
+          int k0, k1;
+          k_range(outer, k0, k1);
           if (p.mode) {
-            const int b = kb / p.kbs, kk = kb - b * p.kbs;
+            const int q = outer / p.splits;
             // TMA needs the inner coordinate 16-byte aligned: X[t + sh] is read from the copy delayed by r = (-sh) mod 4
             // (xt_r[u] = X[u - r]) at the aligned coordinate t + sh + r
             const int sh = p.off[q] * p.P, r = (((-sh) % 4) + 4) % 4;
-            tma_load_3d(sb, &mapB4.m[r], kk * BK + (sh + r), tn * BN, b, &fullB[s]);
-          } else {
-            tma_load_3d(sb, &mapB, kb * BK, tn * BN, q, &fullB[s]);
+            int b = k0 / p.kbs, kk = k0 - b * p.kbs;
+            for (int ki = k0; ki < k1; ++ki) {
+              uint8_t* sa = next_a();
+              tma_load_3d(sa, &mapA, kk * BK, tm * BM, b, &fullA[sA]);
+              done_a();
+              uint8_t* sb = next_b();
+              tma_load_3d(sb, &mapB4.m[r], kk * BK + (sh + r), tn * BN, b, &fullB[sB]);
+              done_b();
+              if (++kk == p.kbs) { kk = 0; ++b; }
+            }
+          } else {                                               // split-K plain GEMM (Z == Q == 1)
+            for (int kb = k0; kb < k1; ++kb) {
+              uint8_t* sa = next_a();
+              tma_load_3d(sa, &mapA, kb * BK, tm * (MT * BM), 0, &fullA[sA]);
+              done_a();
+              uint8_t* sb = next_b();
+              tma_load_3d(sb, &mapB, kb * BK, tn * BN, 0, &fullB[sB]);
+              done_b();
+            }
           }
-          ++itB;
         }
       }
     }
@@ -213,41 +245,46 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
     if (lane == 0) {
       // instruction descriptor: D = f32, A = B = tf32, both K-major, N = BN, M = 128
       constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      int itA = 0, itB = 0, tcount = 0, sA = 0;
+      int sA = 0, phA = 0, sB = 0, phB = 0, tcount = 0;
+      const uint32_t a_ring = smem_u32(gsm), b_ring = smem_u32(gsmB);
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
-        const int outer = tile / tiles_mn;
-        int k0, k1;
-        k_range(outer, k0, k1);
         const int a = tcount % NACC;
         mbar_wait(&acc_empty[a], ((tcount / NACC) & 1) ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;\n");
         const uint32_t tacc = tmem_base + (uint32_t)(a * MT * BN);
-        for (int ki = k0; ki < k1; ++ki) {
-          int q = 0;
-          if (slab) q = ki % p.Q;
-          const bool newA = !slab || q == 0;
-          if (newA) {
-            sA = itA % p.SA;
-            mbar_wait(&fullA[sA], (itA / p.SA) & 1);
-            ++itA;
-          }
-          const int sB = itB % p.SB;
-          mbar_wait(&fullB[sB], (itB / p.SB) & 1);
-          ++itB;
+        uint32_t accum = 0;
+        // one step: MT x 4 MMAs of (128 x BN x 8) from A rows starting `a_off` bytes into the current A stage
+        auto step = [&](uint32_t a_off) {
+          mbar_wait(&fullB[sB], phB);
           asm volatile("tcgen05.fence::after_thread_sync;\n");
-          uint32_t a_addr = smem_u32(gsm + (size_t)sA * p.a_stage);
-          if (slab) a_addr += (uint32_t)((p.off[q] - p.off_min) * p.P) * (BK * 4);
-          uint64_t da[MT];
+          const uint32_t a_addr = a_ring + (uint32_t)sA * (uint32_t)p.a_stage + a_off;
+          const uint64_t db = sw128_desc(b_ring + (uint32_t)sB * B_BYTES);
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) da[mt] = sw128_desc(a_addr + (uint32_t)(mt * BM * BK * 4));
-          const uint64_t db = sw128_desc(smem_u32(gsmB + (size_t)sB * B_BYTES));
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint64_t da = sw128_desc(a_addr + (uint32_t)(mt * BM * BK * 4));
 #pragma unroll
-          for (int k = 0; k < BK / 8; ++k)
-#pragma unroll
-            for (int mt = 0; mt < MT; ++mt)
-              umma_tf32(tacc + (uint32_t)(mt * BN), da[mt] + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, (ki > k0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / 8; ++k) umma_tf32(tacc + (uint32_t)(mt * BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, accum | (uint32_t)k);
+          }
+          accum = 1;
           umma_commit(&emptyB[sB]);
-          if (!slab || q == p.Q - 1) umma_commit(&emptyA[sA]);
+          if (++sB == SB) { sB = 0; phB ^= 1; }
+        };
+        auto wait_a = [&]() { mbar_wait(&fullA[sA], phA); };
+        auto free_a = [&]() { umma_commit(&emptyA[sA]); if (++sA == SA) { sA = 0; phA ^= 1; } };
+        if (slab) {
+          for (int kb = 0; kb < kb_total; ++kb) {
+            wait_a();
+            for (int q = 0; q < Q; ++q) step((uint32_t)((p.off[q] - p.off_min) * p.P) * (BK * 4));
+            free_a();
+          }
+        } else {
+          int k0, k1;
+          k_range(tile / tiles_mn, k0, k1);
+          for (int ki = k0; ki < k1; ++ki) {
+            wait_a();
+            step(0);
+            free_a();
+          }
         }
         umma_commit(&acc_full[a]);
       }
@@ -466,7 +503,7 @@ int launch_bn(const Operands& o, GemmP& p, int splits, cudaStream_t st) {
     cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
   }
   bool mt2 = false;
-  if (g_opt_mt2 && !p.mode && splits <= 1 && p.M >= 2 * BM) {
+  if (g_opt_mt2 && BN <= 128 && !p.mode && splits <= 1 && p.M >= 2 * BM) {      // BN = 256 would lose the second accumulator (epilogue overlap): measured slower
     const long long per = (long long)cdiv(p.N, BN) * p.Z;
     const long long t1 = per * cdiv(p.M, BM), t2 = per * cdiv(p.M, 2 * BM);
     const double c1 = (double)cdiv(t1, g_sm_count), c2 = (double)cdiv(t2, g_sm_count) * 2.0 * 0.65;

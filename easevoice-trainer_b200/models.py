@@ -10,6 +10,7 @@ from the library's Philox streams (no host sync, CUDA-graph safe).  Dropout foll
 reference (p_dropout for enc_p, 0.1 inside MelStyleEncoder).
 """
 import math
+import os
 
 import torch
 from torch import nn
@@ -56,12 +57,42 @@ class ParamTree(nn.Module):
 
     # ---- packed-weight helpers (weight-norm folded into the packing pass) --------------------
     _frozen = False            # True: weights enter the graph as constants (no weight gradients are computed)
+    batch_packing = os.environ.get("EVK_BATCH_PACK", "1") != "0"     # one weight_pack launch per network and step (ops.PackPlan), not one per layer
+
+    def begin_pack(self):
+        """Call at the start of a forward pass.  The first pass of each kind (frozen or not) packs layer by layer and records
+        what it packs; later passes run the recorded plan in one launch and hand out views of its arenas."""
+        self._active, self._recording = None, None
+        if not self.batch_packing or not torch.is_grad_enabled() and not self._frozen:
+            return
+        plans = self.__dict__.setdefault("_plans", {})
+        plan = plans.get(self._frozen)
+        if plan is not None and not plan.valid():
+            plan = plans.pop(self._frozen, None) and None
+        if plan is None:
+            self._recording = []
+            return
+        packed = ops.pack_all(plan)
+        self._active = {req[0]: pw for req, pw in zip(plan.reqs, packed)}
+
+    def end_pack(self):
+        rec, self._recording, self._active = getattr(self, "_recording", None), None, None
+        if rec:
+            self.__dict__.setdefault("_plans", {})[self._frozen] = ops.PackPlan(rec, with_grad=not self._frozen)
 
     def w(self, pfx, need_pb=True, pad0=0, pad1=0):
+        key = (pfx, need_pb, pad0, pad1)
+        act = getattr(self, "_active", None)
+        if act is not None and key in act:
+            return act[key]
         fz = (lambda t: t.detach()) if self._frozen else (lambda t: t)
-        if self.has(pfx + ".weight_v"):
-            return ops.pack_weight(fz(self.P(pfx + ".weight_v")), fz(self.P(pfx + ".weight_g")), need_pb, pad0, pad1)
-        return ops.pack_weight(fz(self.P(pfx + ".weight")), None, need_pb, pad0, pad1)
+        has_g = self.has(pfx + ".weight_v")
+        v = self.P(pfx + (".weight_v" if has_g else ".weight"))
+        g = self.P(pfx + ".weight_g") if has_g else None
+        rec = getattr(self, "_recording", None)
+        if rec is not None and all(r[0] != key for r in rec):
+            rec.append((key, v, g, need_pb, pad0, pad1, torch.is_grad_enabled() and not self._frozen))
+        return ops.pack_weight(fz(v), fz(g) if g is not None else None, need_pb, pad0, pad1)
 
     def b(self, pfx, pad=0):
         if not self.has(pfx + ".bias"):
@@ -369,15 +400,22 @@ class SynthesizerTrn(ParamTree):
     def forward_cl(self, ssl, spec, lengths, text, text_lengths, noise=None, ids_slice=None):
         """Channels-last forward.  ssl [B,T,768], spec [B,T,1025] (pitch may be padded), lengths/text_lengths int32 [B],
         text int64 [B,X].  Returns a dict of channels-last tensors (same quantities as SynthesizerTrn.forward)."""
+        self.begin_pack()
+        try:
+            return self._forward_cl(ssl, spec, lengths, text, text_lengths, noise, ids_slice)
+        finally:
+            self.end_pack()
+
+    def _forward_cl(self, ssl, spec, lengths, text, text_lengths, noise, ids_slice):
         B, T, _ = spec.shape
         assert T % 2 == 0, "frame count must be even (TextAudioSpeakerCollate pads to 2*(Tmax//2+1))"
         I = self.inter_channels
         seg = self.segment_size
         ge = self._ref_enc(spec, lengths)                                        # [B, 1, 512]
         with torch.no_grad():                                                    # frozen quantizer (models.py:911-921)
-            # 3xTF32 products: a TF32-rounded projection flips the argmin of near-tie codewords (measured: 2 of 1 384
-            # codes at the benchmarked shapes); the layer is 1 % of the forward flops
-            s = ops.conv(ssl, self.w("ssl_proj", need_pb=False), self.b("ssl_proj"), stride=2, precise=True)
+            # exact fp32 products: a TF32-rounded (even a 3xTF32) projection flips the argmin of near-tie codewords
+            # (measured at the benchmarked shapes: 2, resp. 1, of 1 384 codes); the layer is 1 % of the forward flops
+            s = ops.conv_k2s2_fp32(ssl, self.P("ssl_proj.weight"), self.P("ssl_proj.bias"))
             embed = self.P("quantizer.vq.layers.0._codebook.embed")
             codes = ops.vq_nearest(s, embed)                                     # [B, T/2] int64
             quantized = ops.embedding(embed, codes, rep=2)                       # nearest x2 (models.py:924-927)
@@ -511,12 +549,14 @@ class MultiPeriodDiscriminator(ParamTree):
         weights_need_grad=False (generator step): D weights are constants, so no D weight gradients are computed --
         the reference computes and then discards them (sovits.py:503,511-520)."""
         self._frozen = not weights_need_grad
+        self.begin_pack()
         try:
             x = ops.cat_batch(y, y_hat)
             outs = [self._disc_s(ops.pad_channels(x, 4))]
             for d, period in enumerate(PERIODS, start=1):
                 outs.append(self._disc_p(d, x, period))
         finally:
+            self.end_pack()
             self._frozen = False
         return outs
 

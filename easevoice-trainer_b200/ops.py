@@ -261,6 +261,134 @@ def pack_weight(v, g=None, need_pb=True, pad0=0, pad1=0):
     return PackedW(pa, pb if need_pb else None, D0, D1, v.numel() // (v.shape[0] * v.shape[1]))
 
 
+# ---- whole-network packing: one launch per network per step (pack_batched.cu) ------------------------------------
+class PackJobC(ctypes.Structure):
+    _fields_ = ([(n, ctypes.c_void_p) for n in ("v", "g", "pa", "pb", "dpa", "dv", "dg")]
+                + [(n, ctypes.c_int32) for n in ("D0", "D1", "Q", "lda", "D0p", "ldb", "D1p", "row0")])
+
+
+_dpa_views = {}          # data_ptr of a packed weight -> its slice of the plan's (pre-zeroed) packed-gradient arena
+
+
+def dpa_buffer(pa):
+    """where a weight-gradient kernel accumulates d(pa): the plan's arena slice when pa comes from a PackPlan (zeroed once
+    per step by the plan), else a fresh zero tensor"""
+    v = _dpa_views.get(pa.data_ptr())
+    if v is not None and v.shape == pa.shape:
+        return v
+    return torch.zeros_like(pa)
+
+
+class PackPlan:
+    """Static layout of every packed weight of one network.  reqs: [(key, v, g or None, need_pb, pad0, pad1, wants_grad)].
+    All arenas are allocated once; the job table holds raw device pointers (parameters must already live where they will
+    stay -- FlatAdamW's arena)."""
+
+    def __init__(self, reqs, with_grad):
+        dev = reqs[0][1].device
+        self.reqs, self.with_grad = reqs, with_grad
+        al = lambda n: (n + 63) // 64 * 64                         # 256-byte aligned regions (TMA bases need 16)
+        geo, off_pa, off_pb, off_g = [], 0, 0, 0
+        for key, v, g, need_pb, pad0, pad1, wants in reqs:
+            D0, D1 = v.shape[0], v.shape[1]
+            Q = v.numel() // (D0 * D1)
+            D0p, D1p = max(D0, pad0), max(D1, pad1)
+            lda, ldb = _pad4(D1p), _pad4(D0p)
+            geo.append((D0, D1, Q, D0p, D1p, lda, ldb, off_pa, off_pb if need_pb else -1, off_g))
+            off_pa += al(Q * D0p * lda)
+            if need_pb:
+                off_pb += al(Q * D1p * ldb)
+            off_g += al(v.numel()) + (al(g.numel()) if g is not None else 0)
+        self.arena_pa = torch.zeros(off_pa, device=dev, dtype=torch.float32)
+        self.arena_pb = torch.zeros(max(off_pb, 1), device=dev, dtype=torch.float32)
+        self.arena_dpa = torch.zeros(off_pa, device=dev, dtype=torch.float32) if with_grad else None
+        self.arena_dvg = torch.zeros(off_g, device=dev, dtype=torch.float32) if with_grad else None
+        jobs = (PackJobC * len(reqs))()
+        rows, rows_bwd, row0 = [], [], 0
+        self.pa, self.pb, self.dpa, self.grads, self.params, self.sig = [], [], [], [], [], []
+        for i, ((key, v, g, need_pb, pad0, pad1, wants), (D0, D1, Q, D0p, D1p, lda, ldb, opa, opb, og)) in enumerate(zip(reqs, geo)):
+            pa = self.arena_pa[opa:opa + Q * D0p * lda].view(Q, D0p, lda)
+            pb = self.arena_pb[opb:opb + Q * D1p * ldb].view(Q, D1p, ldb) if need_pb else None
+            j = jobs[i]
+            j.v, j.g, j.pa, j.pb = v.data_ptr(), (g.data_ptr() if g is not None else None), pa.data_ptr(), (pb.data_ptr() if pb is not None else None)
+            j.D0, j.D1, j.Q, j.lda, j.D0p, j.ldb, j.D1p, j.row0 = D0, D1, Q, lda, D0p, ldb, D1p, row0
+            self.pa.append(pa); self.pb.append(pb)
+            if with_grad:
+                dpa = self.arena_dpa[opa:opa + Q * D0p * lda].view(Q, D0p, lda)
+                dv = self.arena_dvg[og:og + v.numel()].view(v.shape)
+                dg = self.arena_dvg[og + al(v.numel()):og + al(v.numel()) + g.numel()].view(g.shape) if g is not None else None
+                j.dpa, j.dv, j.dg = dpa.data_ptr(), dv.data_ptr(), (dg.data_ptr() if dg is not None else None)
+                self.dpa.append(dpa)
+                _dpa_views[pa.data_ptr()] = dpa
+                self.params.append(v); self.grads.append(dv if wants else None)
+                if g is not None:
+                    self.params.append(g); self.grads.append(dg if wants else None)
+                if wants:
+                    rows_bwd.extend([i] * D0)
+            rows.extend([i] * D0)
+            row0 += D0
+            self.sig.append((v.data_ptr(), g.data_ptr() if g is not None else 0))
+        self.jobs = torch.frombuffer(bytearray(bytes(jobs)), dtype=torch.uint8).to(dev)
+        self.rows = torch.tensor(rows, dtype=torch.int32, device=dev)
+        # the backward table re-bases row0 per job: build a second job table whose row0 counts only the rows that run
+        if with_grad:
+            jb = (PackJobC * len(reqs))()
+            ctypes.memmove(jb, jobs, ctypes.sizeof(jobs))
+            r0 = 0
+            for i, (req, ge) in enumerate(zip(reqs, geo)):
+                jb[i].row0 = r0
+                if req[6]:
+                    r0 += ge[0]
+            self.jobs_bwd = torch.frombuffer(bytearray(bytes(jb)), dtype=torch.uint8).to(dev)
+            self.rows_bwd = torch.tensor(rows_bwd, dtype=torch.int32, device=dev)
+        self.index = {req[0]: i for i, req in enumerate(reqs)}
+
+    def valid(self):
+        """parameters still live where the job table points (they move when an optimizer re-homes them into its arena)"""
+        return all((r[1].data_ptr(), r[2].data_ptr() if r[2] is not None else 0) == sg for r, sg in zip(self.reqs, self.sig))
+
+    def run_pack(self):
+        _call("evk_weight_pack_batched", _p(self.jobs), _p(self.rows), self.rows.numel())
+
+    def run_pack_bwd(self):
+        if self.rows_bwd.numel():
+            _call("evk_weight_pack_bwd_batched", _p(self.jobs_bwd), _p(self.rows_bwd), self.rows_bwd.numel())
+
+    def packed(self, i, pa=None):
+        r = self.reqs[i]
+        v = r[1]
+        D0, D1 = max(v.shape[0], r[4]), max(v.shape[1], r[5])
+        return PackedW(self.pa[i] if pa is None else pa, self.pb[i], D0, D1, v.numel() // (v.shape[0] * v.shape[1]))
+
+
+class _PackAllFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, plan, *params):
+        plan.arena_dpa.zero_()                     # the step's weight-gradient kernels accumulate into it
+        plan.run_pack()
+        ctx.plan = plan
+        return tuple(plan.pa)
+
+    @staticmethod
+    def backward(ctx, *dpas):
+        plan = ctx.plan
+        for d, mine in zip(dpas, plan.dpa):
+            if d is not None and d.data_ptr() != mine.data_ptr():
+                mine.copy_(d)                      # gradient arrived in a foreign buffer (e.g. accumulated over two uses)
+        plan.run_pack_bwd()
+        return (None, *plan.grads)
+
+
+def pack_all(plan):
+    """-> list of PackedW for every request of the plan (differentiable wrt the parameters when plan.with_grad)."""
+    if plan.with_grad:
+        pas = _PackAllFn.apply(plan, *plan.params)
+        return [plan.packed(i, pas[i]) for i in range(len(plan.reqs))]
+    with torch.no_grad():
+        plan.run_pack()
+    return [plan.packed(i) for i in range(len(plan.reqs))]
+
+
 # ------------------------------------------------------------------------------------------------
 # convolution family
 # ------------------------------------------------------------------------------------------------
@@ -404,7 +532,7 @@ class _ConvFn(torch.autograd.Function):
                 _call("evk_rowmask", _p(dx), C, _p(dxm), C, B, Tin * P, C, _p(in_len))
                 dx = dxm
         if ctx.needs_input_grad[1]:
-            dpa = torch.zeros_like(pa)
+            dpa = dpa_buffer(pa)
             _, _, ldx = _rows(x)
             mma = _aligned(x, ldx) and _aligned(dy, N) and (G == 1 or (Cg % 4 == 0 and Ng % 4 == 0))
             rows = B * Tin
@@ -524,7 +652,7 @@ class _ConvTFn(torch.autograd.Function):
             _fwd_like(dy, Tout, pa, 0, 1, Q, lda, Cin * lda, Cout, Cin, dx, J=Tin, P=1, is_=stride, os_=1, o0=0,
                       Tout=Tin, off=off)
         if ctx.needs_input_grad[1]:
-            dpa = torch.zeros_like(pa)
+            dpa = dpa_buffer(pa)
             _, _, ldx = _rows(x)
             # dPA[q][ci][co] += sum_t X[t][ci] * dY[t*stride - pad + q][co]: "x" role = dY (shifted), "y" role = X
             d = _desc(x=dy, w=dpa, y=x, res=None, bias=None, in_len=None, out_len=None,
@@ -1235,6 +1363,26 @@ def attention(q, k, v, *, heads, scale, Ek=None, Ev=None, window=None, fill=-1e4
 # ------------------------------------------------------------------------------------------------
 # VQ, losses, mel
 # ------------------------------------------------------------------------------------------------
+def conv_k2s2_fp32(x, weight, bias):
+    """Conv1d(kernel 2, stride 2) in exact fp32 FMA arithmetic (no tensor cores): the frozen quantizer's input projection
+    (models.py:911-921).  Token indices must not depend on operand rounding -- at the benchmarked shapes the closest
+    runner-up codeword is 5e-6 (relative) away, inside TF32 and even 3xTF32 error.  In channels-last memory two
+    consecutive frames ARE one row of 2C values, so the conv is a plain [rows, 2C] x [N, 2C]^T product.  No gradient."""
+    x = x.detach().contiguous()
+    B, T, C = x.shape
+    assert T % 2 == 0
+    N = weight.shape[0]
+    w2 = weight.detach().permute(0, 2, 1).reshape(N, 2 * C).contiguous()             # [n][tap][c]
+    y = torch.empty((B, T // 2, N), device=x.device, dtype=torch.float32)
+    _call("evk_sgemm_nt_f32", _p(x), 2 * C, _p(w2), 2 * C, _p(y), N, B * (T // 2), N, 2 * C)
+    if bias is not None:
+        vb = bias.detach().reshape(1, N).expand(B, N).contiguous()
+        out = torch.empty_like(y)
+        _call("evk_add_bvec", _p(y), N, _p(vb), N, _p(out), N, B, T // 2, N)
+        y = out
+    return y
+
+
 def vq_nearest(x, embed):
     """x [B, T, D] channels-last, embed [K, D] -> codes int64 [B, T] (no gradient: frozen quantizer)."""
     x = _cl(x.detach())

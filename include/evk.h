@@ -109,6 +109,11 @@ int evk_weight_pack_p(const float* v, const float* g, int32_t D0, int32_t D1, in
 int evk_weight_pack_bwd_p(const float* dpa, int32_t lda, int32_t D0p, const float* v, const float* g, int32_t D0,
                           int32_t D1, int32_t Q, float* dv, float* dg, evk_stream_t stream);
 /* given dPA (gradient in PA layout) -> dv [D0][D1][Q] (written), dg [D0] (written) (g may be NULL) */
+/* Whole-network variants (pack_batched.cu): ONE launch packs / back-propagates every weight of a network.  `jobs` is a
+ * device array of 88-byte records {v, g, pa, pb, dpa, dv, dg (pointers); D0, D1, Q, lda, D0p, ldb, D1p, row0 (int32)},
+ * job_of_row [nrows] maps each (job, output-channel) row to its job.  All pointers are static arenas owned by the caller. */
+int evk_weight_pack_batched(const void* jobs, const int32_t* job_of_row, int32_t nrows, evk_stream_t stream);
+int evk_weight_pack_bwd_batched(const void* jobs, const int32_t* job_of_row, int32_t nrows, evk_stream_t stream);
 int evk_weight_pack_bwd(const float* dpa, int32_t lda, const float* v, const float* g, int32_t D0, int32_t D1,
                         int32_t Q, float* dv, float* dg, evk_stream_t stream);
 
