@@ -367,7 +367,9 @@ class _PackAllFn(torch.autograd.Function):
         plan.arena_dpa.zero_()                     # the step's weight-gradient kernels accumulate into it
         plan.run_pack()
         ctx.plan = plan
-        return tuple(plan.pa)
+        # FRESH tensor objects every call: returning the stored views again would hand autograd tensors that still carry
+        # the previous step's history (it would chain the old graph -- recorded on another stream -- into the new one)
+        return tuple(t.view(t.shape) for t in plan.pa)
 
     @staticmethod
     def backward(ctx, *dpas):
