@@ -23,7 +23,7 @@ namespace evk {
 namespace {
 
 constexpr int BM = 128, BK = 32;                    // 32 floats = one 128-byte swizzle row
-constexpr int GT_THREADS = 192;
+constexpr int GT_THREADS = 320;                     // TMA producer warp, MMA warp, eight epilogue warps
 
 struct GemmP {
   float* d; int ldd;
@@ -130,12 +130,12 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
   uint8_t* gsmB = gsm + (size_t)p.SA * p.a_stage;           // B ring behind the A ring (a_stage is a multiple of 1024)
   __shared__ __align__(8) uint64_t fullA[MAX_RING], emptyA[MAX_RING], fullB[MAX_RING], emptyB[MAX_RING], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_base_s;
-  __shared__ float epi_s[4 * 32 * 33];                          // per-epilogue-warp transpose tile
+  __shared__ __align__(16) float epi_s[8 * 32 * 36];            // per-epilogue-warp transpose tile (pitch 36: 128-bit conflict-free)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < MAX_RING; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], BN >= 64 ? 8 : 4); }   // = participating epilogue warps
     asm volatile("fence.mbarrier_init.release.cluster;\n");
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&mapA4.m[0])));
     asm volatile("prefetch.tensormap [%0];\n" ::"l"(reinterpret_cast<uint64_t>(&mapB4.m[0])));
@@ -290,7 +290,21 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
       }
     }
   } else {
-    const int lq = warp & 3;                                    // TMEM lane quadrant this warp may read
+    // ---- epilogue: EIGHT warps.  ncu (profiles/r2_ncu_gemm_tma.md) showed the round-1 epilogue -- four warps, one per
+    // scheduler, scalar shared-memory transposes and two integer divisions per row -- taking ~3x the main loop of a
+    // K = 11 x 128 tile: the tensor pipe idled at 30 % waiting for acc_empty no matter how the operands were staged.
+    // Now two warps share each TMEM lane quadrant (they split the 32-column chunks), the transpose tile is float4 in and
+    // float4 out (pitch 36: conflict-free for 128-bit accesses), and the row -> output-row mapping is computed once per
+    // 128-row block (no division at all when P == 1).
+    const int ew = warp - 2;
+    const int lq = warp & 3;                                    // TMEM lane quadrant this warp may read (hardware: warp id % 4)
+    const int half = ew >> 2;
+    constexpr int CHUNKS = BN / 32;
+    constexpr int NHALF = CHUNKS >= 2 ? 2 : 1;
+    if (half < NHALF) {
+    float* tr = epi_s + ew * (32 * 36);
+    const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
+    const float comp = p.comp;
     int tcount = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
       const int outer = tile / tiles_mn, mn = tile - outer * tiles_mn;
@@ -302,80 +316,86 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
       const int a = tcount % NACC;
       mbar_wait(&acc_full[a], (tcount / NACC) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;\n");
-      // TMEM gives each lane one ROW (32 consecutive columns); a direct store would touch 32 different rows per
-      // instruction.  Transpose through a padded per-warp smem tile so that every store instruction writes four full
-      // 128-byte row segments (and bias / residual loads are coalesced the same way).
-      float* tr = epi_s + (warp - 2) * (32 * 33);
-      const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
-      const float comp = p.comp;
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
-      const int row_base = tm * (MT * BM) + mt * BM + lq * 32;
-      if (row_base >= p.M) continue;                             // warp-uniform: nothing of this quadrant is inside the problem
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        const int n = tn * BN + c0;
-        if (n >= p.N) break;                                     // warp-uniform
-        float v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * MT * BN + mt * BN + c0), v);
-#pragma unroll
-        for (int e = 0; e < 32; ++e) tr[lane * 33 + e] = v[e];
-        __syncwarp();
-        const int nn = n + c4;
-        float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-        const bool full4 = nn + 4 <= p.N;
-        if (p.bias && !p.atomic) {
-          if (full4 && ((reinterpret_cast<uintptr_t>(p.bias + nn) & 15) == 0)) bv = *reinterpret_cast<const float4*>(p.bias + nn);
-          else { if (nn < p.N) bv.x = p.bias[nn]; if (nn + 1 < p.N) bv.y = p.bias[nn + 1]; if (nn + 2 < p.N) bv.z = p.bias[nn + 2]; if (nn + 3 < p.N) bv.w = p.bias[nn + 3]; }
-        }
+        const int row_base = tm * (MT * BM) + mt * BM + lq * 32;
+        if (row_base >= p.M) continue;                           // warp-uniform: nothing of this quadrant is inside the problem
+        // this lane's 8 rows (rl = i*4 + r_sub): output row index and length-mask flag, once per block
+        size_t orow[8];
+        bool keep[8], inside[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const int rl = i * 4 + r_sub, row = row_base + rl;
-          if (row >= p.M || nn >= p.N) continue;
-          float t[4] = {tr[rl * 33 + c4] * comp, tr[rl * 33 + c4 + 1] * comp, tr[rl * 33 + c4 + 2] * comp, tr[rl * 33 + c4 + 3] * comp};
-          const int jo = p.o0 + (row / p.P) * p.os;
-          const size_t orow = (size_t)jo * p.P + (row % p.P);
-          float* dp = dz + orow * p.ldd + nn;
-          const bool keep = jo < olen;
-          if (p.atomic) {
+          const int row = row_base + i * 4 + r_sub;
+          inside[i] = row < p.M;
+          int jo;
+          if (p.P == 1) { jo = p.o0 + row * p.os; orow[i] = (size_t)jo; }
+          else { const int jq = row / p.P; jo = p.o0 + jq * p.os; orow[i] = (size_t)jo * p.P + (row - jq * p.P); }
+          keep[i] = jo < olen;
+        }
+#pragma unroll 1
+        for (int c = half; c < CHUNKS; c += NHALF) {
+          const int c0 = c * 32;
+          const int n = tn * BN + c0;
+          if (n >= p.N) break;                                   // warp-uniform
+          float v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * MT * BN + mt * BN + c0), v);
+          float4* trw = reinterpret_cast<float4*>(tr + lane * 36);
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (nn + e < p.N) atomicAdd(dp + e, t[e]);
-            continue;
+          for (int e = 0; e < 8; ++e) trw[e] = make_float4(v[4 * e] * comp, v[4 * e + 1] * comp, v[4 * e + 2] * comp, v[4 * e + 3] * comp);
+          __syncwarp();
+          const int nn = n + c4;
+          float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+          const bool full4 = nn + 4 <= p.N;
+          if (p.bias && !p.atomic) {
+            if (full4 && ((reinterpret_cast<uintptr_t>(p.bias + nn) & 15) == 0)) bv = *reinterpret_cast<const float4*>(p.bias + nn);
+            else { if (nn < p.N) bv.x = p.bias[nn]; if (nn + 1 < p.N) bv.y = p.bias[nn + 1]; if (nn + 2 < p.N) bv.z = p.bias[nn + 2]; if (nn + 3 < p.N) bv.w = p.bias[nn + 3]; }
           }
-          t[0] += bv.x; t[1] += bv.y; t[2] += bv.z; t[3] += bv.w;
-          if (rz) {
-            const float* rp = rz + orow * p.ldr + nn;
-            if (full4 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
-              const float4 rv = *reinterpret_cast<const float4*>(rp);
-              t[0] += rv.x; t[1] += rv.y; t[2] += rv.z; t[3] += rv.w;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (!inside[i] || nn >= p.N) continue;
+            const float4 tv = *reinterpret_cast<const float4*>(tr + (i * 4 + r_sub) * 36 + c4);
+            float t[4] = {tv.x, tv.y, tv.z, tv.w};
+            float* dp = dz + orow[i] * p.ldd + nn;
+            if (p.atomic) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (nn + e < p.N) atomicAdd(dp + e, t[e]);
+              continue;
+            }
+            t[0] += bv.x; t[1] += bv.y; t[2] += bv.z; t[3] += bv.w;
+            if (rz) {
+              const float* rp = rz + orow[i] * p.ldr + nn;
+              if (full4 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+                const float4 rv = *reinterpret_cast<const float4*>(rp);
+                t[0] += rv.x; t[1] += rv.y; t[2] += rv.z; t[3] += rv.w;
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  if (nn + e < p.N) t[e] += rp[e];
+              }
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (p.act == EVK_ACT_LRELU) t[e] = t[e] > 0.f ? t[e] : t[e] * p.slope;
+              else if (p.act == EVK_ACT_RELU) t[e] = fmaxf(t[e], 0.f);
+              else if (p.act == EVK_ACT_TANH) t[e] = tanhf(t[e]);
+              if (!keep[i]) t[e] = 0.f;
+            }
+            if (full4 && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
+              *reinterpret_cast<float4*>(dp) = make_float4(t[0], t[1], t[2], t[3]);
             } else {
 #pragma unroll
               for (int e = 0; e < 4; ++e)
-                if (nn + e < p.N) t[e] += rp[e];
+                if (nn + e < p.N) dp[e] = t[e];
             }
           }
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            if (p.act == EVK_ACT_LRELU) t[e] = t[e] > 0.f ? t[e] : t[e] * p.slope;
-            else if (p.act == EVK_ACT_RELU) t[e] = fmaxf(t[e], 0.f);
-            else if (p.act == EVK_ACT_TANH) t[e] = tanhf(t[e]);
-            if (!keep) t[e] = 0.f;
-          }
-          if (full4 && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
-            *reinterpret_cast<float4*>(dp) = make_float4(t[0], t[1], t[2], t[3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              if (nn + e < p.N) dp[e] = t[e];
-          }
+          __syncwarp();
         }
-        __syncwarp();
-      }
       }
       asm volatile("tcgen05.fence::before_thread_sync;\n");
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[a]);
+    }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n");
@@ -434,7 +454,7 @@ struct Operands {
   int raw_operands;                                    // how many of the two operands are un-rounded fp32 (truncated by the MMA)
 };
 
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int SMEM_BUDGET = 184 * 1024;               // + 36.9 KB static epilogue tiles + barriers <= 227 KB
 
 template <int BN, int MT>
 int launch_gemm(const Operands& o, GemmP& p, int splits, cudaStream_t st) {
