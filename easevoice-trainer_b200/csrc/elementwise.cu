@@ -280,6 +280,60 @@ __global__ void transpose_rows_multi_kernel(const float* __restrict__ x, int ldx
   }
 }
 
+// One pass over an output gradient for everything a conv's backward needs from it (round 1 ran three kernels -- activation
+// backward, transpose for the TMA weight gradient, column sums for the bias -- and four trips through memory):
+//   g[t][c]    = dy[t][c] * act'(y[t][c]) * (t < len*P)        -> dpre  (normal layout, only when it differs from dy)
+//   dyt[c][t]  = g[t][c]                                        -> the K-major A operand of the weight-gradient GEMM
+//   dbias[c]  += sum_t g[t][c]                                  (atomics; one per column per block of TPB row tiles)
+constexpr int DYP_TPB = 8;
+__global__ void __launch_bounds__(256) dy_prep_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ yact, int ldy, int act,
+                                                      float slope, const int* __restrict__ len, int P, float* __restrict__ dpre, int ldp,
+                                                      float* __restrict__ dyt, int ldt, long long t_sb, float* __restrict__ dbias, int T, int C) {
+  __shared__ float tile[32][33];
+  __shared__ float csum[8][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, tx = threadIdx.x, ty = threadIdx.y;
+  const long long row0 = (long long)b * T;
+  const int lim = len ? len[b] * P : 0x7fffffff;
+  const int c = c0 + tx;
+  float acc = 0.f;
+  for (int tt = 0; tt < DYP_TPB; ++tt) {
+    const int t0 = (blockIdx.x * DYP_TPB + tt) * 32;
+    if (t0 >= T) break;
+    for (int i = ty; i < 32; i += 8) {
+      const int t = t0 + i;
+      float v = 0.f;
+      if (c < C && t < T) {
+        v = dy[(row0 + t) * lddy + c];
+        if (act) {
+          const float o = yact[(row0 + t) * ldy + c];
+          v *= (act == EVK_ACT_LRELU) ? (o > 0.f ? 1.f : slope) : (act == EVK_ACT_RELU) ? (o > 0.f ? 1.f : 0.f) : (1.f - o * o);
+        }
+        if (t >= lim) v = 0.f;
+        if (dpre) dpre[(row0 + t) * ldp + c] = v;
+      }
+      tile[i][tx] = v;
+      acc += v;
+    }
+    __syncthreads();
+    if (dyt)
+      for (int i = ty; i < 32; i += 8) {
+        const int cc = c0 + i, u = t0 + tx;
+        if (u < T && cc < C) dyt[b * t_sb + (long long)cc * ldt + u] = tile[tx][i];
+      }
+    __syncthreads();
+  }
+  if (dbias) {
+    csum[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && c < C) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sacc += csum[k][tx];
+      atomicAdd(&dbias[c], sacc);
+    }
+  }
+}
+
 // stride-phase split: xs[rho][b][j*P + w][c] = x[b][(j*s + rho)*P + w][c] (zero when j*s + rho >= T), j < Jp
 __global__ void phase_split_kernel(const float* __restrict__ x, int ldx, long long x_sb, float* __restrict__ xs, long long xs_ps,
                                    int B, int T, int P, int C, int s, int Jp) {
@@ -537,6 +591,20 @@ extern "C" int evk_transpose_rows_multi(const float* x, int32_t ldx, int64_t x_s
   EVK_REQUIRE(grid.y <= 65535 && grid.z <= 65535, EVK_ERR_ARG, "transpose_rows_multi: grid too large");
   transpose_rows_multi_kernel<<<grid, block, 0, ST>>>(x, ldx, x_sb, y, ldy, y_sb, y_rs, T, C, mask);
   return check_launch("transpose_rows_multi");
+}
+// dy [B][T][lddy] (T rows per batch item), yact = the conv's activated OUTPUT (nullable when act == 0), len (nullable int32 [B],
+// rows t >= len[b] * P are zeroed), outputs each nullable: dpre [B][T][ldp], dyt [B][C][ldt] (batch pitch t_sb), dbias [C]
+// (accumulated: zero it first).
+extern "C" int evk_dy_prep(const float* dy, int32_t lddy, const float* yact, int32_t ldy, int32_t act, float slope, const int32_t* len, int32_t P,
+                           float* dpre, int32_t ldp, float* dyt, int32_t ldt, int64_t t_sb, float* dbias, int32_t B, int32_t T, int32_t C,
+                           evk_stream_t stream) {
+  EVK_REQUIRE(dy && (act == 0 || yact) && act >= 0 && act <= 3 && P >= 1 && (dpre || dyt || dbias), EVK_ERR_ARG, "dy_prep: bad arguments");
+  EVK_REQUIRE(!dyt || ldt >= T, EVK_ERR_ARG, "dy_prep: ldt too small");
+  if ((long long)B * T * C == 0) return EVK_OK;
+  dim3 grid(cdiv(T, 32 * DYP_TPB), cdiv(C, 32), B), block(32, 8);
+  EVK_REQUIRE(grid.y <= 65535 && grid.z <= 65535, EVK_ERR_ARG, "dy_prep: grid too large");
+  dy_prep_kernel<<<grid, block, 0, ST>>>(dy, lddy, yact, ldy, act, slope, len, P, dpre, ldp, dyt, ldt, t_sb, dbias, T, C);
+  return check_launch("dy_prep");
 }
 extern "C" int evk_phase_split(const float* x, int32_t ldx, int64_t x_sb, float* xs, int64_t xs_ps, int32_t B, int32_t T, int32_t P,
                                int32_t C, int32_t stride, int32_t Jp, evk_stream_t stream) {

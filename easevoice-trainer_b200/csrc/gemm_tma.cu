@@ -523,7 +523,9 @@ int launch_bn(const Operands& o, GemmP& p, int splits, cudaStream_t st) {
     cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
   }
   bool mt2 = false;
-  if (g_opt_mt2 && BN <= 128 && !p.mode && splits <= 1 && p.M >= 2 * BM) {      // BN = 256 would lose the second accumulator (epilogue overlap): measured slower
+  // measured (profiles/r2_ab_tma.md): 256-row tiles pay only on the 32-channel layers (HBM-side bound, +15 %); at 64 channels they
+  // are neutral, at 128 they lose to the wave quantisation of the 148-CTA grid, at 256 they cost the second accumulator
+  if (g_opt_mt2 && BN == 32 && !p.mode && splits <= 1 && p.M >= 2 * BM) {
     const long long per = (long long)cdiv(p.N, BN) * p.Z;
     const long long t1 = per * cdiv(p.M, BM), t2 = per * cdiv(p.M, 2 * BM);
     const double c1 = (double)cdiv(t1, g_sm_count), c2 = (double)cdiv(t2, g_sm_count) * 2.0 * 0.65;

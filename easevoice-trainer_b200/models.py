@@ -80,14 +80,15 @@ class ParamTree(nn.Module):
         if rec:
             self.__dict__.setdefault("_plans", {})[self._frozen] = ops.PackPlan(rec, with_grad=not self._frozen)
 
-    def w(self, pfx, need_pb=True, pad0=0, pad1=0):
+    def w(self, pfx, need_pb=True, pad0=0, pad1=0, suffix=".weight"):
+        """packed (and weight-normed when pfx has weight_g / weight_v) operand of the parameter `pfx + suffix`"""
         key = (pfx, need_pb, pad0, pad1)
         act = getattr(self, "_active", None)
         if act is not None and key in act:
             return act[key]
         fz = (lambda t: t.detach()) if self._frozen else (lambda t: t)
         has_g = self.has(pfx + ".weight_v")
-        v = self.P(pfx + (".weight_v" if has_g else ".weight"))
+        v = self.P(pfx + (".weight_v" if has_g else suffix))
         g = self.P(pfx + ".weight_g") if has_g else None
         rec = getattr(self, "_recording", None)
         if rec is not None and all(r[0] != key for r in rec):

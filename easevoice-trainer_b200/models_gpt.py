@@ -104,7 +104,7 @@ class Text2SemanticDecoder(ParamTree):
         p_attn = self.layer_dropout if self.training else 0.0
         for i in range(self.num_layers):
             p = f"h.layers.{i}."
-            qkv = ops.linear(h, ops.pack_weight(self.P(p + "self_attn.in_proj_weight")), self.P(p + "self_attn.in_proj_bias"))
+            qkv = ops.linear(h, self.w(p + "self_attn.in_proj", suffix="_weight"), self.P(p + "self_attn.in_proj_bias"))
             a = ops.flash_attention(qkv, heads=H, prefix=X, xlen=x_lens, ylen=y_lens, p_drop=p_attn, tag=f"{tagp}gpt.attn{i}")
             a = ops.linear(a, self.w(p + "self_attn.out_proj"), self.b(p + "self_attn.out_proj"))
             h = ops.layernorm(h, self.P(p + "norm1.weight"), self.P(p + "norm1.bias"), res=self._drop(a, f"{tagp}gpt.d1.{i}"))
@@ -134,6 +134,13 @@ class Text2SemanticDecoder(ParamTree):
         x_lens, y_lens, ryl = [t.to(torch.int64).contiguous() for t in (x_lens, y_lens, ryl)]
         y_in, tg = self.make_targets(y, y_lens)
         ry_in, rtg = self.make_targets(ry, ryl)
+        self.begin_pack()
+        try:
+            return self._forward_dpo(x, bert_feature, bert_channels_last, y_in, tg, ry_in, rtg, x_lens, y_lens, ryl, X)
+        finally:
+            self.end_pack()
+
+    def _forward_dpo(self, x, bert_feature, bert_channels_last, y_in, tg, ry_in, rtg, x_lens, y_lens, ryl, X):
         # the text prefix is embedded once per branch in the reference (two make_input_data calls); the branches only share
         # weights, so the second pass re-runs it to keep the dropout streams independent as well
         lc = self._decode(self._embed_text(x, bert_feature, bert_channels_last), y_in, x_lens, y_lens, X)
@@ -148,7 +155,11 @@ class Text2SemanticDecoder(ParamTree):
         B, X = x.shape
         x_lens, y_lens = x_lens.to(torch.int64).contiguous(), y_lens.to(torch.int64).contiguous()
         y_in, tg = self.make_targets(y, y_lens) if targets is None else targets
-        logits = self._decode(self._embed_text(x, bert_feature, bert_channels_last), y_in, x_lens, y_lens, X)
+        self.begin_pack()                      # all 147 weight packs of the step in one launch (ops.PackPlan)
+        try:
+            logits = self._decode(self._embed_text(x, bert_feature, bert_channels_last), y_in, x_lens, y_lens, X)
+        finally:
+            self.end_pack()
         loss, out2 = ops.ce_sum_topk(logits, tg.reshape(-1), self.top_k, self.EOS, V=self.vocab_size)
         self.last_logits = logits.detach()        # detached: a retained graph would pin AccumulateGrad nodes to this stream
         return loss, out2[1]

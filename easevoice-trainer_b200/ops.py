@@ -268,13 +268,17 @@ class PackJobC(ctypes.Structure):
 
 
 _dpa_views = {}          # data_ptr of a packed weight -> its slice of the plan's (pre-zeroed) packed-gradient arena
+_dpa_taken = set()       # slices already handed to a backward since the plan was last zeroed
 
 
 def dpa_buffer(pa):
     """where a weight-gradient kernel accumulates d(pa): the plan's arena slice when pa comes from a PackPlan (zeroed once
-    per step by the plan), else a fresh zero tensor"""
-    v = _dpa_views.get(pa.data_ptr())
-    if v is not None and v.shape == pa.shape:
+    per step by the plan), else a fresh zero tensor.  A weight used twice in one forward (the DPO branches) gets the slice
+    for its first gradient only -- autograd SUMS the gradients of the uses, so they must live in distinct buffers."""
+    key = pa.data_ptr()
+    v = _dpa_views.get(key)
+    if v is not None and v.shape == pa.shape and key not in _dpa_taken:
+        _dpa_taken.add(key)
         return v
     return torch.zeros_like(pa)
 
@@ -342,6 +346,7 @@ class PackPlan:
             self.jobs_bwd = torch.frombuffer(bytearray(bytes(jb)), dtype=torch.uint8).to(dev)
             self.rows_bwd = torch.tensor(rows_bwd, dtype=torch.int32, device=dev)
         self.index = {req[0]: i for i, req in enumerate(reqs)}
+        self.pa_keys = {t.data_ptr() for t in self.pa}
 
     def valid(self):
         """parameters still live where the job table points (they move when an optimizer re-homes them into its arena)"""
@@ -365,6 +370,7 @@ class _PackAllFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, plan, *params):
         plan.arena_dpa.zero_()                     # the step's weight-gradient kernels accumulate into it
+        _dpa_taken.difference_update(plan.pa_keys)
         plan.run_pack()
         ctx.plan = plan
         # FRESH tensor objects every call: returning the stored views again would hand autograd tensors that still carry
@@ -504,16 +510,26 @@ class _ConvFn(torch.autograd.Function):
         has_bias, has_res = ctx.has
         Cg, Ng = C // G, N // G
         dy = dy.contiguous()
-        if act:
-            dpre = torch.empty_like(dy)
-            op = {ACT_LRELU: UN_LRELU, ACT_RELU: UN_RELU, ACT_TANH: UN_TANH_FROM_OUT}[act]
-            _call("evk_unary_bwd", op, ctypes.c_float(slope), _p(y), N, _p(dy), N, _p(dpre), N, B * J * P, N)
-            dy = dpre
-        if out_len is not None:
-            dm = torch.empty_like(dy)
-            _call("evk_rowmask", _p(dy), N, _p(dm), N, B, J * P, N, _p(out_len))   # P == 1 whenever masks are used
-            dy = dm
-        dx = dpa = dbias = dres = None
+        Ro = J * P
+        _, _, ldx_ = _rows(x)
+        mma_w = _aligned(x, ldx_) and _aligned(dy, N) and (G == 1 or (Cg % 4 == 0 and Ng % 4 == 0))
+        tma_w = bool(ctx.needs_input_grad[1] and mma_w and USE_TMA_WGRAD and 1 <= stride <= 4 and (stride == 1 or dil == 1) and G == 1
+                     and in_len is None and B * J * P >= 2048 and J * P >= 64 and C >= 32 and N >= 32 and C % 4 == 0
+                     and not _lib().evk_get_precise())
+        want_b = has_bias and ctx.needs_input_grad[3]
+        dyt = dbias = None
+        if act or out_len is not None or tma_w or want_b:
+            # one pass: activation backward + length mask (-> dpre), the transposed copy the TMA weight gradient reads, bias sums
+            need_pre = bool(act) or out_len is not None
+            dpre = torch.empty_like(dy) if need_pre else None
+            ldo = (Ro + 31) // 32 * 32                                       # 128-byte aligned rows for the TMA boxes
+            dyt = torch.empty((B, N, ldo), device=dy.device, dtype=torch.float32) if tma_w else None
+            dbias = torch.zeros(N, device=dy.device, dtype=torch.float32) if want_b else None
+            _call("evk_dy_prep", _p(dy), N, _p(y), N, act, ctypes.c_float(slope), _p(out_len), P, _p(dpre), N, _p(dyt), ldo, N * ldo, _p(dbias),
+                  B, Ro, N)
+            if need_pre:
+                dy = dpre
+        dx = dpa = dres = None
         offs = [q * dil - pad for q in range(Q)]
         if ctx.needs_input_grad[0]:
             dx = torch.empty((B, Tin * P, C), device=dy.device, dtype=torch.float32)
@@ -535,20 +551,13 @@ class _ConvFn(torch.autograd.Function):
                 dx = dxm
         if ctx.needs_input_grad[1]:
             dpa = dpa_buffer(pa)
-            _, _, ldx = _rows(x)
-            mma = _aligned(x, ldx) and _aligned(dy, N) and (G == 1 or (Cg % 4 == 0 and Ng % 4 == 0))
-            rows = B * Tin
-            if (mma and USE_TMA_WGRAD and 1 <= stride <= 4 and (stride == 1 or dil == 1) and G == 1 and in_len is None
-                    and B * J * P >= 2048 and J * P >= 64 and C >= 32 and N >= 32 and C % 4 == 0 and not _lib().evk_get_precise()):
+            ldx, mma = ldx_, mma_w
+            if tma_w:
                 # dW[q][n][c] = sum_{b,pos} dY[b][pos][n] X[b][pos + shift_q][c]: both operands are transposed once (positions
                 # become the contiguous K dim), then the TMA-fed tcgen05 GEMM runs one output tile per (tap, n, c, K split)
                 # with the tap shift as a TMA coordinate (out-of-range rows = conv padding, zero-filled by the copy engine).
                 # A strided conv is first split into `stride` phase copies of X (as in the forward): taps u = q - pad with
                 # u mod stride == rho form a stride-1 problem on copy rho with shifts floor(u / stride).
-                Ro = J * P
-                ldo = (Ro + 31) // 32 * 32                                   # 128-byte aligned rows for the TMA boxes
-                dyt = torch.empty((B, N, ldo), device=dy.device, dtype=torch.float32)
-                _call("evk_transpose_rows", _p(dy), N, Ro * N, _p(dyt), ldo, N * ldo, B, Ro, N, 0)
                 if stride == 1:
                     srcs = [(x, ldx, Tin, list(range(Q)), offs)]
                 else:
@@ -589,9 +598,6 @@ class _ConvFn(torch.autograd.Function):
                           ldx=ldx, ldw=lda, ldy=N, ldr=0, b_sh=0, Z=B, H=1, C=C, N=N, Q=Q, G=G, Tin=Tin, J=J, P=P,
                           is_=stride, os_=1, o0=0, Tout=J, act=0, slope=0.0, off=offs)
                 _run_desc("evk_conv_direct_wgrad", d)
-        if has_bias and ctx.needs_input_grad[3]:
-            dbias = torch.empty(N, device=dy.device, dtype=torch.float32)
-            _call("evk_colsum", _p(dy), B * J * P, N, N, _p(dbias), 0)
         if has_res and ctx.needs_input_grad[4]:
             dres = dy
         return dx, dpa, None, dbias, dres, None
