@@ -309,6 +309,13 @@ def run_ours(args):
     from easevoice_trainer_b200 import configs
     lib.init()
     trace("lib + process group up")
+    if args.config == 5:
+        if rank == 0:
+            emit(dict(metric="HiFi-GAN generator + MPD/MSD + MR-STFT loss step (BASELINE config 5)", **config5_section(args, dev)))
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
     if args.only_gpt:
         out = gpt_section(args, dev, rank, world)
         if rank == 0:
@@ -616,6 +623,90 @@ def gpt_cpu_baseline(B, X, Y, Bc=2):
                 sample=f"oracle port of forward_old + backward (24 layers, fp32, dropout off), B={Bc}, X={X}, Y={Y}, 1 cold micro-batch, {sec:.1f} s")
 
 
+def config5_section(args, dev):
+    """BASELINE.json configs[4]: HiFi-GAN generator + MPD/MSD + losses only, batch 32 x 1 s at the 48 kHz label (z [32,192,75] ->
+    y_hat [32,1,48000]), with the multi-resolution STFT loss as the opt-in extension (bs_roformer.py:565-581).  One "step" =
+    generator forward, discriminators on (y, y_hat), GAN + feature-matching + MR-STFT losses, backward through everything
+    (weight gradients of G and D, d z).  Reports the step time and the per-layer sweep of SURVEY 8(d): every contraction
+    launch of the step with its shape, device time, achieved TFLOP/s and algorithmic GB/s."""
+    import torch
+    from easevoice_trainer_b200 import ops, models, configs
+    hps = configs.load_s2_config()
+    torch.manual_seed(1234)
+    net_g = models.SynthesizerTrn(hps["data"]["filter_length"] // 2 + 1, hps["train"]["segment_size"] // hps["data"]["hop_length"],
+                                  n_speakers=hps["data"]["n_speakers"], **hps["model"]).to(dev).train()
+    net_d = models.MultiPeriodDiscriminator(False).to(dev).train()
+    B, T = 32, 75
+    g = torch.Generator().manual_seed(5)
+    z = (torch.randn(B, T, 192, generator=g)).to(dev).requires_grad_(True)
+    ge = (torch.randn(B, 1, 512, generator=g) * 0.5).to(dev)
+    y = (torch.rand(B, T * 640, 1, generator=g) - 0.5).to(dev)
+    gp = [p_ for n, p_ in net_g.named_parameters() if n.startswith("dec.")]
+    dp = list(net_d.parameters())
+
+    def step(mr=True):
+        net_g.begin_pack()
+        try:
+            yh = net_g._generator(z, ge)
+        finally:
+            net_g.end_pack()
+        outs = net_d.forward_cl(y, yh)
+        lg = lf = ld = 0.0
+        for logit, fmap in outs:
+            lg = lg + ops.mean_sq_one_minus(logit[B:])
+            ld = ld + ops.mean_sq_one_minus(logit[:B]) + ops.mean_sq(logit[B:])
+            for f in fmap:
+                lf = lf + ops.mean_abs_diff(f[B:], f[:B])
+        loss = lg + 2.0 * lf + ld
+        if mr:
+            loss = loss + ops.mrstft_loss(yh.reshape(B, -1), y.reshape(B, -1))
+        torch.autograd.grad(loss, [z] + gp + dp)
+        return loss.detach()
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    out = {}
+    for key, mr in (("with_mrstft", True), ("without_mrstft", False)):
+        st_ = lambda: step(mr)
+        st_()
+        ms = graph_time(st_)
+        out[key] = dict(ms_per_step=ms, audio_s_per_s=B * 1.0 / (ms * 1e-3))
+    # per-launch sweep from one profiled eager step
+    rows = []
+    orig = ops._run_desc
+
+    def rec_desc(fn, d):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig(fn, d)
+        e1.record()
+        rows.append((fn, dict(Z=d.Z, C=d.C, N=d.N, Q=d.Q, J=d.J, P=d.P, stride=d.is_, os=d.os_, H=d.H), e0, e1,
+                     2.0 * d.Z * d.J * d.P * d.N * d.C * d.Q, 4.0 * d.Z * (d.J * d.P * d.N + d.Tin * d.P * d.C) + 4.0 * d.Q * d.N * d.C))
+    ops._run_desc = rec_desc
+    try:
+        step(True)
+    finally:
+        ops._run_desc = orig
+    torch.cuda.synchronize()
+    agg = {}
+    for fn, shp, e0, e1, fl, by in rows:
+        k = (fn,) + tuple(shp.items())
+        a = agg.setdefault(k, dict(call=fn, **shp, launches=0, ms=0.0, flops=0.0, bytes=0.0))
+        a["launches"] += 1; a["ms"] += e0.elapsed_time(e1); a["flops"] += fl; a["bytes"] += by
+    table = sorted(agg.values(), key=lambda a: -a["ms"])
+    for a in table:
+        a["tflops"] = round(a["flops"] / (a["ms"] * 1e-3) / 1e12, 1)
+        a["gbs"] = round(a["bytes"] / (a["ms"] * 1e-3) / 1e9, 0)
+        a["ms"] = round(a["ms"], 4)
+        del a["flops"], a["bytes"]
+    out["layers"] = table[:60]
+    out["config"] = dict(workload="vocoder_only_B32x1s_sr48000 (z [32,192,75] -> y_hat [32,1,48000])", mrstft_windows=[4096, 2048, 1024, 512, 256], mrstft_hop=147)
+    out["how"] = ("step: CUDA-graph replay between CUDA events; layers: conv-family launches of one eager step (forward, data-gradient phases; weight gradients "
+                  "of the TMA path are listed by the bench roofline instead), grouped by shape, device time from events around each launch; GB/s = (input + output "
+                  "+ weight bytes, once) / time")
+    return out
+
+
 def emit(line):
     """write the one JSON line to the REAL stdout (fd 1 is pointed at stderr while the benchmark runs so that library
     banners -- e.g. NCCL's version line -- cannot pollute the result stream)."""
@@ -642,6 +733,7 @@ def main():
     ap.add_argument("--no-torch-port", action="store_true")
     ap.add_argument("--only-gpt", action="store_true", help="profiling aid: run just the stage-1 AR-GPT section and print its object")
     ap.add_argument("--gpt", type=int, default=2, help="2 (default): also time the stage-1 AR-GPT step at every N; 1: at N=1 only; 0: skip")
+    ap.add_argument("--config", type=int, default=3, help="3 (default): the stage-2 step (BASELINE configs 3/4); 5: vocoder-only per-layer sweep with the MR-STFT loss")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the captured CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
