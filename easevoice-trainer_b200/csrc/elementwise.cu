@@ -285,42 +285,49 @@ __global__ void transpose_rows_multi_kernel(const float* __restrict__ x, int ldx
 //   g[t][c]    = dy[t][c] * act'(y[t][c]) * (t < len*P)        -> dpre  (normal layout, only when it differs from dy)
 //   dyt[c][t]  = g[t][c]                                        -> the K-major A operand of the weight-gradient GEMM
 //   dbias[c]  += sum_t g[t][c]                                  (atomics; one per column per block of TPB row tiles)
-constexpr int DYP_TPB = 8;
+constexpr int DYP_ROWS = 128;          // rows per block: 16 independent loads per thread in flight, one barrier
 __global__ void __launch_bounds__(256) dy_prep_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ yact, int ldy, int act,
                                                       float slope, const int* __restrict__ len, int P, float* __restrict__ dpre, int ldp,
                                                       float* __restrict__ dyt, int ldt, long long t_sb, float* __restrict__ dbias, int T, int C) {
-  __shared__ float tile[32][33];
+  __shared__ float tile[DYP_ROWS][33];
   __shared__ float csum[8][33];
-  const int b = blockIdx.z, c0 = blockIdx.y * 32, tx = threadIdx.x, ty = threadIdx.y;
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * DYP_ROWS, tx = threadIdx.x, ty = threadIdx.y;
   const long long row0 = (long long)b * T;
   const int lim = len ? len[b] * P : 0x7fffffff;
   const int c = c0 + tx;
+  float v[DYP_ROWS / 8], o[DYP_ROWS / 8];
+#pragma unroll
+  for (int k = 0; k < DYP_ROWS / 8; ++k) {                       // all loads first (memory-level parallelism)
+    const int t = t0 + ty + 8 * k;
+    const bool in = c < C && t < T;
+    v[k] = in ? dy[(row0 + t) * lddy + c] : 0.f;
+    o[k] = (in && act) ? yact[(row0 + t) * ldy + c] : 1.f;
+  }
   float acc = 0.f;
-  for (int tt = 0; tt < DYP_TPB; ++tt) {
-    const int t0 = (blockIdx.x * DYP_TPB + tt) * 32;
-    if (t0 >= T) break;
+#pragma unroll
+  for (int k = 0; k < DYP_ROWS / 8; ++k) {
+    const int t = t0 + ty + 8 * k;
+    float g = v[k];
+    if (act) g *= (act == EVK_ACT_LRELU) ? (o[k] > 0.f ? 1.f : slope) : (act == EVK_ACT_RELU) ? (o[k] > 0.f ? 1.f : 0.f) : (1.f - o[k] * o[k]);
+    if (t >= lim) g = 0.f;
+    if (dpre && c < C && t < T) dpre[(row0 + t) * ldp + c] = g;
+    tile[ty + 8 * k][tx] = g;
+    acc += g;
+  }
+  __syncthreads();
+  if (dyt) {
+#pragma unroll
     for (int i = ty; i < 32; i += 8) {
-      const int t = t0 + i;
-      float v = 0.f;
-      if (c < C && t < T) {
-        v = dy[(row0 + t) * lddy + c];
-        if (act) {
-          const float o = yact[(row0 + t) * ldy + c];
-          v *= (act == EVK_ACT_LRELU) ? (o > 0.f ? 1.f : slope) : (act == EVK_ACT_RELU) ? (o > 0.f ? 1.f : 0.f) : (1.f - o * o);
+      const int cc = c0 + i;
+      if (cc < C) {
+        float* dst = dyt + b * t_sb + (long long)cc * ldt + t0;
+#pragma unroll
+        for (int k = 0; k < DYP_ROWS / 32; ++k) {
+          const int u = tx + 32 * k;
+          if (t0 + u < T) dst[u] = tile[u][i];
         }
-        if (t >= lim) v = 0.f;
-        if (dpre) dpre[(row0 + t) * ldp + c] = v;
       }
-      tile[i][tx] = v;
-      acc += v;
     }
-    __syncthreads();
-    if (dyt)
-      for (int i = ty; i < 32; i += 8) {
-        const int cc = c0 + i, u = t0 + tx;
-        if (u < T && cc < C) dyt[b * t_sb + (long long)cc * ldt + u] = tile[tx][i];
-      }
-    __syncthreads();
   }
   if (dbias) {
     csum[ty][tx] = acc;
@@ -601,7 +608,7 @@ extern "C" int evk_dy_prep(const float* dy, int32_t lddy, const float* yact, int
   EVK_REQUIRE(dy && (act == 0 || yact) && act >= 0 && act <= 3 && P >= 1 && (dpre || dyt || dbias), EVK_ERR_ARG, "dy_prep: bad arguments");
   EVK_REQUIRE(!dyt || ldt >= T, EVK_ERR_ARG, "dy_prep: ldt too small");
   if ((long long)B * T * C == 0) return EVK_OK;
-  dim3 grid(cdiv(T, 32 * DYP_TPB), cdiv(C, 32), B), block(32, 8);
+  dim3 grid(cdiv(T, DYP_ROWS), cdiv(C, 32), B), block(32, 8);
   EVK_REQUIRE(grid.y <= 65535 && grid.z <= 65535, EVK_ERR_ARG, "dy_prep: grid too large");
   dy_prep_kernel<<<grid, block, 0, ST>>>(dy, lddy, yact, ldy, act, slope, len, P, dpre, ldp, dyt, ldt, t_sb, dbias, T, C);
   return check_launch("dy_prep");

@@ -261,6 +261,44 @@ def pack_weight(v, g=None, need_pb=True, pad0=0, pad1=0):
     return PackedW(pa, pb if need_pb else None, D0, D1, v.numel() // (v.shape[0] * v.shape[1]))
 
 
+# ---- pooled zero-initialised scratch for small accumulators (bias gradients) -------------------------------------------
+# A backward pass needs ~300 tiny zero-filled vectors (one per bias): as separate torch.zeros they are 300 fill launches.
+# Inside `with grad_pool():` they are slices of one persistent buffer that is cleared by ONE memset when the scope opens.
+# Only for callers that consume the gradients before the next scope opens (the train steps copy them into their flat
+# gradient arena right away); everything else gets ordinary torch.zeros.
+class _ZeroPool:
+    def __init__(self):
+        self.buf, self.off, self.high, self.on = None, 0, 0, False
+
+    def take(self, n, device):
+        if not self.on:
+            return torch.zeros(n, device=device, dtype=torch.float32)
+        device = torch.device(device)
+        if self.buf is None or self.buf.device != device:
+            self.buf, self.off, self.high = torch.zeros(1 << 20, device=device, dtype=torch.float32), 0, 0
+        a = (self.off + 3) // 4 * 4
+        if a + n > self.buf.numel():
+            return torch.zeros(n, device=device, dtype=torch.float32)
+        self.off = a + n
+        self.high = max(self.high, self.off)
+        return self.buf[a:a + n]
+
+
+_zpool = _ZeroPool()
+
+
+class grad_pool:
+    def __enter__(self):
+        if _zpool.buf is not None and _zpool.high:
+            _zpool.buf[:_zpool.high].zero_()
+        _zpool.off, _zpool.on = 0, True
+        return self
+
+    def __exit__(self, *exc):
+        _zpool.on = False
+        return False
+
+
 # ---- whole-network packing: one launch per network per step (pack_batched.cu) ------------------------------------
 class PackJobC(ctypes.Structure):
     _fields_ = ([(n, ctypes.c_void_p) for n in ("v", "g", "pa", "pb", "dpa", "dv", "dg")]
@@ -524,7 +562,7 @@ class _ConvFn(torch.autograd.Function):
             dpre = torch.empty_like(dy) if need_pre else None
             ldo = (Ro + 31) // 32 * 32                                       # 128-byte aligned rows for the TMA boxes
             dyt = torch.empty((B, N, ldo), device=dy.device, dtype=torch.float32) if tma_w else None
-            dbias = torch.zeros(N, device=dy.device, dtype=torch.float32) if want_b else None
+            dbias = _zpool.take(N, dy.device) if want_b else None
             _call("evk_dy_prep", _p(dy), N, _p(y), N, act, ctypes.c_float(slope), _p(out_len), P, _p(dpre), N, _p(dyt), ldo, N * ldo, _p(dbias),
                   B, Ro, N)
             if need_pre:

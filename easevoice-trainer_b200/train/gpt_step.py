@@ -130,14 +130,16 @@ class GptStep:
             loss, acc = m.forward(batch["phoneme_ids"], batch["phoneme_ids_len"], batch["semantic_ids"], batch["semantic_ids_len"],
                                   batch["bert_feature"], reject=batch.get("reject"),
                                   bert_channels_last=batch.get("bert_channels_last", False))
-            grads = torch.autograd.grad(loss, self.opt.params, allow_unused=True)
-            self.opt.accumulate(grads)
+            with ops.grad_pool():
+                grads = torch.autograd.grad(loss, self.opt.params, allow_unused=True)
+                self.opt.accumulate(grads)
             return loss.detach(), acc
         loss, acc = m.forward_old(batch["phoneme_ids"], batch["phoneme_ids_len"], batch["semantic_ids"],
                                   batch["semantic_ids_len"], batch["bert_feature"], targets=batch.get("targets"),
                                   bert_channels_last=batch.get("bert_channels_last", False))
-        grads = torch.autograd.grad(loss, self.opt.params, allow_unused=True)
-        self.opt.accumulate(grads)
+        with ops.grad_pool():
+            grads = torch.autograd.grad(loss, self.opt.params, allow_unused=True)
+            self.opt.accumulate(grads)
         return loss.detach(), acc
 
     def optimizer_step(self):

@@ -273,13 +273,15 @@ class S2Step:
     def _seg_a(self, batch, noise=None, ids_slice=None):
         r = self.losses(batch, noise, ids_slice)
         loss_d = self.d_loss(r)
-        self.opt_d.set_grads(torch.autograd.grad(loss_d, self.opt_d.params, allow_unused=True))
+        with ops.grad_pool():
+            self.opt_d.set_grads(torch.autograd.grad(loss_d, self.opt_d.params, allow_unused=True))
         return r, loss_d
 
     def _seg_b(self, r):
         self.opt_d.step(1.0 / self.world)
         loss_g, parts = self.g_loss(r)
-        self.opt_g.set_grads(torch.autograd.grad(loss_g, self.opt_g.params, allow_unused=True))
+        with ops.grad_pool():
+            self.opt_g.set_grads(torch.autograd.grad(loss_g, self.opt_g.params, allow_unused=True))
         return loss_g, parts
 
     def _seg_c(self):
