@@ -17,6 +17,7 @@ from torch import nn
 
 from . import ops
 
+SIDE_STREAMS = os.environ.get("EVK_SIDE_STREAMS", "0") == "1"
 LRELU_SLOPE = 0.1
 N_SYMBOLS = 732            # len(SYMBOLS): src/easevoice/text/symbols.py:410-412
 PERIODS = (2, 3, 5, 7, 11)
@@ -398,6 +399,13 @@ class SynthesizerTrn(ParamTree):
         return ops.take_channels(y4, 1)
 
     # ---------------------------------------------------------------------------------------------
+    def _side_stream(self, device):
+        st = self.__dict__.get("_side")
+        if st is None or st.device != device:
+            st = torch.cuda.Stream(device=device)
+            self.__dict__["_side"] = st
+        return st
+
     def forward_cl(self, ssl, spec, lengths, text, text_lengths, noise=None, ids_slice=None):
         """Channels-last forward.  ssl [B,T,768], spec [B,T,1025] (pitch may be padded), lengths/text_lengths int32 [B],
         text int64 [B,X].  Returns a dict of channels-last tensors (same quantities as SynthesizerTrn.forward)."""
@@ -420,7 +428,21 @@ class SynthesizerTrn(ParamTree):
             embed = self.P("quantizer.vq.layers.0._codebook.embed")
             codes = ops.vq_nearest(s, embed)                                     # [B, T/2] int64
             quantized = ops.embedding(embed, codes, rep=2)                       # nearest x2 (models.py:924-927)
-        stats_p = self._enc_p(quantized, lengths, text, text_lengths, ge)
+        # The prior encoder (12 attention layers of small kernels, none of which fills the GPU) only meets the rest of the
+        # step again at the KL loss: run it on a side stream so that it overlaps the posterior encoder / flow / generator
+        # (forward AND backward: autograd runs each node on its forward stream).  Inside a captured CUDA graph the fork/join
+        # becomes two parallel branches.
+        side = self._side_stream(spec.device) if SIDE_STREAMS else None
+        if side is not None:
+            cur = torch.cuda.current_stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                stats_p = self._enc_p(quantized, lengths, text, text_lengths, ge)
+            for t in (quantized, ge):
+                t.record_stream(side)
+            stats_p.record_stream(cur)
+        else:
+            stats_p = self._enc_p(quantized, lengths, text, text_lengths, ge)
         m_p, logs_p = stats_p[:, :, :I], stats_p[:, :, I:]
         # enc_q, models.py:348-359
         spec_w = ops.widen_to_pitch(spec)      # [B,T,1028]: the 3 pitch columns are zero, enc_q.pre's packed weight is padded alike
@@ -447,6 +469,8 @@ class SynthesizerTrn(ParamTree):
             ids_slice = ops.rand_slice_ids(lengths, seg)
         z_slice = ops.slice_rows(z, ids_slice, seg)
         o = self._generator(z_slice, ge)                                         # [B, seg*hop, 1]
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
         return dict(y_hat=o, ids_slice=ids_slice, z=z, z_p=z_p, m_p=m_p, logs_p=logs_p, m_q=m_q, logs_q=logs_q,
                     quantized=quantized, codes=codes, ge=ge, lengths=lengths)
 
