@@ -34,9 +34,23 @@ struct FlashArgs {
 };
 
 __device__ __forceinline__ bool allowed(int i, int j, int X, int xl, int yl) {
-  return (j < X) ? (j < xl) : ((j - X) < yl && j <= i);
+  const bool text = j < xl, audio = ((j - X) < yl) & (j <= i);       // both evaluated: selects, no divergent branch
+  return (j < X) ? text : audio;
+}
+// Is EVERY (query i0.., key j0..) pair of a BT x BT tile visible?  Then the per-element mask (a third of the round-1
+// kernels' instructions: ISETP/FSETP/BRA/BSSY, see profiles/r2_ncu_before_epilogue_fix.md) is skipped for the tile -- all
+// but the tiles on the causal diagonal and on the x_len / y_len / prefix boundaries.
+__device__ __forceinline__ bool tile_full(int i0, int j0, int X, int xl, int yl) {
+  const int j1 = j0 + BT - 1;
+  if (j1 < X) return j1 < xl;                                         // text keys only: visible to every query
+  if (j0 >= X) return ((j1 - X) < yl) & (j1 <= i0);                   // audio keys only: every query row is >= i0 >= j1
+  return false;                                                       // straddles the prefix boundary
 }
 
+// Probability dropout.  One 32-bit hash now decides a 2 x 2 block of (query, key) pairs through four 16-bit fields
+// (drop iff field < round(p * 65536); p = 0.1 -> 0.100006), where round 1 hashed every element separately (10..15 integer
+// instructions per element in kernels whose useful work is ~20).  Forward and both backward kernels regenerate the same
+// mask from (seed, offset, stream id, b, h, i, j); nothing is stored.
 struct DropKey { uint32_t s0, s1, thr; float inv; };
 __device__ __forceinline__ DropKey drop_key(const FlashArgs& a) {
   DropKey d{0u, 0u, 0u, 1.f};
@@ -44,20 +58,30 @@ __device__ __forceinline__ DropKey drop_key(const FlashArgs& a) {
     Philox ph(a.rng[0]);
     uint4 r = ph(a.rng[1], a.sid);
     d.s0 = r.x; d.s1 = r.y;
-    d.thr = (uint32_t)fminf(a.p_drop * 4294967296.f, 4294967040.f);
+    d.thr = (uint32_t)fminf(a.p_drop * 65536.f + 0.5f, 65535.f);
     d.inv = 1.f / (1.f - a.p_drop);
   }
   return d;
 }
-__device__ __forceinline__ uint32_t drop_row(const DropKey& d, uint32_t row) {
-  uint32_t x = row * 0x9E3779B1u + d.s0;
+// hash of a PAIR of query rows: index = z * ceil(L / 2) + (i >> 1)
+__device__ __forceinline__ uint32_t drop_row(const DropKey& d, uint32_t rowpair) {
+  uint32_t x = rowpair * 0x9E3779B1u + d.s0;
   x ^= x >> 15; x *= 0x85EBCA77u; x ^= x >> 13;
   return x;
 }
-__device__ __forceinline__ bool drop_keep(const DropKey& d, uint32_t rowh, uint32_t col) {
-  uint32_t x = rowh ^ (col * 0xC2B2AE3Du + d.s1);
+// 32 bits for rows (2r, 2r+1) x columns (2c, 2c+1): even row = the value itself, odd row = one more mixing round
+__device__ __forceinline__ uint32_t drop_block(const DropKey& d, uint32_t rowh, uint32_t colpair) {
+  uint32_t x = rowh ^ (colpair * 0xC2B2AE3Du + d.s1);
   x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
-  return x >= d.thr;
+  return x;
+}
+__device__ __forceinline__ uint32_t drop_odd(uint32_t x) { x *= 0x9E3779B1u; return x ^ (x >> 15); }
+// keep flags of (row i, cols j, j+1), j even
+__device__ __forceinline__ void drop_pair(const DropKey& d, uint32_t rowh, int i, int j, bool& k0, bool& k1) {
+  uint32_t x = drop_block(d, rowh, (uint32_t)j >> 1);
+  if (i & 1) x = drop_odd(x);
+  k0 = (x & 0xffffu) >= d.thr;
+  k1 = (x >> 16) >= d.thr;
 }
 
 // stage a [BT x 32] tile (rows r0.., zero-filled past L) into smem with pitch LDT: 128 threads, 4 x 16 B each
@@ -152,7 +176,7 @@ __device__ __forceinline__ int key_tiles(int i0, int L, int X, int yl) {
 
 // ------------------------------------------------------------------------------------------------
 template <bool PR>
-__global__ void __launch_bounds__(128) flash_fwd_kernel(FlashArgs a) {
+__global__ void __launch_bounds__(128, 5) flash_fwd_kernel(FlashArgs a) {
   __shared__ __align__(16) float sK[2][BT * LDT];
   __shared__ __align__(16) float sV[2][BT * LDT];
   const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * BT;
@@ -167,8 +191,8 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(FlashArgs a) {
   float qa[4][4];
   load_a_frags(qa, Q, a.ld, i0 + warp * 16, L);
   const int ra = i0 + warp * 16 + gq, rb = ra + 8;
-  const uint32_t z = (uint32_t)(b * a.H + h);
-  const uint32_t rha = drop_row(dkey, z * (uint32_t)L + (uint32_t)ra), rhb = drop_row(dkey, z * (uint32_t)L + (uint32_t)rb);
+  const uint32_t z = (uint32_t)(b * a.H + h), Lh = (uint32_t)(L + 1) >> 1;
+  const uint32_t rha = drop_row(dkey, z * Lh + ((uint32_t)ra >> 1)), rhb = drop_row(dkey, z * Lh + ((uint32_t)rb >> 1));
 
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   float acc[4][4];
@@ -192,13 +216,19 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(FlashArgs a) {
     gemm_nt<PR>(s, qa, sK[cur]);
     const int j0 = kt * BT;
     float mx0 = m0, mx1 = m1;
+    const bool full = tile_full(i0, j0, X, xl, yl);              // CTA-uniform: interior tiles skip the mask arithmetic
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      const int j = j0 + nt * 8 + 2 * t;
-      s[nt][0] = allowed(ra, j, X, xl, yl) ? s[nt][0] * sl2 : -INFINITY;
-      s[nt][1] = allowed(ra, j + 1, X, xl, yl) ? s[nt][1] * sl2 : -INFINITY;
-      s[nt][2] = allowed(rb, j, X, xl, yl) ? s[nt][2] * sl2 : -INFINITY;
-      s[nt][3] = allowed(rb, j + 1, X, xl, yl) ? s[nt][3] * sl2 : -INFINITY;
+      bool ok0 = true, ok1 = true, ok2 = true, ok3 = true;
+      if (!full) {
+        const int j = j0 + nt * 8 + 2 * t;
+        ok0 = allowed(ra, j, X, xl, yl); ok1 = allowed(ra, j + 1, X, xl, yl);
+        ok2 = allowed(rb, j, X, xl, yl); ok3 = allowed(rb, j + 1, X, xl, yl);
+      }
+      s[nt][0] = ok0 ? s[nt][0] * sl2 : -INFINITY;
+      s[nt][1] = ok1 ? s[nt][1] * sl2 : -INFINITY;
+      s[nt][2] = ok2 ? s[nt][2] * sl2 : -INFINITY;
+      s[nt][3] = ok3 ? s[nt][3] * sl2 : -INFINITY;
       mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
       mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
     }
@@ -214,10 +244,13 @@ __global__ void __launch_bounds__(128) flash_fwd_kernel(FlashArgs a) {
       float p0 = exp2f(s[nt][0] - e0), p1 = exp2f(s[nt][1] - e0), p2 = exp2f(s[nt][2] - e1), p3 = exp2f(s[nt][3] - e1);
       rs0 += p0 + p1; rs1 += p2 + p3;
       if (dkey.thr) {
-        p0 = drop_keep(dkey, rha, j) ? p0 * dkey.inv : 0.f;
-        p1 = drop_keep(dkey, rha, j + 1) ? p1 * dkey.inv : 0.f;
-        p2 = drop_keep(dkey, rhb, j) ? p2 * dkey.inv : 0.f;
-        p3 = drop_keep(dkey, rhb, j + 1) ? p3 * dkey.inv : 0.f;
+        bool k0, k1, k2, k3;
+        drop_pair(dkey, rha, ra, j, k0, k1);
+        drop_pair(dkey, rhb, rb, j, k2, k3);
+        p0 = k0 ? p0 * dkey.inv : 0.f;
+        p1 = k1 ? p1 * dkey.inv : 0.f;
+        p2 = k2 ? p2 * dkey.inv : 0.f;
+        p3 = k3 ? p3 * dkey.inv : 0.f;
       }
       s[nt][0] = p0; s[nt][1] = p1; s[nt][2] = p2; s[nt][3] = p3;
     }
@@ -256,7 +289,7 @@ __global__ void flash_delta_kernel(FlashArgs a) {
 }
 
 template <bool PR>
-__global__ void __launch_bounds__(128) flash_dq_kernel(FlashArgs a) {
+__global__ void __launch_bounds__(128, 3) flash_dq_kernel(FlashArgs a) {
   __shared__ __align__(16) float sK[2][BT * LDT];
   __shared__ __align__(16) float sV[2][BT * LDT];
   const int b = blockIdx.z, h = blockIdx.y, i0 = blockIdx.x * BT;
@@ -274,7 +307,8 @@ __global__ void __launch_bounds__(128) flash_dq_kernel(FlashArgs a) {
   load_a_frags(qa, Q, a.ld, i0 + warp * 16, L);
   load_a_frags(da, dO, a.lddo, i0 + warp * 16, L);
   const int ra = i0 + warp * 16 + gq, rb = ra + 8;
-  const uint32_t rha = drop_row(dkey, z * (uint32_t)L + (uint32_t)ra), rhb = drop_row(dkey, z * (uint32_t)L + (uint32_t)rb);
+  const uint32_t Lh = (uint32_t)(L + 1) >> 1;
+  const uint32_t rha = drop_row(dkey, z * Lh + ((uint32_t)ra >> 1)), rhb = drop_row(dkey, z * Lh + ((uint32_t)rb >> 1));
   const float* lse = a.lse + (size_t)z * L;
   const float* dl = a.delta + (size_t)z * L;
   const float lse0 = ra < L ? lse[ra] : 0.f, lse1 = rb < L ? lse[rb] : 0.f;
@@ -300,15 +334,22 @@ __global__ void __launch_bounds__(128) flash_dq_kernel(FlashArgs a) {
     gemm_nt<PR>(s, qa, sK[cur]);
     gemm_nt<PR>(dp, da, sV[cur]);
     const int j0 = kt * BT;
+    const bool full = tile_full(i0, j0, X, xl, yl);              // CTA-uniform
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       const int j = j0 + nt * 8 + 2 * t;
+      bool keep[4] = {true, true, true, true};
+      if (dkey.thr) {
+        drop_pair(dkey, rha, ra, j, keep[0], keep[1]);
+        drop_pair(dkey, rhb, rb, j, keep[2], keep[3]);
+      }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int i = (e < 2) ? ra : rb, jj = j + (e & 1);
-        float p = allowed(i, jj, X, xl, yl) ? exp2f(s[nt][e] * sl2 - ((e < 2) ? lse0 : lse1)) : 0.f;
+        float p = exp2f(s[nt][e] * sl2 - ((e < 2) ? lse0 : lse1));
+        if (!full) p = allowed(i, jj, X, xl, yl) ? p : 0.f;
         float g = dp[nt][e];
-        if (dkey.thr) g = drop_keep(dkey, (e < 2) ? rha : rhb, jj) ? g * dkey.inv : 0.f;
+        if (dkey.thr) g = keep[e] ? g * dkey.inv : 0.f;
         s[nt][e] = p * (g - ((e < 2) ? d0 : d1));
       }
     }
@@ -324,10 +365,11 @@ __global__ void __launch_bounds__(128) flash_dq_kernel(FlashArgs a) {
 }
 
 template <bool PR>
-__global__ void __launch_bounds__(128) flash_dkv_kernel(FlashArgs a) {
+__global__ void __launch_bounds__(128, 3) flash_dkv_kernel(FlashArgs a) {
   __shared__ __align__(16) float sQ[2][BT * LDT];
   __shared__ __align__(16) float sD[2][BT * LDT];
   __shared__ float sL[2][BT], sDl[2][BT];
+  __shared__ uint32_t sRh[2][BT / 2];                              // dropout hashes of the query-row pairs of the staged tile
   const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * BT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
   const int L = a.L, X = a.X;
@@ -361,6 +403,9 @@ __global__ void __launch_bounds__(128) flash_dkv_kernel(FlashArgs a) {
       int i = qt * BT + threadIdx.x;
       sL[buf][threadIdx.x] = i < L ? lse[i] : 0.f;
       sDl[buf][threadIdx.x] = i < L ? dl[i] : 0.f;
+    } else if (threadIdx.x < BT + BT / 2) {
+      const int r = threadIdx.x - BT;
+      sRh[buf][r] = drop_row(dkey, z * ((uint32_t)(L + 1) >> 1) + (uint32_t)(qt * (BT / 2) + r));
     }
   };
   const bool dead = (j0 >= X + yl) && (j0 >= X);   // every key of the tile is padding: gradients are zero
@@ -377,20 +422,31 @@ __global__ void __launch_bounds__(128) flash_dkv_kernel(FlashArgs a) {
       gemm_nt<PR>(s, ka, sQ[cur]);      // S^T[key][query]
       gemm_nt<PR>(dp, va, sD[cur]);     // dPd^T[key][query]
       const int i0 = qt * BT;
+      const bool full = (i0 + BT <= L) && tile_full(i0, j0, X, xl, yl);   // CTA-uniform
       float pd[8][4];
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
+        const int ile = nt * 8 + 2 * t;                              // even local query index: rows (ile, ile + 1) share a hash
+        bool keep[4] = {true, true, true, true};
+        if (dkey.thr) {
+          const uint32_t rowh = sRh[cur][ile >> 1];
+          const uint32_t xa = drop_block(dkey, rowh, (uint32_t)ja >> 1), xb = drop_block(dkey, rowh, (uint32_t)jb >> 1);
+          const uint32_t sa = (ja & 1) ? 16u : 0u, sb = (jb & 1) ? 16u : 0u;
+          keep[0] = ((xa >> sa) & 0xffffu) >= dkey.thr;
+          keep[1] = ((drop_odd(xa) >> sa) & 0xffffu) >= dkey.thr;
+          keep[2] = ((xb >> sb) & 0xffffu) >= dkey.thr;
+          keep[3] = ((drop_odd(xb) >> sb) & 0xffffu) >= dkey.thr;
+        }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int il = nt * 8 + 2 * t + (e & 1), i = i0 + il, j = (e < 2) ? ja : jb;
-          const bool ok = i < L && allowed(i, j, X, xl, yl);
-          float p = ok ? exp2f(s[nt][e] * sl2 - sL[cur][il]) : 0.f;
+          const int il = ile + (e & 1), i = i0 + il, j = (e < 2) ? ja : jb;
+          float p = exp2f(s[nt][e] * sl2 - sL[cur][il]);
+          if (!full) p = (i < L && allowed(i, j, X, xl, yl)) ? p : 0.f;
           float g = dp[nt][e];
           float pdv = p;
           if (dkey.thr) {
-            const bool keep = drop_keep(dkey, drop_row(dkey, z * (uint32_t)L + (uint32_t)i), (uint32_t)j);
-            g = keep ? g * dkey.inv : 0.f;
-            pdv = keep ? p * dkey.inv : 0.f;
+            g = keep[e] ? g * dkey.inv : 0.f;
+            pdv = keep[e] ? p * dkey.inv : 0.f;
           }
           pd[nt][e] = pdv;
           s[nt][e] = p * (g - sDl[cur][il]);

@@ -576,10 +576,9 @@ int gemm_tma_run(const evk_gconv_desc* d, int phases, long long x_ps, const int*
     p.M = (int)rows; p.Z = 1; p.y_sb = 0; p.r_sb = 0;
     o.A = d->x; o.lda = d->ldx; o.a_sb = 0; o.a_rows = rows;
   } else {                                                  // stride-1 tap sum: one TMA box per (tap, channel block), OOB rows = padding
-    // 16-channel layers (generator stage 4: T = 20 480 positions x 16 channels) run here too: the 32-float K box is half
-    // out of range (zero-filled by the copy engine, not fetched), the layer is HBM-bound either way and the staged-slab
-    // tcgen05 kernel of round 1 reached only ~1.2 TB/s on it
-    if (npos < 64 || (long long)d->Z * npos < 1024 || d->C < 16 || d->N < 16 || npos > 0x7fffffff) return 1;
+    // 16-channel layers stay on gconv_tc_kernel: routed here (half of every 32-float K box out of range) the generator's
+    // stage-4 convs measured 56 us against 36 us there (profiles/r2_bench_history.md)
+    if (npos < 64 || (long long)d->Z * npos < 1024 || d->C < 32 || d->N < 32 || npos > 0x7fffffff) return 1;
     p.M = (int)npos; p.Z = d->Z; p.y_sb = d->y_sb; p.r_sb = d->r_sb;
     o.A = d->x; o.lda = d->ldx; o.a_sb = d->x_sb; o.a_rows = in_rows;
   }

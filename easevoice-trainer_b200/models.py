@@ -17,7 +17,7 @@ from torch import nn
 
 from . import ops
 
-SIDE_STREAMS = os.environ.get("EVK_SIDE_STREAMS", "0") == "1"
+SIDE_STREAMS = os.environ.get("EVK_SIDE_STREAMS", "1") != "0"     # prior encoder on a side stream (measured 66.5 -> 63.0 ms / step)
 LRELU_SLOPE = 0.1
 N_SYMBOLS = 732            # len(SYMBOLS): src/easevoice/text/symbols.py:410-412
 PERIODS = (2, 3, 5, 7, 11)
