@@ -33,6 +33,14 @@ struct FlashArgs {
   const unsigned long long* rng; unsigned long long sid;
 };
 
+// 2^x on the SFU without ex2()'s range handling (ex2.approx.ftz: 2^-22 relative error, 2^-inf = 0): the kernels evaluate it
+// for every score and are issue-bound
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ bool allowed(int i, int j, int X, int xl, int yl) {
   const bool text = j < xl, audio = ((j - X) < yl) & (j <= i);       // both evaluated: selects, no divergent branch
   return (j < X) ? text : audio;
@@ -235,13 +243,13 @@ __global__ void __launch_bounds__(128, 5) flash_fwd_kernel(FlashArgs a) {
     mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1)); mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
     mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1)); mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
     const float e0 = (mx0 == -INFINITY) ? 0.f : mx0, e1 = (mx1 == -INFINITY) ? 0.f : mx1;
-    const float c0 = exp2f(m0 - e0), c1 = exp2f(m1 - e1);      // m == -inf -> 0
+    const float c0 = ex2(m0 - e0), c1 = ex2(m1 - e1);      // m == -inf -> 0
     m0 = mx0; m1 = mx1;
     float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
       const int j = j0 + nt * 8 + 2 * t;
-      float p0 = exp2f(s[nt][0] - e0), p1 = exp2f(s[nt][1] - e0), p2 = exp2f(s[nt][2] - e1), p3 = exp2f(s[nt][3] - e1);
+      float p0 = ex2(s[nt][0] - e0), p1 = ex2(s[nt][1] - e0), p2 = ex2(s[nt][2] - e1), p3 = ex2(s[nt][3] - e1);
       rs0 += p0 + p1; rs1 += p2 + p3;
       if (dkey.thr) {
         bool k0, k1, k2, k3;
@@ -346,7 +354,7 @@ __global__ void __launch_bounds__(128, 3) flash_dq_kernel(FlashArgs a) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int i = (e < 2) ? ra : rb, jj = j + (e & 1);
-        float p = exp2f(s[nt][e] * sl2 - ((e < 2) ? lse0 : lse1));
+        float p = ex2(s[nt][e] * sl2 - ((e < 2) ? lse0 : lse1));
         if (!full) p = allowed(i, jj, X, xl, yl) ? p : 0.f;
         float g = dp[nt][e];
         if (dkey.thr) g = keep[e] ? g * dkey.inv : 0.f;
@@ -440,7 +448,7 @@ __global__ void __launch_bounds__(128, 3) flash_dkv_kernel(FlashArgs a) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int il = ile + (e & 1), i = i0 + il, j = (e < 2) ? ja : jb;
-          float p = exp2f(s[nt][e] * sl2 - sL[cur][il]);
+          float p = ex2(s[nt][e] * sl2 - sL[cur][il]);
           if (!full) p = (i < L && allowed(i, j, X, xl, yl)) ? p : 0.f;
           float g = dp[nt][e];
           float pdv = p;
