@@ -396,7 +396,7 @@ def run_ours(args):
         #      (ops.profile_begin) and the library's own dispatch accounting telling which kernel family served each
         #      contraction; flops are the analytic 2*Z*J*P*N*C*Q of the descriptors the calls carried.
         ops.profile_begin()
-        st.step(batch)
+        st.step(batch, collectives=False)          # rank 0 alone: the profiled step must not enter the gradient all-reduces
         prof = ops.profile_end()
         tma_keys = [k for k in prof if "gemm_tma" in k or k.startswith("evk_gemm_tf32")]
         tma_ms = sum(prof[k]["ms"] for k in tma_keys)

@@ -25,6 +25,7 @@ using namespace evk;
 
 extern "C" const char* evk_last_error(void) { return g_err; }
 extern "C" int evk_version(void) { return 100; }
+extern "C" int evk_gconv_desc_size(void) { return (int)sizeof(evk_gconv_desc); }
 
 extern "C" int evk_init(void) {
   int dev = 0;

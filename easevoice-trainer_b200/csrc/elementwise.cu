@@ -287,8 +287,9 @@ __global__ void transpose_rows_multi_kernel(const float* __restrict__ x, int ldx
 //   dbias[c]  += sum_t g[t][c]                                  (atomics; one per column per block of TPB row tiles)
 constexpr int DYP_ROWS = 128;          // rows per block: 16 independent loads per thread in flight, one barrier
 __global__ void __launch_bounds__(256) dy_prep_kernel(const float* __restrict__ dy, int lddy, const float* __restrict__ yact, int ldy, int act,
-                                                      float slope, const int* __restrict__ len, int P, float* __restrict__ dpre, int ldp,
-                                                      float* __restrict__ dyt, int ldt, long long t_sb, float* __restrict__ dbias, int T, int C) {
+                                                      float slope, float gscale, const int* __restrict__ len, int P, float* __restrict__ dpre,
+                                                      int ldp, float* __restrict__ dyt, int ldt, long long t_sb, float* __restrict__ dbias, int T,
+                                                      int C) {
   __shared__ float tile[DYP_ROWS][33];
   __shared__ float csum[8][33];
   const int b = blockIdx.z, c0 = blockIdx.y * 32, t0 = blockIdx.x * DYP_ROWS, tx = threadIdx.x, ty = threadIdx.y;
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(256) dy_prep_kernel(const float* __restrict__ 
 #pragma unroll
   for (int k = 0; k < DYP_ROWS / 8; ++k) {
     const int t = t0 + ty + 8 * k;
-    float g = v[k];
+    float g = v[k] * gscale;
     if (act) g *= (act == EVK_ACT_LRELU) ? (o[k] > 0.f ? 1.f : slope) : (act == EVK_ACT_RELU) ? (o[k] > 0.f ? 1.f : 0.f) : (1.f - o[k] * o[k]);
     if (t >= lim) g = 0.f;
     if (dpre && c < C && t < T) dpre[(row0 + t) * ldp + c] = g;
@@ -602,15 +603,15 @@ extern "C" int evk_transpose_rows_multi(const float* x, int32_t ldx, int64_t x_s
 // dy [B][T][lddy] (T rows per batch item), yact = the conv's activated OUTPUT (nullable when act == 0), len (nullable int32 [B],
 // rows t >= len[b] * P are zeroed), outputs each nullable: dpre [B][T][ldp], dyt [B][C][ldt] (batch pitch t_sb), dbias [C]
 // (accumulated: zero it first).
-extern "C" int evk_dy_prep(const float* dy, int32_t lddy, const float* yact, int32_t ldy, int32_t act, float slope, const int32_t* len, int32_t P,
-                           float* dpre, int32_t ldp, float* dyt, int32_t ldt, int64_t t_sb, float* dbias, int32_t B, int32_t T, int32_t C,
-                           evk_stream_t stream) {
+extern "C" int evk_dy_prep(const float* dy, int32_t lddy, const float* yact, int32_t ldy, int32_t act, float slope, float gscale,
+                           const int32_t* len, int32_t P, float* dpre, int32_t ldp, float* dyt, int32_t ldt, int64_t t_sb, float* dbias,
+                           int32_t B, int32_t T, int32_t C, evk_stream_t stream) {
   EVK_REQUIRE(dy && (act == 0 || yact) && act >= 0 && act <= 3 && P >= 1 && (dpre || dyt || dbias), EVK_ERR_ARG, "dy_prep: bad arguments");
   EVK_REQUIRE(!dyt || ldt >= T, EVK_ERR_ARG, "dy_prep: ldt too small");
   if ((long long)B * T * C == 0) return EVK_OK;
   dim3 grid(cdiv(T, DYP_ROWS), cdiv(C, 32), B), block(32, 8);
   EVK_REQUIRE(grid.y <= 65535 && grid.z <= 65535, EVK_ERR_ARG, "dy_prep: grid too large");
-  dy_prep_kernel<<<grid, block, 0, ST>>>(dy, lddy, yact, ldy, act, slope, len, P, dpre, ldp, dyt, ldt, t_sb, dbias, T, C);
+  dy_prep_kernel<<<grid, block, 0, ST>>>(dy, lddy, yact, ldy, act, slope, gscale, len, P, dpre, ldp, dyt, ldt, t_sb, dbias, T, C);
   return check_launch("dy_prep");
 }
 extern "C" int evk_phase_split(const float* x, int32_t ldx, int64_t x_sb, float* xs, int64_t xs_ps, int32_t B, int32_t T, int32_t P,

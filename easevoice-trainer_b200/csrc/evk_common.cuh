@@ -109,6 +109,34 @@ struct Philox {
     return make_uint4(c0, c1, c2, c3);
   }
 };
+// Cheap counter-based dropout for FUSED kernels (GEMM epilogue, LayerNorm): one hash decides a group of 4 consecutive elements
+// through four 16-bit fields (drop iff field < round(p * 65536)).  Key = Philox(seed)(offset, stream id) read from the
+// device-resident RNG state, so it is CUDA-graph safe and changes every step like the stand-alone dropout kernel.
+struct DropK { uint32_t k0, k1, thr; float inv; };
+__device__ __forceinline__ DropK dropk_make(const unsigned long long* rng, unsigned long long sid, float p) {
+  DropK d{0u, 0u, 0u, 1.f};
+  if (p > 0.f) {
+    Philox ph(rng[0]);
+    const uint4 r = ph(rng[1], sid);
+    d.k0 = r.x; d.k1 = r.y;
+    d.thr = (uint32_t)fminf(p * 65536.f + 0.5f, 65535.f);
+    d.inv = 1.f / (1.f - p);
+  }
+  return d;
+}
+// scale factors (0 or 1/(1-p)) of the 4 elements of group g4 (= linear element index / 4)
+__device__ __forceinline__ void dropk_scale4(const DropK& d, unsigned long long g4, float (&m)[4]) {
+  uint32_t x = (uint32_t)g4 * 0x9E3779B1u + d.k0;
+  x ^= (uint32_t)(g4 >> 32) * 0x85EBCA77u;
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  uint32_t y = (x + d.k1) * 0x9E3779B1u;
+  y ^= y >> 15;
+  m[0] = (x & 0xffffu) >= d.thr ? d.inv : 0.f;
+  m[1] = (x >> 16) >= d.thr ? d.inv : 0.f;
+  m[2] = (y & 0xffffu) >= d.thr ? d.inv : 0.f;
+  m[3] = (y >> 16) >= d.thr ? d.inv : 0.f;
+}
+
 __device__ __forceinline__ float u32_to_unit(uint32_t x) { return (x >> 8) * (1.0f / 16777216.0f); }  // [0,1)
 
 }  // namespace evk

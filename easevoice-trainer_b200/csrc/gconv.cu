@@ -450,9 +450,11 @@ extern "C" int evk_gconv_fwd(const evk_gconv_desc* d, evk_stream_t stream) {
   if (g_backend_tc && !g_precise && (d->ldx % 4) == 0) {
     rc = gemm_tma_try(d, st);          // TMA-fed persistent tcgen05 GEMM / implicit-GEMM conv
     if (rc <= 0) { if (rc == 0) g_disp_flops[0] += desc_flops(d); return rc; }
+    EVK_REQUIRE(!(d->drop_rng && d->drop_p > 0.f), EVK_ERR_UNSUPPORTED, "gconv_fwd: fused dropout needs a launch the TMA kernel takes");
     rc = gconv_tc_try(d, st);
     if (rc <= 0) { if (rc == 0) g_disp_flops[1] += desc_flops(d); return rc; }
   }
+  EVK_REQUIRE(!(d->drop_rng && d->drop_p > 0.f), EVK_ERR_UNSUPPORTED, "gconv_fwd: fused dropout needs a launch the TMA kernel takes");
   g_disp_flops[2] += desc_flops(d);
   // pick the N tile with the least padding (prefer wide)
   const int N = p.N;

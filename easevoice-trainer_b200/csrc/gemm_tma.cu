@@ -45,6 +45,7 @@ struct GemmP {
   // a_bytes = bytes the TMA loads of one A stage deliver (expect_tx), slab mode: off_min, span rows after the MT*128-row box
   int SA, SB, a_stage, a_bytes, slab, off_min;
   float comp;                                        // accumulator scale compensating the tensor core's operand TRUNCATION (see run_gemm)
+  const unsigned long long* drop_rng; unsigned long long drop_sid; float drop_p;   // fused dropout after the activation (0: off)
 };
 
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -305,6 +306,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
     float* tr = epi_s + ew * (32 * 36);
     const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
     const float comp = p.comp;
+    const DropK dropk = dropk_make(p.drop_rng, p.drop_sid, p.drop_p);
     int tcount = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
       const int outer = tile / tiles_mn, mn = tile - outer * tiles_mn;
@@ -380,6 +382,11 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
               else if (p.act == EVK_ACT_RELU) t[e] = fmaxf(t[e], 0.f);
               else if (p.act == EVK_ACT_TANH) t[e] = tanhf(t[e]);
               if (!keep[i]) t[e] = 0.f;
+            }
+            if (dropk.thr) {                                     // group index = offset of the float4 in the output tensor / 4
+              float m[4];
+              dropk_scale4(dropk, (unsigned long long)(dp - p.d) >> 2, m);
+              t[0] *= m[0]; t[1] *= m[1]; t[2] *= m[2]; t[3] *= m[3];
             }
             if (full4 && ((reinterpret_cast<uintptr_t>(dp) & 15) == 0)) {
               *reinterpret_cast<float4*>(dp) = make_float4(t[0], t[1], t[2], t[3]);
@@ -560,6 +567,8 @@ int gemm_tma_run(const evk_gconv_desc* d, int phases, long long x_ps, const int*
   p.d = d->y; p.ldd = d->ldy; p.bias = d->bias; p.res = d->res; p.ldr = d->ldr;
   p.N = d->N; p.K = d->C; p.act = d->act; p.slope = d->slope; p.atomic = 0;
   p.Q = d->Q; p.P = d->P; p.out_len = d->out_len; p.os = d->os; p.o0 = d->o0;
+  p.drop_rng = reinterpret_cast<const unsigned long long*>(d->drop_rng); p.drop_sid = d->drop_sid; p.drop_p = d->drop_rng ? d->drop_p : 0.f;
+  if (p.drop_p > 0.f && ((d->N % 4) || (d->ldy % 4) || (d->y_sb % 4))) return 1;     // the mask is keyed by float4 groups of the output
   for (int i = 0; i < EVK_MAX_TAPS; ++i) {
     p.off[i] = i < d->Q ? d->off[i] : 0;
     p.src[i] = (src && i < d->Q) ? src[i] : 0;

@@ -77,6 +77,134 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ x, int ldx, const
   }
 }
 
+// ---- LayerNorm(x + dropout(res)) with the dropout fused (stage-1 GPT: transformer.py:300-315) --------------------------
+// One warp per row, float4 per lane (C % 4 == 0, C <= 2048, contiguous rows).  The dropout scale factors come from
+// dropk_scale4 keyed by the float4's linear index, so the backward regenerates the identical mask.
+constexpr int LND_MAXV = 4;            // float4 per lane: C <= 512 (the GPT's model width); fixed trip counts keep everything in registers
+__global__ void __launch_bounds__(256) layernorm_drop_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ res,
+                                                                 const float4* __restrict__ gamma, const float4* __restrict__ beta, float eps,
+                                                                 float p, const unsigned long long* __restrict__ rng, unsigned long long sid,
+                                                                 float4* __restrict__ y, float* __restrict__ stats, long long rows, int C4) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const DropK dk = dropk_make(rng, sid, p);
+  float4 v[LND_MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < LND_MAXV; ++i) {
+    const int c = lane + 32 * i;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C4) {
+      const long long g4 = row * C4 + c;
+      float4 t = x[g4];
+      const float4 r = res[g4];
+      float m[4];
+      dropk_scale4(dk, (unsigned long long)g4, m);
+      t.x += r.x * m[0]; t.y += r.y * m[1]; t.z += r.z * m[2]; t.w += r.w * m[3];
+      v[i] = t;
+      s += t.x + t.y + t.z + t.w;
+    }
+  }
+  s = warp_sum(s);
+  const float mean = s / (float)(4 * C4);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < LND_MAXV; ++i)
+    if (lane + 32 * i < C4) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += a * a + b * b + c * c + d * d;
+    }
+  q = warp_sum(q);
+  const float rstd = rsqrtf(q / (float)(4 * C4) + eps);
+#pragma unroll
+  for (int i = 0; i < LND_MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < C4) {
+      const float4 g = gamma[c], b = beta[c], t = v[i];
+      y[row * C4 + c] = make_float4((t.x - mean) * rstd * g.x + b.x, (t.y - mean) * rstd * g.y + b.y, (t.z - mean) * rstd * g.z + b.z,
+                                    (t.w - mean) * rstd * g.w + b.w);
+    }
+  }
+  if (lane == 0) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
+}
+
+__global__ void __launch_bounds__(256) layernorm_drop_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ res,
+                                                                 const float4* __restrict__ gamma, const float* __restrict__ stats,
+                                                                 const float4* __restrict__ dy, float p, const unsigned long long* __restrict__ rng,
+                                                                 unsigned long long sid, float4* __restrict__ dx, float4* __restrict__ dres,
+                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C4,
+                                                                 int rows_per_block) {
+  extern __shared__ float sm[];              // [2][C] partial dgamma/dbeta of this block
+  const int C = 4 * C4;
+  float* sg = sm;
+  float* sb = sm + C;
+  for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) sm[c] = 0.f;
+  __syncthreads();
+  const DropK dk = dropk_make(rng, sid, p);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(rows, r0 + rows_per_block);
+  float4 ag[LND_MAXV], ab[LND_MAXV];         // this warp's dgamma / dbeta partial sums over its rows (registers, flushed once)
+#pragma unroll
+  for (int i = 0; i < LND_MAXV; ++i) { ag[i] = make_float4(0.f, 0.f, 0.f, 0.f); ab[i] = ag[i]; }
+  for (long long row = r0 + wid; row < r1; row += nw) {
+    const float mean = stats[row * 2], rstd = stats[row * 2 + 1];
+    float4 xh[LND_MAXV], gd[LND_MAXV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LND_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      xh[i] = make_float4(0.f, 0.f, 0.f, 0.f); gd[i] = xh[i];
+      if (c < C4) {
+        const long long g4 = row * C4 + c;
+        float4 t = x[g4];
+        const float4 r = res[g4];
+        float m[4];
+        dropk_scale4(dk, (unsigned long long)g4, m);
+        t.x += r.x * m[0]; t.y += r.y * m[1]; t.z += r.z * m[2]; t.w += r.w * m[3];
+        const float4 h = make_float4((t.x - mean) * rstd, (t.y - mean) * rstd, (t.z - mean) * rstd, (t.w - mean) * rstd);
+        const float4 d = dy[g4], gm = gamma[c];
+        const float4 g = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
+        xh[i] = h; gd[i] = g;
+        s1 += g.x + g.y + g.z + g.w;
+        s2 += g.x * h.x + g.y * h.y + g.z * h.z + g.w * h.w;
+        ag[i].x += d.x * h.x; ag[i].y += d.y * h.y; ag[i].z += d.z * h.z; ag[i].w += d.w * h.w;
+        ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+      }
+    }
+    s1 = warp_sum(s1) / (float)C;
+    s2 = warp_sum(s2) / (float)C;
+#pragma unroll
+    for (int i = 0; i < LND_MAXV; ++i) {
+      const int c = lane + 32 * i;
+      if (c < C4) {
+        const long long g4 = row * C4 + c;
+        const float4 h = xh[i], g = gd[i];
+        const float4 o = make_float4(rstd * (g.x - s1 - h.x * s2), rstd * (g.y - s1 - h.y * s2), rstd * (g.z - s1 - h.z * s2),
+                                     rstd * (g.w - s1 - h.w * s2));
+        dx[g4] = o;
+        float m[4];
+        dropk_scale4(dk, (unsigned long long)g4, m);
+        dres[g4] = make_float4(o.x * m[0], o.y * m[1], o.z * m[2], o.w * m[3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < LND_MAXV; ++i) {
+    const int c = lane + 32 * i;
+    if (c < C4) {
+      atomicAdd(&sg[4 * c], ag[i].x); atomicAdd(&sg[4 * c + 1], ag[i].y); atomicAdd(&sg[4 * c + 2], ag[i].z); atomicAdd(&sg[4 * c + 3], ag[i].w);
+      atomicAdd(&sb[4 * c], ab[i].x); atomicAdd(&sb[4 * c + 1], ab[i].y); atomicAdd(&sb[4 * c + 2], ab[i].z); atomicAdd(&sb[4 * c + 3], ab[i].w);
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    atomicAdd(&dgamma[c], sg[c]);
+    atomicAdd(&dbeta[c], sb[c]);
+  }
+}
+
 // ---- weight-norm + pack ------------------------------------------------------------------
 // block per d0: w[d0][d1][q] = v * (g[d0] / ||v[d0]||);  PA[q][d0][d1], PB[q][d1][d0]
 // round_tf32: weights are rounded to TF32 (round-to-nearest) here, once, so the tensor-core kernels can stage them
@@ -186,6 +314,32 @@ extern "C" int evk_layernorm_bwd(const float* x, int32_t ldx, const float* res, 
   layernorm_bwd_kernel<<<cdiv(rows, rpb), 256, 2 * C * sizeof(float), ST>>>(x, ldx, res, ldr, gamma, stats, dy, lddy, dx,
                                                                             lddx, dgamma, dbeta, rows, C, rpb);
   return check_launch("layernorm_bwd");
+}
+
+extern "C" int evk_layernorm_drop_fwd(const float* x, const float* res, const float* gamma, const float* beta, float eps, float p,
+                                      const uint64_t* rng, uint64_t sid, float* y, float* stats, int64_t rows, int32_t C, evk_stream_t stream) {
+  EVK_REQUIRE(x && res && gamma && beta && y && stats && rng, EVK_ERR_ARG, "layernorm_drop_fwd: null tensor");
+  EVK_REQUIRE(C >= 4 && (C % 4) == 0 && C <= 128 * LND_MAXV && p >= 0.f && p < 1.f, EVK_ERR_UNSUPPORTED, "layernorm_drop_fwd: C=%d p=%f unsupported", C, p);
+  EVK_REQUIRE(((((uintptr_t)x) | ((uintptr_t)res) | ((uintptr_t)gamma) | ((uintptr_t)beta) | ((uintptr_t)y)) & 15) == 0, EVK_ERR_ARG,
+              "layernorm_drop_fwd: tensors must be 16-byte aligned");
+  if (rows == 0) return EVK_OK;
+  layernorm_drop_fwd_kernel<<<cdiv(rows, 8), 256, 0, ST>>>((const float4*)x, (const float4*)res, (const float4*)gamma, (const float4*)beta, eps, p,
+                                                           (const unsigned long long*)rng, sid, (float4*)y, stats, rows, C / 4);
+  return check_launch("layernorm_drop_fwd");
+}
+
+extern "C" int evk_layernorm_drop_bwd(const float* x, const float* res, const float* gamma, const float* stats, const float* dy, float p,
+                                      const uint64_t* rng, uint64_t sid, float* dx, float* dres, float* dgamma, float* dbeta, int64_t rows,
+                                      int32_t C, evk_stream_t stream) {
+  EVK_REQUIRE(x && res && gamma && stats && dy && dx && dres && dgamma && dbeta && rng, EVK_ERR_ARG, "layernorm_drop_bwd: null tensor");
+  EVK_REQUIRE(C >= 4 && (C % 4) == 0 && C <= 128 * LND_MAXV, EVK_ERR_UNSUPPORTED, "layernorm_drop_bwd: C=%d unsupported", C);
+  if (rows == 0) return EVK_OK;
+  int rpb = (int)((rows + 148 * 4 - 1) / (148 * 4));
+  if (rpb < 8) rpb = 8;
+  layernorm_drop_bwd_kernel<<<cdiv(rows, rpb), 256, 2 * C * sizeof(float), ST>>>((const float4*)x, (const float4*)res, (const float4*)gamma, stats,
+                                                                                 (const float4*)dy, p, (const unsigned long long*)rng, sid, (float4*)dx,
+                                                                                 (float4*)dres, dgamma, dbeta, rows, C / 4, rpb);
+  return check_launch("layernorm_drop_bwd");
 }
 
 extern "C" int evk_weight_pack(const float* v, const float* g, int32_t D0, int32_t D1, int32_t Q, float* pa,

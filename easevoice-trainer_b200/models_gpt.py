@@ -107,10 +107,12 @@ class Text2SemanticDecoder(ParamTree):
             qkv = ops.linear(h, self.w(p + "self_attn.in_proj", suffix="_weight"), self.P(p + "self_attn.in_proj_bias"))
             a = ops.flash_attention(qkv, heads=H, prefix=X, xlen=x_lens, ylen=y_lens, p_drop=p_attn, tag=f"{tagp}gpt.attn{i}")
             a = ops.linear(a, self.w(p + "self_attn.out_proj"), self.b(p + "self_attn.out_proj"))
-            h = ops.layernorm(h, self.P(p + "norm1.weight"), self.P(p + "norm1.bias"), res=self._drop(a, f"{tagp}gpt.d1.{i}"))
-            f = ops.linear(h, self.w(p + "linear1"), self.b(p + "linear1"), act=ops.ACT_RELU)
-            f = ops.linear(self._drop(f, f"{tagp}gpt.df.{i}"), self.w(p + "linear2"), self.b(p + "linear2"))
-            h = ops.layernorm(h, self.P(p + "norm2.weight"), self.P(p + "norm2.bias"), res=self._drop(f, f"{tagp}gpt.d2.{i}"))
+            pd = self.layer_dropout if self.training else 0.0
+            # the three layer dropouts are fused: into the two LayerNorm kernels (residual branch) and into linear1's epilogue
+            h = ops.layernorm(h, self.P(p + "norm1.weight"), self.P(p + "norm1.bias"), res=a, res_drop=(pd, f"{tagp}gpt.d1.{i}"))
+            f = ops.linear(h, self.w(p + "linear1"), self.b(p + "linear1"), act=ops.ACT_RELU, drop=(pd, f"{tagp}gpt.df.{i}"))
+            f = ops.linear(f, self.w(p + "linear2"), self.b(p + "linear2"))
+            h = ops.layernorm(h, self.P(p + "norm2.weight"), self.P(p + "norm2.bias"), res=f, res_drop=(pd, f"{tagp}gpt.d2.{i}"))
         key = (B, X, str(dev))
         if getattr(self, "_xoff_key", None) != key:
             self._xoff, self._xoff_key = torch.full((B,), X, device=dev, dtype=torch.int64), key

@@ -443,7 +443,7 @@ def _conv_out_len(Tin, Q, stride, pad, dil):
 
 
 def _fwd_like(x, Tin, w, wq0, wqstep, nq, ldw, w_sq, C, N, y, *, J, P, is_, os_, o0, Tout, off, bias=None, res=None,
-              act=0, slope=0.0, in_len=None, out_len=None, H=1, x_sh=0, w_sh=0, y_sh=0, b_sh=0):
+              act=0, slope=0.0, in_len=None, out_len=None, H=1, x_sh=0, w_sh=0, y_sh=0, b_sh=0, drop=None):
     """one launch of the generalised conv on the tensor-core kernel.  Grouped convs pass H = groups with the per-group
     channel offsets x_sh / w_sh / y_sh / b_sh (C, N are then per-group sizes)."""
     B = x.shape[0]
@@ -456,6 +456,8 @@ def _fwd_like(x, Tin, w, wq0, wqstep, nq, ldw, w_sq, C, N, y, *, J, P, is_, os_,
               r_sb=Tout * P * ldr, r_sh=y_sh, ldx=ldx, ldw=ldw, ldy=ldy, ldr=ldr, b_sh=b_sh, Z=B * H, H=H, C=C, N=N, Q=nq,
               G=1, Tin=Tin, J=J, P=P, is_=is_, os_=os_, o0=o0, Tout=Tout, act=act, slope=float(slope), off=off)
     d.w = wbase
+    if drop is not None:                      # fused dropout after the activation (TMA kernel epilogue only; the library rejects other routes)
+        d.drop_rng, d.drop_sid, d.drop_p = rng_state(x.device).data_ptr(), int(drop[1]), float(drop[0])
     mma = _aligned(x, ldx) and ldw % 4 == 0 and (wbase % 16 == 0) and (d.w_sq % 4 == 0) and x_sh % 4 == 0 and w_sh % 4 == 0
     if not mma:
         assert H == 1, "grouped convs need 16-byte aligned group slices"
@@ -500,7 +502,8 @@ class _ConvFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, pa, pb, bias, res, cfg):
-        Q, stride, pad, dil, P, G, act, slope, in_len, out_len = cfg
+        Q, stride, pad, dil, P, G, act, slope, in_len, out_len = cfg[:10]
+        drop = cfg[10] if len(cfg) > 10 else None
         x = _cl(x)
         B, R, C = x.shape
         assert R % P == 0
@@ -533,7 +536,7 @@ class _ConvFn(torch.autograd.Function):
                    2.0 * B * J * P * N * C * Q)
         else:
             _fwd_like(x, Tin, pa, 0, 1, Q, lda, N * lda, Cg, Ng, y, J=J, P=P, is_=stride, os_=1, o0=0, Tout=J, off=off,
-                      bias=bias, res=res, act=act, slope=slope, in_len=in_len, out_len=out_len, **gk)
+                      bias=bias, res=res, act=act, slope=slope, in_len=in_len, out_len=out_len, drop=drop, **gk)
         ctx.cfg = cfg
         ctx.dims = (B, Tin, C, N, J, lda)
         ctx.has = (bias is not None, res is not None)
@@ -542,7 +545,11 @@ class _ConvFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dy):
-        Q, stride, pad, dil, P, G, act, slope, in_len, out_len = ctx.cfg
+        Q, stride, pad, dil, P, G, act, slope, in_len, out_len = ctx.cfg[:10]
+        drop = ctx.cfg[10] if len(ctx.cfg) > 10 else None
+        # dropout fused after a ReLU: the saved output is zero exactly where the element was dropped or the ReLU was off, so
+        # the activation backward only needs the extra 1/(1-p) factor -- no mask is regenerated
+        gscale = 1.0 / (1.0 - drop[0]) if drop is not None else 1.0
         B, Tin, C, N, J, lda = ctx.dims
         x, pa, pb, y = ctx.saved_tensors
         has_bias, has_res = ctx.has
@@ -563,8 +570,8 @@ class _ConvFn(torch.autograd.Function):
             ldo = (Ro + 31) // 32 * 32                                       # 128-byte aligned rows for the TMA boxes
             dyt = torch.empty((B, N, ldo), device=dy.device, dtype=torch.float32) if tma_w else None
             dbias = _zpool.take(N, dy.device) if want_b else None
-            _call("evk_dy_prep", _p(dy), N, _p(y), N, act, ctypes.c_float(slope), _p(out_len), P, _p(dpre), N, _p(dyt), ldo, N * ldo, _p(dbias),
-                  B, Ro, N)
+            _call("evk_dy_prep", _p(dy), N, _p(y), N, act, ctypes.c_float(slope), ctypes.c_float(gscale), _p(out_len), P, _p(dpre), N, _p(dyt),
+                  ldo, N * ldo, _p(dbias), B, Ro, N)
             if need_pre:
                 dy = dpre
         dx = dpa = dres = None
@@ -657,8 +664,23 @@ def conv(x, w: PackedW, bias=None, *, stride=1, pad=0, dil=1, P=1, groups=1, act
     return _ConvFn.apply(x, w.pa, w.pb, bias, res, cfg)
 
 
-def linear(x, w: PackedW, bias=None, act=ACT_NONE, slope=0.0, out_len=None, in_len=None, res=None):
-    """nn.Linear / 1x1 conv on [B, T, C] or [rows, C]."""
+def fused_dropout_ok(x, w, act):
+    """can `linear(..., act=ReLU, drop=...)` fuse the dropout into the GEMM epilogue?  Mirrors the flat-GEMM eligibility of
+    gemm_tma_run (csrc/gemm_tma.cu); the library raises if a launch with dropout requested is not taken by that kernel."""
+    if act != ACT_RELU or x.dim() != 3 or not x.is_contiguous() or _lib().evk_get_precise():
+        return False
+    rows, C, N = x.shape[0] * x.shape[1], x.shape[2], w.D0
+    return w.Q == 1 and rows >= 512 and C >= 64 and C % 4 == 0 and N >= 64 and N % 4 == 0 and x.data_ptr() % 16 == 0
+
+
+def linear(x, w: PackedW, bias=None, act=ACT_NONE, slope=0.0, out_len=None, in_len=None, res=None, drop=None):
+    """nn.Linear / 1x1 conv on [B, T, C] or [rows, C].  drop = (p, tag): dropout_p(relu(x W^T + b)) with the dropout applied in
+    the GEMM epilogue when fused_dropout_ok (else as a separate kernel)."""
+    if drop is not None and drop[0] > 0.0:
+        if fused_dropout_ok(x, w, act) and out_len is None and in_len is None and res is None:
+            cfg = (w.Q, 1, 0, 1, 1, 1, act, slope, None, None, (float(drop[0]), stream_id(drop[1])))
+            return _ConvFn.apply(x, w.pa, w.pb, bias, None, cfg)
+        return dropout(linear(x, w, bias, act, slope, out_len, in_len, res), drop[0], drop[1])
     if x.dim() == 2:
         return conv(x.unsqueeze(0), w, bias, act=act, slope=slope, res=res.unsqueeze(0) if res is not None else None).squeeze(0)
     return conv(x, w, bias, act=act, slope=slope, out_len=out_len, in_len=in_len, res=res)
@@ -1272,8 +1294,43 @@ class _LayerNormFn(torch.autograd.Function):
         return dx, (dx if res is not None else None), dgb[0], dgb[1], None
 
 
-def layernorm(x, gamma, beta, res=None, eps=1e-5):
-    """LayerNorm over channels of (x + res)."""
+class _LayerNormDropFn(torch.autograd.Function):
+    """LayerNorm(x + dropout_p(res)) in one kernel; the backward regenerates the mask and emits dres = dx * mask / (1-p)."""
+
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, eps, p, sid):
+        x, res = x.contiguous(), res.contiguous()
+        C = x.shape[-1]
+        rows = x.numel() // C
+        y = torch.empty_like(x)
+        stats = torch.empty((rows, 2), device=x.device, dtype=torch.float32)
+        gamma, beta = gamma.contiguous(), beta.contiguous()
+        _call("evk_layernorm_drop_fwd", _p(x), _p(res), _p(gamma), _p(beta), ctypes.c_float(eps), ctypes.c_float(p), _p(rng_state(x.device)),
+              ctypes.c_uint64(sid), _p(y), _p(stats), rows, C)
+        ctx.save_for_backward(x, res, gamma, stats)
+        ctx.k = (p, sid, rows, C)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, res, gamma, stats = ctx.saved_tensors
+        p, sid, rows, C = ctx.k
+        dy = dy.contiguous()
+        dx, dres = torch.empty_like(x), torch.empty_like(x)
+        dgb = torch.zeros((2, C), device=x.device, dtype=torch.float32)
+        _call("evk_layernorm_drop_bwd", _p(x), _p(res), _p(gamma), _p(stats), _p(dy), ctypes.c_float(p), _p(rng_state(x.device)),
+              ctypes.c_uint64(sid), _p(dx), _p(dres), _p(dgb[0]), _p(dgb[1]), rows, C)
+        return dx, dres, dgb[0], dgb[1], None, None, None
+
+
+def layernorm(x, gamma, beta, res=None, eps=1e-5, res_drop=None):
+    """LayerNorm over channels of (x + res).  res_drop = (p, tag): LayerNorm(x + dropout_p(res)) with the dropout fused into the
+    kernel (C % 4 == 0, C <= 512, contiguous tensors); other shapes apply the dropout as a separate kernel."""
+    if res_drop is not None and res_drop[0] > 0.0 and res is not None:
+        C = x.shape[-1]
+        if C % 4 == 0 and C <= 512 and x.data_ptr() % 16 == 0 and res.data_ptr() % 16 == 0 and x.is_contiguous() and res.is_contiguous():
+            return _LayerNormDropFn.apply(x, res, gamma, beta, eps, float(res_drop[0]), stream_id(res_drop[1]))
+        res = dropout(res, res_drop[0], res_drop[1])
     return _LayerNormFn.apply(x, res, gamma, beta, eps)
 
 

@@ -60,9 +60,13 @@ typedef struct evk_gconv_desc {
   int32_t Tout;          /* output positions per batch (bounds for (o0 + j*os)) */
   int32_t act; float slope;
   int32_t off[EVK_MAX_TAPS];
+  /* optional fused dropout AFTER the activation (forward launches taken by gemm_tma_kernel only; any other route returns
+   * EVK_ERR_UNSUPPORTED): y = dropout_p(act(...)); rng = device [seed, offset] (the library's RNG state), sid = stream id. */
+  const uint64_t* drop_rng; uint64_t drop_sid; float drop_p;
 } evk_gconv_desc;
 
 int evk_gconv_fwd(const evk_gconv_desc* d, evk_stream_t stream);
+int evk_gconv_desc_size(void);         /* sizeof(evk_gconv_desc) as compiled: bindings check their mirror against it */
 /* 0 (default): one TF32 product per MAC.  1: 3xTF32 error-compensated products (~fp32 accuracy, 3x tensor work);
  * the parity tests use it to separate indexing errors from TF32 operand rounding. Process-wide. */
 int evk_set_precise(int32_t on);
@@ -229,6 +233,13 @@ int evk_layernorm_fwd(const float* x, int32_t ldx, const float* res, int32_t ldr
 int evk_layernorm_bwd(const float* x, int32_t ldx, const float* res, int32_t ldr, const float* gamma,
                       const float* stats, const float* dy, int32_t lddy, float* dx, int32_t lddx, float* dgamma,
                       float* dbeta, int64_t rows, int32_t C, evk_stream_t stream);
+/* LayerNorm(x + dropout_p(res)) with the dropout fused (transformer.py:300-315 `x + dropout(sa)` / `x + dropout(ff)`): the mask
+ * is regenerated in the backward from (rng state, sid), which also emits dres = dx * mask / (1-p).  C % 4 == 0, contiguous rows. */
+int evk_layernorm_drop_fwd(const float* x, const float* res, const float* gamma, const float* beta, float eps, float p,
+                           const uint64_t* rng, uint64_t sid, float* y, float* stats, int64_t rows, int32_t C, evk_stream_t stream);
+int evk_layernorm_drop_bwd(const float* x, const float* res, const float* gamma, const float* stats, const float* dy, float p,
+                           const uint64_t* rng, uint64_t sid, float* dx, float* dres, float* dgamma, float* dbeta, int64_t rows,
+                           int32_t C, evk_stream_t stream);
 
 /* attention softmax (attentions.py:243-279, modules.py:669-682): in place on S [Z][Tq][Tk] (row pitch lds)
  *   s = (S + relk[z][i][j-i+win]) * scale (|j-i|<=win, relk nullable [Z][Tq][2win+1], both unscaled);
@@ -316,9 +327,11 @@ int evk_conv_wgrad_tma(const float* dyt, int32_t ld_dy, int64_t dy_sb, const flo
  * dpre (nullable) = g in the layout of dy; dyt (nullable) [B][C][ldt] = g transposed (the K-major operand of evk_conv_wgrad_tma);
  * dbias (nullable, [C], zero-initialised by the caller) += column sums of g.  act: evk_act of the forward epilogue, yact = its
  * OUTPUT (derivatives are taken from the output: leaky-ReLU / ReLU by sign, tanh by 1 - y^2). */
-int evk_dy_prep(const float* dy, int32_t lddy, const float* yact, int32_t ldy, int32_t act, float slope, const int32_t* len, int32_t P,
-                float* dpre, int32_t ldp, float* dyt, int32_t ldt, int64_t t_sb, float* dbias, int32_t B, int32_t T, int32_t C,
+int evk_dy_prep(const float* dy, int32_t lddy, const float* yact, int32_t ldy, int32_t act, float slope, float gscale, const int32_t* len,
+                int32_t P, float* dpre, int32_t ldp, float* dyt, int32_t ldt, int64_t t_sb, float* dbias, int32_t B, int32_t T, int32_t C,
                 evk_stream_t stream);
+/* gscale multiplies g: 1/(1-p) when the forward epilogue applied dropout after a ReLU -- the saved OUTPUT is then zero exactly
+ * where the element was dropped or the ReLU was off, so no mask needs to be regenerated. */
 /* Strided conv forward on the same kernel: the input is first split into `stride` phase copies
  *   xs[rho][b][j*P + w][c] = x[b][(j*stride + rho)*P + w][c]   (zero for j*stride + rho >= T; j < Jp = ceil(T / stride))
  * and the conv becomes a stride-1 tap sum in which tap q (u = q*dil - pad) reads copy src[q] = u mod stride at row shift

@@ -481,6 +481,58 @@ def check_stft():
     return out
 
 
+def check_fused_dropout():
+    """Dropout fused into the GEMM epilogue (linear + ReLU + dropout, backward from the saved output) and into LayerNorm
+    (LN(x + dropout(res)), mask regenerated in the backward): the mask is recovered from the kernels' own outputs and the
+    results are compared with the unfused operators applied with that mask."""
+    from easevoice_trainer_b200 import ops
+    out = []
+    g = _gen(77)
+    p = 0.1
+    # ---- linear -> ReLU -> dropout
+    x = torch.randn(4, 256, 128, generator=g).to(DEV)
+    v = (torch.randn(256, 128, 1, generator=g) * 0.1).to(DEV)
+    b = (torch.randn(256, generator=g) * 0.1).to(DEV)
+    gy = torch.randn(4, 256, 256, generator=g).to(DEV)
+    xa, va, ba = [t.clone().requires_grad_(True) for t in (x, v, b)]
+    yf = ops.linear(xa, ops.pack_weight(va, None), ba, act=ops.ACT_RELU, drop=(p, "chk.drop.lin"))
+    out.append(("fused dropout taken by the GEMM epilogue", 0.0 if ops.fused_dropout_ok(x, ops.pack_weight(v, None), ops.ACT_RELU) else 1.0, 0.5))
+    yf.backward(gy)
+    xb, vb, bb = [t.clone().requires_grad_(True) for t in (x, v, b)]
+    yp = ops.linear(xb, ops.pack_weight(vb, None), bb, act=ops.ACT_RELU)
+    pos = yp.detach() > 0
+    M = ((yf.detach() != 0) & pos).float() / (1.0 - p)
+    out.append(("linear+relu+dropout: kept values = relu(.)/(1-p), dropped = 0", rel(yf, yp.detach() * M), 1e-6))
+    frac = 1.0 - float(((yf.detach() != 0) & pos).sum()) / float(pos.sum())
+    out.append(("linear+relu+dropout: drop fraction vs p", abs(frac - p) / p, 5e-2))
+    (yp * M).backward(gy)
+    out.append(("linear+relu+dropout dx (mask-free backward from the saved output)", rel(xa.grad, xb.grad), TOL_TC2))
+    out.append(("linear+relu+dropout dW", rel(va.grad, vb.grad), TOL_TC2))
+    out.append(("linear+relu+dropout dbias", rel(ba.grad, bb.grad), 1e-5))
+    # ---- LayerNorm(x + dropout(res))
+    x = torch.randn(4, 300, 512, generator=g).to(DEV)
+    a = torch.randn(4, 300, 512, generator=g).to(DEV)
+    gm = (1.0 + 0.1 * torch.randn(512, generator=g)).to(DEV)
+    bt = (0.1 * torch.randn(512, generator=g)).to(DEV)
+    gy = torch.randn(4, 300, 512, generator=g).to(DEV)
+    x1, a1, g1, b1 = [t.clone().requires_grad_(True) for t in (x, a, gm, bt)]
+    y1 = ops.layernorm(x1, g1, b1, res=a1, res_drop=(p, "chk.drop.ln"))
+    y1.backward(gy)
+    ratio = a1.grad / x1.grad                                   # = mask / (1-p) wherever dx != 0
+    M = (ratio.abs() > 0.5).float() / (1.0 - p)
+    out.append(("LN+dropout: dres = dx * mask/(1-p) (mask is 0/1)", float((ratio - M).abs().max()), 1e-5))
+    out.append(("LN+dropout: drop fraction vs p", abs(float((M == 0).float().mean()) - p) / p, 5e-2))
+    x2, a2, g2, b2 = [t.clone().requires_grad_(True) for t in (x, a, gm, bt)]
+    y2 = ops.layernorm(x2, g2, b2, res=a2 * M)
+    y2.backward(gy)
+    out.append(("LN+dropout forward vs unfused LN(x + res * mask/(1-p))", rel(y1, y2), 2e-6))
+    out.append(("LN+dropout dx", rel(x1.grad, x2.grad), 2e-5))
+    out.append(("LN+dropout dres", rel(a1.grad, a2.grad), 2e-5))
+    out.append(("LN+dropout dgamma", rel(g1.grad, g2.grad), 2e-5))
+    out.append(("LN+dropout dbeta", rel(b1.grad, b2.grad), 2e-5))
+    return out
+
+
 def _load_models(seed_g=1234, seed_d=4321):
     from easevoice_trainer_b200 import models
     net_g = models.SynthesizerTrn(1025, 32, n_speakers=300, **s2_oracle.S2_MODEL)
@@ -1293,7 +1345,7 @@ ALL = [check_conv, check_conv_transpose, check_elementwise, check_attention, che
        check_gpt_kernels, check_scaled_adam, lambda: check_gpt("small"), lambda: check_gpt("ragged"),
        check_gpt_dpo_and_trainer, check_gemm_tma, check_vocoder_cfg5,
        lambda: check_s2_full("cfg3"), lambda: check_s2_full("cfg3r"), lambda: check_gpt_full("cfg2"),
-       check_sovits_train_e2e, check_stft]
+       check_sovits_train_e2e, check_stft, check_fused_dropout]
 NAMES = ["conv", "conv_transpose", "elementwise", "attention", "vq_losses_optim", "mel", "s2_small", "s2_ragged", "api",
          "gpt_kernels", "scaled_adam", "gpt_small", "gpt_ragged", "gpt_dpo_trainer", "gemm_tma", "vocoder_cfg5",
-         "s2_cfg3", "s2_cfg3r", "gpt_cfg2", "sovits_train_e2e", "stft_mrstft"]
+         "s2_cfg3", "s2_cfg3r", "gpt_cfg2", "sovits_train_e2e", "stft_mrstft", "fused_dropout"]

@@ -25,10 +25,12 @@ def test_library_exports_every_symbol_declared_in_header():
 
 def test_descriptor_struct_layout():
     from easevoice_trainer_b200 import lib
-    # 7 pointers + 9 int64 + 19 int32 + float + int32[48], padded to 8 bytes
-    expect = 7 * 8 + 9 * 8 + 19 * 4 + 4 + 48 * 4
+    # 7 pointers + 9 int64 + 19 int32 + float + int32[48] + (pointer, uint64, float) of the fused-dropout request, padded to 8 bytes
+    expect = 7 * 8 + 9 * 8 + 19 * 4 + 4 + 48 * 4 + 8 + 8 + 4
     assert ctypes.sizeof(lib.GconvDesc) == (expect + 7) // 8 * 8
     assert lib.GconvDesc.off.offset == 7 * 8 + 9 * 8 + 19 * 4 + 4
+    assert lib.GconvDesc.drop_rng.offset == 400 and lib.GconvDesc.drop_sid.offset == 408 and lib.GconvDesc.drop_p.offset == 416
+    assert lib.load().evk_gconv_desc_size() == ctypes.sizeof(lib.GconvDesc)          # the compiled header agrees with the ctypes mirror
 
 
 def test_no_cpu_fallback():
