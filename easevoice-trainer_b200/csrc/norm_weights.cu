@@ -80,9 +80,11 @@ __global__ void layernorm_bwd_kernel(const float* __restrict__ x, int ldx, const
 // ---- LayerNorm(x + dropout(res)) with the dropout fused (stage-1 GPT: transformer.py:300-315) --------------------------
 // One warp per row, float4 per lane (C % 4 == 0, C <= 2048, contiguous rows).  The dropout scale factors come from
 // dropk_scale4 keyed by the float4's linear index, so the backward regenerates the identical mask.
+// gamma / beta are parameter views (any 4-byte alignment: flat optimizer storage packs them back to back)
+__device__ __forceinline__ float4 ld4_any(const float* __restrict__ p) { return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3)); }
 constexpr int LND_MAXV = 4;            // float4 per lane: C <= 512 (the GPT's model width); fixed trip counts keep everything in registers
 __global__ void __launch_bounds__(256) layernorm_drop_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ res,
-                                                                 const float4* __restrict__ gamma, const float4* __restrict__ beta, float eps,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                                                                  float p, const unsigned long long* __restrict__ rng, unsigned long long sid,
                                                                  float4* __restrict__ y, float* __restrict__ stats, long long rows, int C4) {
   const int lane = threadIdx.x & 31;
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(256) layernorm_drop_fwd_kernel(const float4* _
   for (int i = 0; i < LND_MAXV; ++i) {
     const int c = lane + 32 * i;
     if (c < C4) {
-      const float4 g = gamma[c], b = beta[c], t = v[i];
+      const float4 g = ld4_any(gamma + 4 * c), b = ld4_any(beta + 4 * c), t = v[i];
       y[row * C4 + c] = make_float4((t.x - mean) * rstd * g.x + b.x, (t.y - mean) * rstd * g.y + b.y, (t.z - mean) * rstd * g.z + b.z,
                                     (t.w - mean) * rstd * g.w + b.w);
     }
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(256) layernorm_drop_fwd_kernel(const float4* _
 }
 
 __global__ void __launch_bounds__(256) layernorm_drop_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ res,
-                                                                 const float4* __restrict__ gamma, const float* __restrict__ stats,
+                                                                 const float* __restrict__ gamma, const float* __restrict__ stats,
                                                                  const float4* __restrict__ dy, float p, const unsigned long long* __restrict__ rng,
                                                                  unsigned long long sid, float4* __restrict__ dx, float4* __restrict__ dres,
                                                                  float* __restrict__ dgamma, float* __restrict__ dbeta, long long rows, int C4,
@@ -164,7 +166,7 @@ __global__ void __launch_bounds__(256) layernorm_drop_bwd_kernel(const float4* _
         dropk_scale4(dk, (unsigned long long)g4, m);
         t.x += r.x * m[0]; t.y += r.y * m[1]; t.z += r.z * m[2]; t.w += r.w * m[3];
         const float4 h = make_float4((t.x - mean) * rstd, (t.y - mean) * rstd, (t.z - mean) * rstd, (t.w - mean) * rstd);
-        const float4 d = dy[g4], gm = gamma[c];
+        const float4 d = dy[g4], gm = ld4_any(gamma + 4 * c);
         const float4 g = make_float4(d.x * gm.x, d.y * gm.y, d.z * gm.z, d.w * gm.w);
         xh[i] = h; gd[i] = g;
         s1 += g.x + g.y + g.z + g.w;
@@ -320,10 +322,9 @@ extern "C" int evk_layernorm_drop_fwd(const float* x, const float* res, const fl
                                       const uint64_t* rng, uint64_t sid, float* y, float* stats, int64_t rows, int32_t C, evk_stream_t stream) {
   EVK_REQUIRE(x && res && gamma && beta && y && stats && rng, EVK_ERR_ARG, "layernorm_drop_fwd: null tensor");
   EVK_REQUIRE(C >= 4 && (C % 4) == 0 && C <= 128 * LND_MAXV && p >= 0.f && p < 1.f, EVK_ERR_UNSUPPORTED, "layernorm_drop_fwd: C=%d p=%f unsupported", C, p);
-  EVK_REQUIRE(((((uintptr_t)x) | ((uintptr_t)res) | ((uintptr_t)gamma) | ((uintptr_t)beta) | ((uintptr_t)y)) & 15) == 0, EVK_ERR_ARG,
-              "layernorm_drop_fwd: tensors must be 16-byte aligned");
+  EVK_REQUIRE(((((uintptr_t)x) | ((uintptr_t)res) | ((uintptr_t)y)) & 15) == 0, EVK_ERR_ARG, "layernorm_drop_fwd: x / res / y must be 16-byte aligned");
   if (rows == 0) return EVK_OK;
-  layernorm_drop_fwd_kernel<<<cdiv(rows, 8), 256, 0, ST>>>((const float4*)x, (const float4*)res, (const float4*)gamma, (const float4*)beta, eps, p,
+  layernorm_drop_fwd_kernel<<<cdiv(rows, 8), 256, 0, ST>>>((const float4*)x, (const float4*)res, gamma, beta, eps, p,
                                                            (const unsigned long long*)rng, sid, (float4*)y, stats, rows, C / 4);
   return check_launch("layernorm_drop_fwd");
 }
@@ -333,10 +334,12 @@ extern "C" int evk_layernorm_drop_bwd(const float* x, const float* res, const fl
                                       int32_t C, evk_stream_t stream) {
   EVK_REQUIRE(x && res && gamma && stats && dy && dx && dres && dgamma && dbeta && rng, EVK_ERR_ARG, "layernorm_drop_bwd: null tensor");
   EVK_REQUIRE(C >= 4 && (C % 4) == 0 && C <= 128 * LND_MAXV, EVK_ERR_UNSUPPORTED, "layernorm_drop_bwd: C=%d unsupported", C);
+  EVK_REQUIRE(((((uintptr_t)x) | ((uintptr_t)res) | ((uintptr_t)dy) | ((uintptr_t)dx) | ((uintptr_t)dres)) & 15) == 0, EVK_ERR_ARG,
+              "layernorm_drop_bwd: x / res / dy / dx / dres must be 16-byte aligned");
   if (rows == 0) return EVK_OK;
   int rpb = (int)((rows + 148 * 4 - 1) / (148 * 4));
   if (rpb < 8) rpb = 8;
-  layernorm_drop_bwd_kernel<<<cdiv(rows, rpb), 256, 2 * C * sizeof(float), ST>>>((const float4*)x, (const float4*)res, (const float4*)gamma, stats,
+  layernorm_drop_bwd_kernel<<<cdiv(rows, rpb), 256, 2 * C * sizeof(float), ST>>>((const float4*)x, (const float4*)res, gamma, stats,
                                                                                  (const float4*)dy, p, (const unsigned long long*)rng, sid, (float4*)dx,
                                                                                  (float4*)dres, dgamma, dbeta, rows, C / 4, rpb);
   return check_launch("layernorm_drop_bwd");

@@ -56,6 +56,14 @@ class ParamTree(nn.Module):
             node = getattr(node, p)
         return True
 
+    def _side_stream(self, device, idx=0):
+        key = f"_side{idx}"
+        st = self.__dict__.get(key)
+        if st is None or st.device != device:
+            st = torch.cuda.Stream(device=device)
+            self.__dict__[key] = st
+        return st
+
     # ---- packed-weight helpers (weight-norm folded into the packing pass) --------------------
     _frozen = False            # True: weights enter the graph as constants (no weight gradients are computed)
     batch_packing = os.environ.get("EVK_BATCH_PACK", "1") != "0"     # one weight_pack launch per network and step (ops.PackPlan), not one per layer
@@ -399,12 +407,18 @@ class SynthesizerTrn(ParamTree):
         return ops.take_channels(y4, 1)
 
     # ---------------------------------------------------------------------------------------------
-    def _side_stream(self, device):
-        st = self.__dict__.get("_side")
-        if st is None or st.device != device:
-            st = torch.cuda.Stream(device=device)
-            self.__dict__["_side"] = st
-        return st
+    def _flow(self, z, lengths, ge):
+        I = self.inter_channels
+        zf, half = z, I // 2
+        for f in range(4):
+            p = f"flow.flows.{2 * f}"
+            x0, x1 = zf[:, :, :half], zf[:, :, half:]
+            h = ops.linear(x0, self.w(p + ".pre"), self.b(p + ".pre"), out_len=lengths)
+            h = self._wn_stack(p + ".enc", h, lengths, ge, 4)
+            m = ops.linear(h, self.w(p + ".post"), self.b(p + ".post"), out_len=lengths)
+            x1 = ops.add(m, x1, length=lengths)
+            zf = ops.cat_flip(x0, x1)
+        return zf
 
     def forward_cl(self, ssl, spec, lengths, text, text_lengths, noise=None, ids_slice=None):
         """Channels-last forward.  ssl [B,T,768], spec [B,T,1025] (pitch may be padded), lengths/text_lengths int32 [B],
@@ -453,24 +467,27 @@ class SynthesizerTrn(ParamTree):
             noise = ops.randn((B, T, I), "enc_q.noise", device=spec.device)
         z = ops.reparam(stats_q, noise, lengths)
         m_q, logs_q = stats_q[:, :, :I], stats_q[:, :, I:]
-        # flow, models.py:308-315
-        zf = z
-        half = I // 2
-        for f in range(4):
-            p = f"flow.flows.{2 * f}"
-            x0, x1 = zf[:, :, :half], zf[:, :, half:]
-            h = ops.linear(x0, self.w(p + ".pre"), self.b(p + ".pre"), out_len=lengths)
-            h = self._wn_stack(p + ".enc", h, lengths, ge, 4)
-            m = ops.linear(h, self.w(p + ".post"), self.b(p + ".post"), out_len=lengths)
-            x1 = ops.add(m, x1, length=lengths)
-            zf = ops.cat_flip(x0, x1)
-        z_p = zf
+        # flow, models.py:308-315.  Like the prior encoder it only feeds the KL loss: second side stream, so that its four
+        # WaveNet stacks overlap the generator and the discriminators.
+        side2 = self._side_stream(spec.device, 1) if SIDE_STREAMS else None
+        if side2 is not None:
+            cur = torch.cuda.current_stream()
+            side2.wait_stream(cur)
+            with torch.cuda.stream(side2):
+                z_p = self._flow(z, lengths, ge)
+            for t in (z, ge):
+                t.record_stream(side2)
+            z_p.record_stream(cur)
+        else:
+            z_p = self._flow(z, lengths, ge)
         if ids_slice is None:
             ids_slice = ops.rand_slice_ids(lengths, seg)
         z_slice = ops.slice_rows(z, ids_slice, seg)
         o = self._generator(z_slice, ge)                                         # [B, seg*hop, 1]
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
+        if side2 is not None:
+            torch.cuda.current_stream().wait_stream(side2)
         return dict(y_hat=o, ids_slice=ids_slice, z=z, z_p=z_p, m_p=m_p, logs_p=logs_p, m_q=m_q, logs_q=logs_q,
                     quantized=quantized, codes=codes, ge=ge, lengths=lengths)
 
@@ -577,9 +594,30 @@ class MultiPeriodDiscriminator(ParamTree):
         self.begin_pack()
         try:
             x = ops.cat_batch(y, y_hat)
-            outs = [self._disc_s(ops.pad_channels(x, 4))]
-            for d, period in enumerate(PERIODS, start=1):
-                outs.append(self._disc_p(d, x, period))
+            x4 = ops.pad_channels(x, 4)
+            if SIDE_STREAMS and x.is_cuda:
+                # the six discriminators are independent chains whose later layers are far too small to fill the GPU: spread
+                # them over three streams (parallel branches of the captured graph; the backward follows the same streams)
+                cur = torch.cuda.current_stream()
+                lanes = [None, self._side_stream(x.device, 0), self._side_stream(x.device, 1)]
+                for st in lanes[1:]:
+                    st.wait_stream(cur)
+                    x.record_stream(st); x4.record_stream(st)
+                outs = []
+                for d in range(6):
+                    st = lanes[d % 3]
+                    with torch.cuda.stream(st if st is not None else cur):
+                        o = self._disc_s(x4) if d == 0 else self._disc_p(d, x, PERIODS[d - 1])
+                    if st is not None:
+                        for t in (o[0], *o[1]):
+                            t.record_stream(cur)
+                    outs.append(o)
+                for st in lanes[1:]:
+                    cur.wait_stream(st)
+            else:
+                outs = [self._disc_s(x4)]
+                for d, period in enumerate(PERIODS, start=1):
+                    outs.append(self._disc_p(d, x, period))
         finally:
             self.end_pack()
             self._frozen = False

@@ -1316,6 +1316,8 @@ class _LayerNormDropFn(torch.autograd.Function):
         x, res, gamma, stats = ctx.saved_tensors
         p, sid, rows, C = ctx.k
         dy = dy.contiguous()
+        if dy.data_ptr() % 16:
+            dy = dy.clone()
         dx, dres = torch.empty_like(x), torch.empty_like(x)
         dgb = torch.zeros((2, C), device=x.device, dtype=torch.float32)
         _call("evk_layernorm_drop_bwd", _p(x), _p(res), _p(gamma), _p(stats), _p(dy), ctypes.c_float(p), _p(rng_state(x.device)),

@@ -530,6 +530,11 @@ def check_fused_dropout():
     out.append(("LN+dropout dres", rel(a1.grad, a2.grad), 2e-5))
     out.append(("LN+dropout dgamma", rel(g1.grad, g2.grad), 2e-5))
     out.append(("LN+dropout dbeta", rel(b1.grad, b2.grad), 2e-5))
+    # gamma / beta as 4-byte-aligned views of flat parameter storage (the DPO trainer's layout)
+    flat = torch.zeros(2 * 512 + 3, device=DEV)
+    flat[1:513] = gm; flat[514:1026] = bt
+    y3 = ops.layernorm(x, flat[1:513], flat[514:1026], res=a, res_drop=(p, "chk.drop.ln"))
+    out.append(("LN+dropout with gamma/beta at odd element offsets == aligned result", rel(y3, y1.detach()), 0.0))
     return out
 
 
