@@ -103,6 +103,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+#ifdef GT_PROFILE
+// developer build only (tools/exp/gt_profile.py): per-CTA cycle counters of the three roles
+__device__ unsigned long long g_gt_prof[160 * 16];
+#define PROF_T0() const long long prof_t0 = clock64()
+#define PROF_ADD(slot) g_gt_prof[blockIdx.x * 16 + (slot)] += (unsigned long long)(clock64() - prof_t0)
+#define PROF_INC(slot) g_gt_prof[blockIdx.x * 16 + (slot)] += 1ull
+#define PROF_WAIT(slot, stmt) do { PROF_T0(); stmt; PROF_ADD(slot); } while (0)
+#else
+#define PROF_WAIT(slot, stmt) stmt
+#define PROF_INC(slot)
+#endif
+
 struct MapB4 { CUtensorMap m[4]; };                  // B: mode 1 uses one map per delayed copy of X^T, mode 0 only m[0]
                                                      // A: mode 0 uses one map per stride phase of the input, mode 1 only m[0];
                                                      //    slab mode: m[1] = the same tensor with a `span`-row box (the slab tail)
@@ -133,6 +145,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
   __shared__ uint32_t tmem_base_s;
   __shared__ __align__(16) float epi_s[8 * 32 * 36];            // per-epilogue-warp transpose tile (pitch 36: 128-bit conflict-free)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef GT_PROFILE
+  const long long prof_start = clock64();
+#endif
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < MAX_RING; ++i) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
@@ -149,6 +164,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n");
   const uint32_t tmem_base = tmem_base_s;
+#ifdef GT_PROFILE
+  if (threadIdx.x == 0) g_gt_prof[blockIdx.x * 16 + 9] += (unsigned long long)(clock64() - prof_start);
+#endif
 
   const int tiles_mn = p.tiles_m * p.tiles_n;
   // mode 0: tile -> (outer = batch item or K split, m tile, n tile); K iterations = taps x channel blocks (splits > 1 only
@@ -174,13 +192,13 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
         const int tm = mn / p.tiles_n, tn = mn - tm * p.tiles_n;
         const int z = (p.splits > 1 || p.mode) ? 0 : outer;
         auto next_a = [&]() -> uint8_t* {
-          mbar_wait(&emptyA[sA], phA);
+          PROF_WAIT(1, mbar_wait(&emptyA[sA], phA));
           mbar_expect_tx(&fullA[sA], (uint32_t)p.a_bytes);
           return gsm + (size_t)sA * p.a_stage;
         };
         auto done_a = [&]() { if (++sA == SA) { sA = 0; phA ^= 1; } };
         auto next_b = [&]() -> uint8_t* {
-          mbar_wait(&emptyB[sB], phB);
+          PROF_WAIT(2, mbar_wait(&emptyB[sB], phB));
           mbar_expect_tx(&fullB[sB], B_BYTES);
           return gsmB + (size_t)sB * B_BYTES;
         };
@@ -250,13 +268,14 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
       const uint32_t a_ring = smem_u32(gsm), b_ring = smem_u32(gsmB);
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
         const int a = tcount % NACC;
-        mbar_wait(&acc_empty[a], ((tcount / NACC) & 1) ^ 1);
+        PROF_WAIT(5, mbar_wait(&acc_empty[a], ((tcount / NACC) & 1) ^ 1));
+        PROF_INC(8);
         asm volatile("tcgen05.fence::after_thread_sync;\n");
         const uint32_t tacc = tmem_base + (uint32_t)(a * MT * BN);
         uint32_t accum = 0;
         // one step: MT x 4 MMAs of (128 x BN x 8) from A rows starting `a_off` bytes into the current A stage
         auto step = [&](uint32_t a_off) {
-          mbar_wait(&fullB[sB], phB);
+          PROF_WAIT(4, mbar_wait(&fullB[sB], phB));
           asm volatile("tcgen05.fence::after_thread_sync;\n");
           const uint32_t a_addr = a_ring + (uint32_t)sA * (uint32_t)p.a_stage + a_off;
           const uint64_t db = sw128_desc(b_ring + (uint32_t)sB * B_BYTES);
@@ -270,7 +289,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
           umma_commit(&emptyB[sB]);
           if (++sB == SB) { sB = 0; phB ^= 1; }
         };
-        auto wait_a = [&]() { mbar_wait(&fullA[sA], phA); };
+        auto wait_a = [&]() { PROF_WAIT(3, mbar_wait(&fullA[sA], phA)); };
         auto free_a = [&]() { umma_commit(&emptyA[sA]); if (++sA == SA) { sA = 0; phA ^= 1; } };
         if (slab) {
           for (int kb = 0; kb < kb_total; ++kb) {
@@ -316,7 +335,14 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
       const float* rz = p.res ? p.res + (size_t)z * p.r_sb : nullptr;
       const int olen = p.out_len ? p.out_len[z] : 0x7fffffff;
       const int a = tcount % NACC;
+#ifdef GT_PROFILE
+      const long long prof_e0 = clock64();
+#endif
       mbar_wait(&acc_full[a], (tcount / NACC) & 1);
+#ifdef GT_PROFILE
+      const long long prof_e1 = clock64();
+      if (threadIdx.x == 64) g_gt_prof[blockIdx.x * 16 + 6] += (unsigned long long)(prof_e1 - prof_e0);
+#endif
       asm volatile("tcgen05.fence::after_thread_sync;\n");
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
@@ -402,11 +428,17 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
       asm volatile("tcgen05.fence::before_thread_sync;\n");
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[a]);
+#ifdef GT_PROFILE
+      if (threadIdx.x == 64) g_gt_prof[blockIdx.x * 16 + 7] += (unsigned long long)(clock64() - prof_e1);
+#endif
     }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n");
   __syncthreads();
+#ifdef GT_PROFILE
+  if (threadIdx.x == 0) g_gt_prof[blockIdx.x * 16 + 0] += (unsigned long long)(clock64() - prof_start);
+#endif
   if (warp == 1) {
     asm volatile("tcgen05.fence::after_thread_sync;\n");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(TCOLS));
@@ -664,3 +696,11 @@ extern "C" int evk_conv_wgrad_tma(const float* dyt, int32_t ld_dy, int64_t dy_sb
   if (rc == 0) g_disp_flops[4] += 2.0 * B * (double)out_rows * N * C * Q;
   return rc;
 }
+
+#ifdef GT_PROFILE
+extern "C" int evk_gt_prof_read(unsigned long long* host, int reset) {
+  if (host) cudaMemcpyFromSymbol(host, evk::g_gt_prof, sizeof(evk::g_gt_prof));
+  if (reset) { static unsigned long long z[160 * 16]; cudaMemcpyToSymbol(evk::g_gt_prof, z, sizeof(z)); }
+  return 0;
+}
+#endif

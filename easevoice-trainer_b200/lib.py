@@ -7,7 +7,7 @@ import threading
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 HEADER = os.path.join(os.path.dirname(HERE), "include", "evk.h")
-LIB_PATH = os.path.join(HERE, "libevk_sm100.so")
+LIB_PATH = os.environ.get("EVK_LIB_PATH") or os.path.join(HERE, "libevk_sm100.so")   # override: instrumented developer builds (tools/exp)
 MAX_TAPS = 48
 
 

@@ -1345,12 +1345,60 @@ def check_sovits_train_e2e(gpu_ids="0"):
     return out
 
 
+def check_side_streams():
+    """The forward puts the prior encoder, the flow and four of the six discriminators on side streams (models.SIDE_STREAMS).
+    Same networks, same batch, streams on vs off: losses and every parameter gradient must agree to atomics noise."""
+    from easevoice_trainer_b200 import ops, models
+    from easevoice_trainer_b200.train import s2_step
+    out = []
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "s2_ragged.json")))
+    c = gold["cfg"]
+    B, T, X = c["B"], c["T"], c["X"]
+    net_g, net_d, _, _ = _load_models(c["g_seed"], c["d_seed"])
+    wav, ssl, text, spec_len, text_len = s2_oracle.synthetic_batch(B, T, X, c["batch_seed"], c["ragged"])
+    spec = mel_oracle.spectrogram(wav.squeeze(1), 2048, 640, 2048)
+    g = _gen(c["noise_seed"])
+    noise = torch.randn(B, 192, T, generator=g)
+    ids = (torch.rand(B, generator=g) * (spec_len - 32 + 1)).long()
+    stepper = s2_step.S2Step(net_g, net_d, dict(s2_oracle.S2_TRAIN), dict(s2_oracle.S2_DATA))
+    batch = dict(ssl=cl(ssl), spec=ops.to_channels_last(spec.to(DEV), pad_to=4), lengths=spec_len.to(DEV).to(torch.int32),
+                 wav=wav.reshape(B, -1, 1).to(DEV), text=text.to(DEV), text_lengths=text_len.to(DEV).to(torch.int32))
+    res = {}
+    old = models.SIDE_STREAMS
+    try:
+        for on in (True, False, True):
+            models.SIDE_STREAMS = on
+            r = stepper.losses(batch, noise=cl(noise), ids_slice=ids.to(DEV))
+            ld = stepper.d_loss(r)
+            lg, _ = stepper.g_loss(r)
+            gd = torch.autograd.grad(ld, [p for _, p in net_d.named_parameters()], retain_graph=True, allow_unused=True)
+            gg = torch.autograd.grad(lg, [p for _, p in net_g.named_parameters()], allow_unused=True)
+            torch.cuda.synchronize()
+            res.setdefault(on, []).append((float(ld), float(lg), [t.detach().clone() for t in gd], [None if t is None else t.detach().clone() for t in gg]))
+    finally:
+        models.SIDE_STREAMS = old
+    a, b, a2 = res[True][0], res[False][0], res[True][1]
+
+    def worst(x, y):
+        w = 0.0
+        for u, v in zip(x, y):
+            if u is not None:
+                w = max(w, rel(u, v))
+        return w
+    out.append(("side streams on vs off: loss_disc", abs(a[0] - b[0]) / abs(b[0]), 1e-5))
+    out.append(("side streams on vs off: loss_gen_all", abs(a[1] - b[1]) / abs(b[1]), 1e-5))
+    out.append(("side streams on vs off: D param grads worst rel-L2", worst(a[2], b[2]), 1e-4))
+    out.append(("side streams on vs off: G param grads worst rel-L2", worst(a[3], b[3]), 1e-4))
+    out.append(("side streams on, run twice: G param grads worst rel-L2 (atomics noise floor)", worst(a[3], a2[3]), 1e-4))
+    return out
+
+
 ALL = [check_conv, check_conv_transpose, check_elementwise, check_attention, check_vq_losses_optim, check_mel,
        lambda: check_s2("small"), lambda: check_s2("ragged"), check_api_layouts,
        check_gpt_kernels, check_scaled_adam, lambda: check_gpt("small"), lambda: check_gpt("ragged"),
        check_gpt_dpo_and_trainer, check_gemm_tma, check_vocoder_cfg5,
        lambda: check_s2_full("cfg3"), lambda: check_s2_full("cfg3r"), lambda: check_gpt_full("cfg2"),
-       check_sovits_train_e2e, check_stft, check_fused_dropout]
+       check_sovits_train_e2e, check_stft, check_fused_dropout, check_side_streams]
 NAMES = ["conv", "conv_transpose", "elementwise", "attention", "vq_losses_optim", "mel", "s2_small", "s2_ragged", "api",
          "gpt_kernels", "scaled_adam", "gpt_small", "gpt_ragged", "gpt_dpo_trainer", "gemm_tma", "vocoder_cfg5",
-         "s2_cfg3", "s2_cfg3r", "gpt_cfg2", "sovits_train_e2e", "stft_mrstft", "fused_dropout"]
+         "s2_cfg3", "s2_cfg3r", "gpt_cfg2", "sovits_train_e2e", "stft_mrstft", "fused_dropout", "side_streams"]
