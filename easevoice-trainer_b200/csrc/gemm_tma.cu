@@ -44,6 +44,7 @@ struct GemmP {
   // staging geometry (host-chosen): SA / SB ring depths, a_stage = shared-memory pitch of an A stage (multiple of 1024),
   // a_bytes = bytes the TMA loads of one A stage deliver (expect_tx), slab mode: off_min, span rows after the MT*128-row box
   int SA, SB, a_stage, a_bytes, slab, off_min;
+  int fast;                                          // epilogue: every pointer / pitch 16-byte aligned, N % 4 == 0, no atomics, no tanh
   float comp;                                        // accumulator scale compensating the tensor core's operand TRUNCATION (see run_gemm)
   const unsigned long long* drop_rng; unsigned long long drop_sid; float drop_p;   // fused dropout after the activation (0: off)
 };
@@ -104,16 +105,61 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 #ifdef GT_PROFILE
-// developer build only (tools/exp/gt_profile.py): per-CTA cycle counters of the three roles
+// developer build only (tools/exp/gt_profile.py): per-CTA cycle counters of the three roles.  Each role accumulates in
+// registers (prof_acc[]) and flushes once when it leaves its loop -- a global read-modify-write per wait would cost more
+// than the waits being measured.
 __device__ unsigned long long g_gt_prof[160 * 16];
-#define PROF_T0() const long long prof_t0 = clock64()
-#define PROF_ADD(slot) g_gt_prof[blockIdx.x * 16 + (slot)] += (unsigned long long)(clock64() - prof_t0)
-#define PROF_INC(slot) g_gt_prof[blockIdx.x * 16 + (slot)] += 1ull
-#define PROF_WAIT(slot, stmt) do { PROF_T0(); stmt; PROF_ADD(slot); } while (0)
+#define PROF_DECL() unsigned long long prof_acc[4] = {0ull, 0ull, 0ull, 0ull}
+#define PROF_WAIT(i, stmt) do { const long long prof_t0 = clock64(); stmt; prof_acc[i] += (unsigned long long)(clock64() - prof_t0); } while (0)
+#define PROF_INC(i) prof_acc[i] += 1ull
+#define PROF_FLUSH(i, slot) g_gt_prof[blockIdx.x * 16 + (slot)] += prof_acc[i]
 #else
-#define PROF_WAIT(slot, stmt) stmt
-#define PROF_INC(slot)
+#define PROF_DECL()
+#define PROF_WAIT(i, stmt) stmt
+#define PROF_INC(i)
+#define PROF_FLUSH(i, slot)
 #endif
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// Fast epilogue rows of one 32 x 32 chunk: this lane owns columns nn .. nn+3 of rows i*4 + r_sub (i = 0..7).  Straight-line
+// code: the only conditionals left are single predicated loads / stores (the branchy general path cost ~4800 cycles per
+// chunk against ~500 for this one -- tools/exp/gt_profile.py -- and made the GPT Linear layers epilogue-bound).
+template <bool RES, bool DROP>
+__device__ __forceinline__ void epi_rows_fast(const float* __restrict__ tr, int r_sub, int c4, float4 bv, float* __restrict__ dz,
+                                              const float* __restrict__ rz, const size_t (&orow)[8], const bool (&keep)[8],
+                                              const bool (&ok)[8], int ldd, int ldr, int nn, float neg, const DropK& dropk,
+                                              const float* dbase) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float4 t = *reinterpret_cast<const float4*>(tr + (i * 4 + r_sub) * 36 + c4);
+    float* dp = dz + orow[i] * ldd + nn;
+    t.x += bv.x; t.y += bv.y; t.z += bv.z; t.w += bv.w;
+    if (RES) {
+      float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ok[i]) rv = *reinterpret_cast<const float4*>(rz + orow[i] * ldr + nn);
+      t.x += rv.x; t.y += rv.y; t.z += rv.z; t.w += rv.w;
+    }
+    t.x = keep[i] ? (t.x > 0.f ? t.x : t.x * neg) : 0.f; t.y = keep[i] ? (t.y > 0.f ? t.y : t.y * neg) : 0.f;
+    t.z = keep[i] ? (t.z > 0.f ? t.z : t.z * neg) : 0.f; t.w = keep[i] ? (t.w > 0.f ? t.w : t.w * neg) : 0.f;
+    if (DROP) {
+      float m[4];
+      dropk_scale4(dropk, (unsigned long long)(dp - dbase) >> 2, m);
+      t.x *= m[0]; t.y *= m[1]; t.z *= m[2]; t.w *= m[3];
+    }
+    if (ok[i]) *reinterpret_cast<float4*>(dp) = t;
+  }
+}
 
 struct MapB4 { CUtensorMap m[4]; };                  // B: mode 1 uses one map per delayed copy of X^T, mode 0 only m[0]
                                                      // A: mode 0 uses one map per stride phase of the input, mode 1 only m[0];
@@ -185,21 +231,26 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
   // division or modulo by run-time values inside the step loops.
   const int SA = p.SA, SB = p.SB, Q = p.Q;
   if (warp == 0) {
-    if (lane == 0) {
+    // The whole warp walks the tile list with warp-uniform state; only the elected lane touches the barriers' tx counts and
+    // issues the TMA.  (Running the loop under `lane == 0` made the compiler wrap every UTMALDG / UTCHMMA in a
+    // divergence "waterfall" loop with R2UR moves: ~480 cycles per 4-MMA step, twice the tensor time at BN = 128.)
+    {
       int sA = 0, phA = 1, sB = 0, phB = 1;                      // empty barriers: the first pass over a ring passes immediately
+      PROF_DECL();
+      const bool leader = elect_one();
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int outer = tile / tiles_mn, mn = tile - outer * tiles_mn;
         const int tm = mn / p.tiles_n, tn = mn - tm * p.tiles_n;
         const int z = (p.splits > 1 || p.mode) ? 0 : outer;
         auto next_a = [&]() -> uint8_t* {
-          PROF_WAIT(1, mbar_wait(&emptyA[sA], phA));
-          mbar_expect_tx(&fullA[sA], (uint32_t)p.a_bytes);
+          PROF_WAIT(0, mbar_wait(&emptyA[sA], phA));
+          if (leader) mbar_expect_tx(&fullA[sA], (uint32_t)p.a_bytes);
           return gsm + (size_t)sA * p.a_stage;
         };
         auto done_a = [&]() { if (++sA == SA) { sA = 0; phA ^= 1; } };
         auto next_b = [&]() -> uint8_t* {
-          PROF_WAIT(2, mbar_wait(&emptyB[sB], phB));
-          mbar_expect_tx(&fullB[sB], B_BYTES);
+          PROF_WAIT(1, mbar_wait(&emptyB[sB], phB));
+          if (leader) mbar_expect_tx(&fullB[sB], B_BYTES);
           return gsmB + (size_t)sB * B_BYTES;
         };
         auto done_b = [&]() { if (++sB == SB) { sB = 0; phB ^= 1; } };
@@ -207,12 +258,12 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
           const int row0 = tm * (MT * BM) + p.off_min * p.P;
           for (int kb = 0; kb < kb_total; ++kb) {
             uint8_t* sa = next_a();
-            tma_load_3d(sa, &mapA, kb * BK, row0, z, &fullA[sA]);
-            tma_load_3d(sa + MT * BM * BK * 4, &mapA4.m[1], kb * BK, row0 + MT * BM, z, &fullA[sA]);
+            if (leader) tma_load_3d(sa, &mapA, kb * BK, row0, z, &fullA[sA]);
+            if (leader) tma_load_3d(sa + MT * BM * BK * 4, &mapA4.m[1], kb * BK, row0 + MT * BM, z, &fullA[sA]);
             done_a();
             for (int q = 0; q < Q; ++q) {
               uint8_t* sb = next_b();
-              tma_load_3d(sb, &mapB, kb * BK, tn * BN, q, &fullB[sB]);
+              if (leader) tma_load_3d(sb, &mapB, kb * BK, tn * BN, q, &fullB[sB]);
               done_b();
             }
           }
@@ -222,10 +273,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
             const int arow = tm * (MT * BM) + p.off[q] * p.P;
             for (int kb = 0; kb < kb_total; ++kb) {
               uint8_t* sa = next_a();
-              tma_load_3d(sa, am, kb * BK, arow, z, &fullA[sA]);
+              if (leader) tma_load_3d(sa, am, kb * BK, arow, z, &fullA[sA]);
               done_a();
               uint8_t* sb = next_b();
-              tma_load_3d(sb, &mapB, kb * BK, tn * BN, q, &fullB[sB]);
+              if (leader) tma_load_3d(sb, &mapB, kb * BK, tn * BN, q, &fullB[sB]);
               done_b();
             }
           }
@@ -240,57 +291,62 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
             int b = k0 / p.kbs, kk = k0 - b * p.kbs;
             for (int ki = k0; ki < k1; ++ki) {
               uint8_t* sa = next_a();
-              tma_load_3d(sa, &mapA, kk * BK, tm * BM, b, &fullA[sA]);
+              if (leader) tma_load_3d(sa, &mapA, kk * BK, tm * BM, b, &fullA[sA]);
               done_a();
               uint8_t* sb = next_b();
-              tma_load_3d(sb, &mapB4.m[r], kk * BK + (sh + r), tn * BN, b, &fullB[sB]);
+              if (leader) tma_load_3d(sb, &mapB4.m[r], kk * BK + (sh + r), tn * BN, b, &fullB[sB]);
               done_b();
               if (++kk == p.kbs) { kk = 0; ++b; }
             }
           } else {                                               // split-K plain GEMM (Z == Q == 1)
             for (int kb = k0; kb < k1; ++kb) {
               uint8_t* sa = next_a();
-              tma_load_3d(sa, &mapA, kb * BK, tm * (MT * BM), 0, &fullA[sA]);
+              if (leader) tma_load_3d(sa, &mapA, kb * BK, tm * (MT * BM), 0, &fullA[sA]);
               done_a();
               uint8_t* sb = next_b();
-              tma_load_3d(sb, &mapB, kb * BK, tn * BN, 0, &fullB[sB]);
+              if (leader) tma_load_3d(sb, &mapB, kb * BK, tn * BN, 0, &fullB[sB]);
               done_b();
             }
           }
         }
       }
+      if (leader) { PROF_FLUSH(0, 1); PROF_FLUSH(1, 2); }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {
+      PROF_DECL();
+      const bool leader = elect_one();
       // instruction descriptor: D = f32, A = B = tf32, both K-major, N = BN, M = 128
       constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int sA = 0, phA = 0, sB = 0, phB = 0, tcount = 0;
       const uint32_t a_ring = smem_u32(gsm), b_ring = smem_u32(gsmB);
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
         const int a = tcount % NACC;
-        PROF_WAIT(5, mbar_wait(&acc_empty[a], ((tcount / NACC) & 1) ^ 1));
-        PROF_INC(8);
+        PROF_WAIT(2, mbar_wait(&acc_empty[a], ((tcount / NACC) & 1) ^ 1));
+        PROF_INC(3);
         asm volatile("tcgen05.fence::after_thread_sync;\n");
         const uint32_t tacc = tmem_base + (uint32_t)(a * MT * BN);
         uint32_t accum = 0;
         // one step: MT x 4 MMAs of (128 x BN x 8) from A rows starting `a_off` bytes into the current A stage
         auto step = [&](uint32_t a_off) {
-          PROF_WAIT(4, mbar_wait(&fullB[sB], phB));
+          PROF_WAIT(1, mbar_wait(&fullB[sB], phB));
           asm volatile("tcgen05.fence::after_thread_sync;\n");
           const uint32_t a_addr = a_ring + (uint32_t)sA * (uint32_t)p.a_stage + a_off;
           const uint64_t db = sw128_desc(b_ring + (uint32_t)sB * B_BYTES);
+          if (leader) {
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            const uint64_t da = sw128_desc(a_addr + (uint32_t)(mt * BM * BK * 4));
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint64_t da = sw128_desc(a_addr + (uint32_t)(mt * BM * BK * 4));
 #pragma unroll
-            for (int k = 0; k < BK / 8; ++k) umma_tf32(tacc + (uint32_t)(mt * BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, accum | (uint32_t)k);
+              for (int k = 0; k < BK / 8; ++k) umma_tf32(tacc + (uint32_t)(mt * BN), da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), IDESC, accum | (uint32_t)k);
+            }
+            umma_commit(&emptyB[sB]);
           }
           accum = 1;
-          umma_commit(&emptyB[sB]);
           if (++sB == SB) { sB = 0; phB ^= 1; }
         };
-        auto wait_a = [&]() { PROF_WAIT(3, mbar_wait(&fullA[sA], phA)); };
-        auto free_a = [&]() { umma_commit(&emptyA[sA]); if (++sA == SA) { sA = 0; phA ^= 1; } };
+        auto wait_a = [&]() { PROF_WAIT(0, mbar_wait(&fullA[sA], phA)); };
+        auto free_a = [&]() { if (leader) umma_commit(&emptyA[sA]); if (++sA == SA) { sA = 0; phA ^= 1; } };
         if (slab) {
           for (int kb = 0; kb < kb_total; ++kb) {
             wait_a();
@@ -306,8 +362,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
             free_a();
           }
         }
-        umma_commit(&acc_full[a]);
+        if (leader) umma_commit(&acc_full[a]);
       }
+      if (leader) { PROF_FLUSH(0, 3); PROF_FLUSH(1, 4); PROF_FLUSH(2, 5); PROF_FLUSH(3, 8); }
     }
   } else {
     // ---- epilogue: EIGHT warps.  ncu (profiles/r2_ncu_gemm_tma.md) showed the round-1 epilogue -- four warps, one per
@@ -326,7 +383,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
     const int r_sub = lane >> 3, c4 = (lane & 7) * 4;
     const float comp = p.comp;
     const DropK dropk = dropk_make(p.drop_rng, p.drop_sid, p.drop_p);
+    const float neg = p.act == EVK_ACT_LRELU ? p.slope : (p.act == EVK_ACT_RELU ? 0.f : 1.f);   // fast path: x > 0 ? x : x * neg
     int tcount = 0;
+    PROF_DECL();
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++tcount) {
       const int outer = tile / tiles_mn, mn = tile - outer * tiles_mn;
       const int tm = mn / p.tiles_n, tn = mn - tm * p.tiles_n;
@@ -335,13 +394,9 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
       const float* rz = p.res ? p.res + (size_t)z * p.r_sb : nullptr;
       const int olen = p.out_len ? p.out_len[z] : 0x7fffffff;
       const int a = tcount % NACC;
-#ifdef GT_PROFILE
-      const long long prof_e0 = clock64();
-#endif
-      mbar_wait(&acc_full[a], (tcount / NACC) & 1);
+      PROF_WAIT(0, mbar_wait(&acc_full[a], (tcount / NACC) & 1));
 #ifdef GT_PROFILE
       const long long prof_e1 = clock64();
-      if (threadIdx.x == 64) g_gt_prof[blockIdx.x * 16 + 6] += (unsigned long long)(prof_e1 - prof_e0);
 #endif
       asm volatile("tcgen05.fence::after_thread_sync;\n");
 #pragma unroll 1
@@ -372,6 +427,24 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
           for (int e = 0; e < 8; ++e) trw[e] = make_float4(v[4 * e] * comp, v[4 * e + 1] * comp, v[4 * e + 2] * comp, v[4 * e + 3] * comp);
           __syncwarp();
           const int nn = n + c4;
+          if (p.fast) {
+            const bool colok = nn < p.N;                          // N % 4 == 0: the float4 is entirely inside or outside
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias && colok) bv = *reinterpret_cast<const float4*>(p.bias + nn);
+            bool ok[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ok[i] = inside[i] && colok;
+            if (dropk.thr) {
+              if (rz) epi_rows_fast<true, true>(tr, r_sub, c4, bv, dz, rz, orow, keep, ok, p.ldd, p.ldr, nn, neg, dropk, p.d);
+              else epi_rows_fast<false, true>(tr, r_sub, c4, bv, dz, rz, orow, keep, ok, p.ldd, p.ldr, nn, neg, dropk, p.d);
+            } else if (rz) {
+              epi_rows_fast<true, false>(tr, r_sub, c4, bv, dz, rz, orow, keep, ok, p.ldd, p.ldr, nn, neg, dropk, p.d);
+            } else {
+              epi_rows_fast<false, false>(tr, r_sub, c4, bv, dz, rz, orow, keep, ok, p.ldd, p.ldr, nn, neg, dropk, p.d);
+            }
+            __syncwarp();
+            continue;
+          }
           float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
           const bool full4 = nn + 4 <= p.N;
           if (p.bias && !p.atomic) {
@@ -429,9 +502,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) gemm_tma_kernel(const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[a]);
 #ifdef GT_PROFILE
-      if (threadIdx.x == 64) g_gt_prof[blockIdx.x * 16 + 7] += (unsigned long long)(clock64() - prof_e1);
+      prof_acc[1] += (unsigned long long)(clock64() - prof_e1);
 #endif
     }
+    if (threadIdx.x == 64) { PROF_FLUSH(0, 6); PROF_FLUSH(1, 7); }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;\n");
@@ -538,6 +612,12 @@ int launch_gemm(const Operands& o, GemmP& p, int splits, cudaStream_t st) {
   }
   p.comp = 1.f;
   for (int i = 0; i < o.raw_operands; ++i) p.comp *= 1.f + g_trunc_comp;
+  {
+    auto al16 = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const bool act_ok = p.act == EVK_ACT_NONE || p.act == EVK_ACT_LRELU || p.act == EVK_ACT_RELU;
+    p.fast = (act_ok && !p.atomic && !p.mode && (p.N % 4) == 0 && (p.ldd % 4) == 0 && (p.y_sb % 4) == 0 && al16(p.d) && (!p.bias || al16(p.bias)) &&
+              (!p.res || (al16(p.res) && (p.ldr % 4) == 0 && (p.r_sb % 4) == 0))) ? 1 : 0;
+  }
   p.tiles_m = cdiv(p.M, MT * BM);
   p.tiles_n = cdiv(p.N, BN);
   const int kb_total = p.mode ? p.Z * p.kbs : cdiv(p.K, BK);

@@ -9,19 +9,23 @@ import os
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["EVK_LIB_PATH"] = os.path.join(ROOT, "tools", "exp", "libevk_prof.so")
+PLAIN = "--plain" in sys.argv          # product library, timings only (what the instrumentation costs)
+if not PLAIN:
+    os.environ["EVK_LIB_PATH"] = os.path.join(ROOT, "tools", "exp", "libevk_prof.so")
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 from easevoice_trainer_b200 import lib, ops  # noqa: E402
 
 L = lib.init()
-raw = ctypes.CDLL(os.environ["EVK_LIB_PATH"])
+raw = None if PLAIN else ctypes.CDLL(os.environ["EVK_LIB_PATH"])
 dev = torch.device("cuda", 0)
 NAMES = ["kernel", "prod:emptyA", "prod:emptyB", "mma:fullA", "mma:fullB", "mma:acc_empty", "epi:acc_full", "epi:body", "tiles", "prologue"]
 
 
 def read(reset):
+    if PLAIN:
+        return torch.zeros(148, 16, dtype=torch.float64)
     buf = (ctypes.c_ulonglong * (160 * 16))()
     raw.evk_gt_prof_read(buf, int(reset))
     return torch.tensor(list(buf), dtype=torch.float64).view(160, 16)[:148]
@@ -44,6 +48,8 @@ def run(name, fn, flops):
     tiles = c[:, 8]
     busy = c[tiles > 0]
     print(f"== {name}: {us:.1f} us/launch, {flops / us / 1e6:.0f} TFLOP/s; tiles/CTA min {tiles.min():.0f} max {tiles.max():.0f}")
+    if PLAIN:
+        return
     worst = busy[busy[:, 0].argmax()]
     for i, n in enumerate(NAMES):
         if i == 8:
