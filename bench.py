@@ -395,9 +395,19 @@ def run_ours(args):
         # ---- dominant kernel, accounted FROM THE STEP: one eager step with a CUDA-event pair around every library call
         #      (ops.profile_begin) and the library's own dispatch accounting telling which kernel family served each
         #      contraction; flops are the analytic 2*Z*J*P*N*C*Q of the descriptors the calls carried.
-        ops.profile_begin()
-        st.step(batch, collectives=False)          # rank 0 alone: the profiled step must not enter the gradient all-reduces
-        prof = ops.profile_end()
+        # An eager step is CPU-bound (3 400 launches x ~20 us of host work): a stream that drains faster than it is fed makes every
+        # event pair also time the host gap between "record" and the launch behind it.  So the GPU is parked on a 30 ms spin
+        # first (the host runs ~1 000 launches ahead and stays ahead), and the side streams are off so that kernels do not share
+        # the SMs while they are being timed one by one.
+        from easevoice_trainer_b200 import models as _models
+        _ss, _models.SIDE_STREAMS = _models.SIDE_STREAMS, False
+        try:
+            torch.cuda._sleep(int(0.03 * 1.9e9))
+            ops.profile_begin()
+            st.step(batch, collectives=False)      # rank 0 alone: the profiled step must not enter the gradient all-reduces
+            prof = ops.profile_end()
+        finally:
+            _models.SIDE_STREAMS = _ss
         tma_keys = [k for k in prof if "gemm_tma" in k or k.startswith("evk_gemm_tf32")]
         tma_ms = sum(prof[k]["ms"] for k in tma_keys)
         tma_fl = sum(prof[k]["flops"] for k in tma_keys)
@@ -415,7 +425,7 @@ def run_ours(args):
                                  step_tflops=all_fl / (ms * 1e-3) / 1e12,
                                  peak_source=f"{src} cuBLAS bf16 sustained; the kernel computes in TF32 whose nominal peak is half of bf16",
                                  how="achieved = analytic flops of EVERY gemm_tma launch of one training step / the sum of their CUDA-event durations "
-                                     "(events recorded on the launching stream around each call of an eager step, same process, after the timed region); "
+                                     "(events recorded on the launching stream around each call of an eager step run behind a 30 ms spin kernel so the host stays ahead, single stream, same process, after the timed region); "
                                      "share_of_step_time is against the event time of all library calls of that step (torch fill/add/copy kernels excluded); "
                                      "traffic = dram read+write bytes per launch of the heaviest layer from the committed ncu capture (profiles/r2_ncu_traffic.json), null if absent",
                                  by_call={k: dict(calls=v["calls"], ms=round(v["ms"], 3), tflops=(round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["flops"] else None))
@@ -579,6 +589,7 @@ def gpt_section(args, dev, rank, world):
     if rank == 0:
         hbm, tf_burst, tf_sus, src = peaks()
         st.batch_idx = 1
+        torch.cuda._sleep(int(0.03 * 1.9e9))       # host runs ahead of the GPU: event pairs time kernels, not launch gaps
         ops.profile_begin()
         st.step(batch)
         prof = ops.profile_end()

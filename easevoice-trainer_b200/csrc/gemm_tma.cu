@@ -16,6 +16,7 @@
 // persistent (one per SM) and walk the tile list n-fastest so that concurrent CTAs share the A row block in L2.
 // Out-of-range rows / K tails are zero-filled by TMA, so no shape needs padding.
 #include <cuda.h>
+#include <cstdlib>
 
 #include "evk_common.cuh"
 
@@ -653,11 +654,47 @@ int launch_bn(const Operands& o, GemmP& p, int splits, cudaStream_t st) {
   return mt2 ? launch_gemm<BN, 2>(o, p, splits, st) : launch_gemm<BN, 1>(o, p, splits, st);
 }
 
+// Tile width.  A wide tile is the cheapest per flop (one A read per 256 columns; the TF32 shared-memory-operand MMA is bound
+// by shared-memory bandwidth, so the A re-read of narrower tiles is real cost), but most launches of the step are SMALL:
+// 5536 rows x 192..384 channels is 44..88 tiles of 128 x 256 on 148 SMs.  Pick the width that minimises
+//   waves * max(main loop, epilogue) + epilogue      (cycles; per-step and epilogue costs measured by tools/exp/gt_profile.py)
+int pick_bn(const GemmP& p, int splits) {
+  static int auto_bn = -1;
+  if (auto_bn < 0) { const char* e = getenv("EVK_TMA_AUTO_BN"); auto_bn = (e && e[0] == '1') ? 1 : 0; }   // opt-in: measured neutral on the step (53.48 vs 53.49 ms), slower in aggregate
+  int widest = p.N > 128 ? 256 : p.N > 64 ? 128 : p.N > 32 ? 64 : 32;
+  if (!auto_bn) return widest;
+  if (!g_sm_count) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const int cand[4] = {256, 128, 64, 32};
+  const double step_c[4] = {560.0, 340.0, 325.0, 310.0}, epi_c[4] = {8000.0, 4300.0, 2300.0, 1500.0};
+  const int kb_total = p.mode ? p.Z * p.kbs : cdiv(p.K, BK);
+  const int sp = max(1, min(splits, kb_total));
+  const double steps = (double)cdiv(kb_total, sp) * (p.mode ? 1 : p.Q);
+  const long long outer = (long long)sp * (p.mode ? p.Q : p.Z);
+  const long long tiles_m = cdiv(p.M, BM);
+  int best = widest;
+  double best_cost = 1e30;
+  for (int i = 0; i < 4; ++i) {
+    const int bn = cand[i];
+    if (bn > widest) continue;
+    const long long tiles = tiles_m * cdiv(p.N, bn) * outer;
+    const double waves = (double)cdiv(tiles, (long long)g_sm_count);
+    const double cost = waves * fmax(steps * step_c[i], epi_c[i]) + epi_c[i];
+    if (cost < best_cost * 0.97) { best_cost = cost; best = bn; }      // ties (within 3 %) go to the wider tile
+  }
+  return best;
+}
+
 int run_gemm(const Operands& o, GemmP& p, int splits, cudaStream_t st) {
-  if (p.N > 128) return launch_bn<256>(o, p, splits, st);
-  if (p.N > 64) return launch_bn<128>(o, p, splits, st);
-  if (p.N > 32) return launch_bn<64>(o, p, splits, st);
-  return launch_bn<32>(o, p, splits, st);
+  switch (pick_bn(p, splits)) {
+    case 256: return launch_bn<256>(o, p, splits, st);
+    case 128: return launch_bn<128>(o, p, splits, st);
+    case 64: return launch_bn<64>(o, p, splits, st);
+    default: return launch_bn<32>(o, p, splits, st);
+  }
 }
 
 }  // namespace

@@ -10,6 +10,7 @@ from the library's Philox streams (no host sync, CUDA-graph safe).  Dropout foll
 reference (p_dropout for enc_p, 0.1 inside MelStyleEncoder).
 """
 import math
+import contextlib
 import os
 
 import torch
@@ -17,6 +18,7 @@ from torch import nn
 
 from . import ops
 
+D_LANES = max(1, min(6, int(os.environ.get("EVK_D_LANES", "6"))))   # streams the six discriminators are spread over
 SIDE_STREAMS = os.environ.get("EVK_SIDE_STREAMS", "1") != "0"     # prior encoder on a side stream (measured 66.5 -> 63.0 ms / step)
 LRELU_SLOPE = 0.1
 N_SYMBOLS = 732            # len(SYMBOLS): src/easevoice/text/symbols.py:410-412
@@ -390,16 +392,31 @@ class SynthesizerTrn(ParamTree):
             x = ops.conv_transpose(x, self.w(f"dec.ups.{i}"), self.b(f"dec.ups.{i}"), stride=u, pad=(k - u) // 2)
             xa = ops.lrelu(x, LRELU_SLOPE)                 # shared first activation of the three resblocks
             outs = []
+            # the three resblocks of a stage are independent chains of six convolutions; stage 0 is 40 tiles on 148 SMs and
+            # stage 1 is 2.16 waves of the persistent grid, so they run as three parallel branches (streams 2, 3 + current;
+            # 0 and 1 may still be busy with the prior encoder and the flow)
+            cur = torch.cuda.current_stream() if (SIDE_STREAMS and x.is_cuda) else None
+            lanes = [None, self._side_stream(x.device, 2), self._side_stream(x.device, 3)] if cur is not None and nk == 3 else [None] * nk
             for j, (rk, rd) in enumerate(zip(self.resblock_kernel_sizes, self.resblock_dilation_sizes)):
                 r = f"dec.resblocks.{i * nk + j}"
-                h, ha = x, xa
-                for l, d in enumerate(rd):
-                    t = ops.conv(ha, self.w(f"{r}.convs1.{l}"), self.b(f"{r}.convs1.{l}"), pad=(rk * d - d) // 2, dil=d,
-                                 act=ops.ACT_LRELU, slope=LRELU_SLOPE)
-                    h = ops.conv(t, self.w(f"{r}.convs2.{l}"), self.b(f"{r}.convs2.{l}"), pad=(rk - 1) // 2, res=h)
-                    if l < len(rd) - 1:
-                        ha = ops.lrelu(h, LRELU_SLOPE)
+                st = lanes[j]
+                if st is not None:
+                    st.wait_stream(cur)
+                    x.record_stream(st); xa.record_stream(st)
+                with (torch.cuda.stream(st) if st is not None else contextlib.nullcontext()):
+                    h, ha = x, xa
+                    for l, d in enumerate(rd):
+                        t = ops.conv(ha, self.w(f"{r}.convs1.{l}"), self.b(f"{r}.convs1.{l}"), pad=(rk * d - d) // 2, dil=d,
+                                     act=ops.ACT_LRELU, slope=LRELU_SLOPE)
+                        h = ops.conv(t, self.w(f"{r}.convs2.{l}"), self.b(f"{r}.convs2.{l}"), pad=(rk - 1) // 2, res=h)
+                        if l < len(rd) - 1:
+                            ha = ops.lrelu(h, LRELU_SLOPE)
+                if st is not None:
+                    h.record_stream(cur)
                 outs.append(h)
+            for st in lanes:
+                if st is not None:
+                    cur.wait_stream(st)
             x = ops.add3(outs[0], outs[1], outs[2], 1.0 / nk, 1.0 / nk, 1.0 / nk)
         x = ops.lrelu(x, 0.01)                             # F.leaky_relu default slope (models.py:467)
         # the single output channel is padded to 4 (zero weights) so that its gradients stay on the tensor-core kernels
@@ -599,13 +616,13 @@ class MultiPeriodDiscriminator(ParamTree):
                 # the six discriminators are independent chains whose later layers are far too small to fill the GPU: spread
                 # them over three streams (parallel branches of the captured graph; the backward follows the same streams)
                 cur = torch.cuda.current_stream()
-                lanes = [None, self._side_stream(x.device, 0), self._side_stream(x.device, 1)]
+                lanes = [None] + [self._side_stream(x.device, k) for k in range(D_LANES - 1)]
                 for st in lanes[1:]:
                     st.wait_stream(cur)
                     x.record_stream(st); x4.record_stream(st)
                 outs = []
                 for d in range(6):
-                    st = lanes[d % 3]
+                    st = lanes[d % D_LANES]
                     with torch.cuda.stream(st if st is not None else cur):
                         o = self._disc_s(x4) if d == 0 else self._disc_p(d, x, PERIODS[d - 1])
                     if st is not None:

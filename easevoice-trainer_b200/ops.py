@@ -77,7 +77,10 @@ def dispatch_stats():
     return dict(zip(DISPATCH_SLOTS, [float(v) for v in buf]))
 
 
-def _timed(name, fn, flops=0.0, nbytes=0.0):
+PROF_SHAPES = False        # tools/shape_profile.py: key the profile by launch shape as well as by kernel family
+
+
+def _timed(name, fn, flops=0.0, nbytes=0.0, tag=None):
     if _prof is None:
         return fn()
     before = dispatch_stats() if flops else None
@@ -90,6 +93,8 @@ def _timed(name, fn, flops=0.0, nbytes=0.0):
         grown = [k for k in DISPATCH_SLOTS if after[k] > before[k]]
         if grown:
             name = f"{name}:{grown[0]}"
+    if PROF_SHAPES and tag is not None:
+        name = f"{name}|{tag}"
     _prof.append((name, e0, e1, flops, nbytes))
     return r
 
@@ -100,11 +105,11 @@ def _call(name, *args):
     _timed(name, lambda: L.check(getattr(_lib(), name)(*args, _st())))
 
 
-def _call_f(name, flops, *args):
+def _call_f(name, flops, *args, tag=None):
     """_call with an algorithmic flop count attached (contractions: shows up in profile_end / the bench roofline)."""
     global _launches
     _launches += 1
-    _timed(name, lambda: L.check(getattr(_lib(), name)(*args, _st())), flops)
+    _timed(name, lambda: L.check(getattr(_lib(), name)(*args, _st())), flops, tag=tag)
 
 
 def _rows(t):
@@ -201,7 +206,8 @@ def _run_desc(fn, d):
     global _launches
     _launches += 1
     flops = 2.0 * d.Z * d.J * d.P * d.N * (d.C // max(d.G, 1)) * d.Q
-    _timed(fn, lambda: L.check(getattr(_lib(), fn)(ctypes.byref(d), _st())), flops)
+    _timed(fn, lambda: L.check(getattr(_lib(), fn)(ctypes.byref(d), _st())), flops,
+           tag=(f"Z{d.Z} J{d.J} P{d.P} C{d.C} N{d.N} Q{d.Q} s{d.is_}" if PROF_SHAPES else None))
 
 
 def _aligned(t, ld):
@@ -629,7 +635,8 @@ class _ConvFn(torch.autograd.Function):
                     splits = max(1, min(64, 148 // tiles, kblocks // 8))        # one full wave of (tile, split) CTAs
                     offa = (ctypes.c_int32 * nq)(*shifts)
                     _call_f("evk_conv_wgrad_tma", 2.0 * B * Ro * N * C * nq, _p(dyt), ldo, N * ldo, _p(xt), ldi, C * ldi, B * C * ldi,
-                            dpa.data_ptr() + 4 * qs[0] * N * lda, lda, qstep * N * lda, B, N, C, Ro, Ri, nq, P, offa, splits)
+                            dpa.data_ptr() + 4 * qs[0] * N * lda, lda, qstep * N * lda, B, N, C, Ro, Ri, nq, P, offa, splits,
+                            tag=f"B{B} Ro{Ro} P{P} C{C} N{N} nq{nq} splits{splits}")
             elif mma:
                 d = _desc(x=x, w=dpa, y=dy, res=None, bias=None, in_len=in_len, out_len=None,
                           x_sb=Tin * P * ldx, x_sh=Cg if G > 1 else 0, w_sb=0, w_sh=Ng * lda if G > 1 else 0, w_sq=N * lda,
