@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Small driver for ncu captures: a few launches of each kernel the roofline numbers are about.
   ncu --set full --clock-control none --import-source on -k regex:'gemm_tma|mel_fwd_warp|stft_|flash' -o gpurun_out/prof python tests/prof_kernels.py
-Order of launches (ncu ids): [gemm_tma slab=0] k11 128ch x2, [slab=1] k11 128ch x2, [slab=1] discP 1024 x2, mel x2 (|X|+mel), flash fwd/bwd x1.
+Order of launches (ncu ids): [gemm_tma slab=0] k11 128ch x2, [slab=1] k11 128ch x2, [slab=1] discP 1024 x2, GPT linear1 x2, mel x2 (|X|+mel), flash fwd/bwd x1.
 """
 import os
 import sys
@@ -28,6 +28,13 @@ with torch.no_grad():
     bd = torch.zeros(1024, device=dev)
     for _ in range(2):
         ops.conv(xd, wd, bd, pad=2, P=2)
+# GPT linear1 (20 480 x 512 -> 2048, ReLU): launches 6, 7 of gemm_tma
+xg = torch.randn(1, 20480, 512, device=dev)
+wg = ops.pack_weight(torch.randn(2048, 512, 1, device=dev) * 0.02, None)
+bg = torch.zeros(2048, device=dev)
+with torch.no_grad():
+    for _ in range(2):
+        ops.linear(xg, wg, bg, act=ops.ACT_RELU)
 bank = get_bank(32000, 2048, 128, 0.0, None, dev)
 wav = torch.rand(64, 221440, device=dev) - 0.5
 for _ in range(2):

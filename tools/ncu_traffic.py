@@ -5,7 +5,7 @@
   python tools/ncu_traffic.py gpurun_out/prof_raw.csv [key=kernel-name-substring ...]
 
 Each `key=substr` selects the launches whose kernel name contains `substr`; the heaviest one (largest duration) is
-reported under `key`.  Metrics: dram__bytes_read.sum + dram__bytes_write.sum, gpu__time_duration.sum, tensor-pipe and
+reported under `key`; `key=substr@n` takes the n-th matching launch (0-based, launch order) instead.  Metrics: dram__bytes_read.sum + dram__bytes_write.sum, gpu__time_duration.sum, tensor-pipe and
 DRAM utilisation."""
 import csv
 import json
@@ -32,11 +32,20 @@ def main():
     out = {}
     for key, sub in sel.items():
         best = None
+        nth = None
+        if "@" in sub:
+            sub, nth = sub.rsplit("@", 1)
+            nth = int(nth)
+        seen = 0
         for r in rows[2:]:
             if sub not in r[col["Kernel Name"]]:
                 continue
             dur = fnum(r[col["gpu__time_duration.sum"]]) * scale.get(unit("gpu__time_duration.sum"), 1.0)
-            if best is None or dur > best[0]:
+            if nth is not None:
+                if seen == nth:
+                    best = (dur, r)
+                seen += 1
+            elif best is None or dur > best[0]:
                 best = (dur, r)
         if best is None:
             continue
