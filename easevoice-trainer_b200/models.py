@@ -19,6 +19,7 @@ from torch import nn
 from . import ops
 
 D_LANES = max(1, min(6, int(os.environ.get("EVK_D_LANES", "6"))))   # streams the six discriminators are spread over
+D_PRIO = os.environ.get("EVK_D_PRIO", "0") == "1"                    # DiscriminatorS on a high-priority stream (experiment)
 SIDE_STREAMS = os.environ.get("EVK_SIDE_STREAMS", "1") != "0"     # prior encoder on a side stream (measured 66.5 -> 63.0 ms / step)
 LRELU_SLOPE = 0.1
 N_SYMBOLS = 732            # len(SYMBOLS): src/easevoice/text/symbols.py:410-412
@@ -58,11 +59,11 @@ class ParamTree(nn.Module):
             node = getattr(node, p)
         return True
 
-    def _side_stream(self, device, idx=0):
+    def _side_stream(self, device, idx=0, priority=0):
         key = f"_side{idx}"
         st = self.__dict__.get(key)
         if st is None or st.device != device:
-            st = torch.cuda.Stream(device=device)
+            st = torch.cuda.Stream(device=device, priority=priority)
             self.__dict__[key] = st
         return st
 
@@ -617,9 +618,13 @@ class MultiPeriodDiscriminator(ParamTree):
                 # them over three streams (parallel branches of the captured graph; the backward follows the same streams)
                 cur = torch.cuda.current_stream()
                 lanes = [None] + [self._side_stream(x.device, k) for k in range(D_LANES - 1)]
-                for st in lanes[1:]:
-                    st.wait_stream(cur)
-                    x.record_stream(st); x4.record_stream(st)
+                if D_PRIO and D_LANES == 6:
+                    # DiscriminatorS (grouped k = 41 convs, the longest of the six chains) on a high-priority stream
+                    lanes = [self._side_stream(x.device, 6, priority=-1), None] + lanes[1:5]
+                for st in lanes:
+                    if st is not None:
+                        st.wait_stream(cur)
+                        x.record_stream(st); x4.record_stream(st)
                 outs = []
                 for d in range(6):
                     st = lanes[d % D_LANES]
@@ -629,8 +634,9 @@ class MultiPeriodDiscriminator(ParamTree):
                         for t in (o[0], *o[1]):
                             t.record_stream(cur)
                     outs.append(o)
-                for st in lanes[1:]:
-                    cur.wait_stream(st)
+                for st in lanes:
+                    if st is not None:
+                        cur.wait_stream(st)
             else:
                 outs = [self._disc_s(x4)]
                 for d, period in enumerate(PERIODS, start=1):
