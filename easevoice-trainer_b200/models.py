@@ -527,6 +527,26 @@ class SynthesizerTrn(ParamTree):
         return cf(r["y_hat"]), commit, r["ids_slice"], y_mask, y_mask, lat, cf(r["quantized"])
 
 
+    @torch.no_grad()
+    def extract_latent(self, x, lengths=None):
+        """Reference contract (models.py:1015-1018; the one model call of Normalize.token, normalize.py:203):
+        x = HuBERT features [B, 768, T] -> semantic tokens `codes.transpose(0, 1)` = int64 [B, 1, T // 2].
+        Same two kernels as the frozen quantizer of the training forward: exact-fp32 stride-2 projection + exact-fp32
+        nearest-codeword search (token indices are bit-exact against the reference).  `lengths` (frames per row, optional):
+        rows may be zero-padded to a common T; tokens past lengths[b] // 2 are set to 0 and must be ignored by the caller."""
+        B, C, T = x.shape
+        T2 = T // 2                                              # the stride-2 projection drops an odd last frame
+        if T2 == 0:
+            return torch.zeros((B, 1, 0), device=x.device, dtype=torch.int64)
+        ssl = ops.to_channels_last(x[:, :, :2 * T2].float())
+        s = ops.conv_k2s2_fp32(ssl, self.P("ssl_proj.weight"), self.P("ssl_proj.bias"))
+        codes = ops.vq_nearest(s, self.P("quantizer.vq.layers.0._codebook.embed"))      # [B, T2]
+        if lengths is not None:
+            keep = torch.arange(T2, device=x.device)[None, :] < (lengths.to(x.device) // 2)[:, None]
+            codes = codes * keep
+        return codes.unsqueeze(1)
+
+
 # ====================================================================================================
 # MultiPeriodDiscriminator
 # ====================================================================================================

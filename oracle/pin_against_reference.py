@@ -345,10 +345,37 @@ def pin_gpt(cases=None, adam=True):
     return res
 
 
+def pin_extract_latent(models):
+    """Reference SynthesizerTrn.extract_latent (models.py:1015-1018) vs the oracle on seeded [1, 768, T] features of several
+    lengths (odd T included: the stride-2 projection drops the last frame); codes must be IDENTICAL.  Writes the golden the GPU
+    test and the CPU test read."""
+    m = dict(s2_oracle.S2_MODEL)
+    net_g = models.SynthesizerTrn(1025, 32, n_speakers=300, **m)
+    PG = s2_oracle.init_params(s2_oracle.generator_param_spec(), 1234)
+    net_g.load_state_dict(PG)
+    net_g.eval()
+    gold = {"g_seed": 1234, "ssl_seed": 77, "scale": 1.0, "cases": []}
+    g = torch.Generator().manual_seed(77)
+    for T in (2, 99, 346, 1001):
+        ssl = torch.randn(1, 768, T, generator=g)
+        with torch.no_grad():
+            ref = net_g.extract_latent(ssl)
+        ora = s2_oracle.extract_latent(PG, ssl)
+        assert ref.shape == ora.shape == (1, 1, T // 2), (ref.shape, ora.shape)
+        assert torch.equal(ref, ora), f"extract_latent codes differ at T={T}"
+        gold["cases"].append({"T": T, "codes": ref[0, 0].tolist()})
+    with open(os.path.join(GOLD, "extract_latent.json"), "w") as f:
+        json.dump(gold, f)
+    return {"cases": [c["T"] for c in gold["cases"]], "identical": True}
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     mp, models, losses, commons = import_reference()
+    if "--extract-latent" in sys.argv:   # only the Normalize.token golden (seconds)
+        print(pin_extract_latent(models))
+        return
     if "--full" in sys.argv:          # the benchmarked shapes (minutes of CPU time): python oracle/pin_against_reference.py --full
         mp.mel_basis.clear()
         report = {"s2": pin_s2(models, losses, commons, S2_FULL_CASES), "gpt": pin_gpt(GPT_FULL_CASES, adam=False)}
@@ -361,6 +388,7 @@ def main():
     mp.mel_basis.clear()  # see pin_mel: the reference's filterbank cache is not keyed by sampling rate
     report["s2"] = pin_s2(models, losses, commons)
     report["gpt"] = pin_gpt()
+    report["extract_latent"] = pin_extract_latent(models)
     with open(os.path.join(GOLD, "pin_report.json"), "w") as f:
         json.dump(report, f, indent=1)
     print("PIN OK")

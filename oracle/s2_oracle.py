@@ -422,6 +422,15 @@ def vq_nearest(x, embed):
     return dist.max(dim=-1).indices
 
 
+def extract_latent(P, ssl):
+    """SynthesizerTrn.extract_latent, models.py:1015-1018 (Normalize.token's only model call, normalize.py:203): ssl [B, 768, T]
+    -> ssl_proj (k = 2, stride 2) -> nearest codebook entry -> codes.transpose(0, 1) = [B, 1, T // 2] int64."""
+    s = F.conv1d(ssl, P["ssl_proj.weight"], P["ssl_proj.bias"], stride=2)
+    B, D, N = s.shape
+    embed = P["quantizer.vq.layers.0._codebook.embed"]
+    return vq_nearest(s.transpose(1, 2).reshape(B * N, D), embed).view(B, 1, N)
+
+
 def synthesizer_forward(P, ssl, y, y_lengths, text, text_lengths, noise, ids_slice, m=S2_MODEL, segment=32):
     """SynthesizerTrn.forward, models.py:904-946, with frozen quantizer (eval), dropout off,
     `noise` [B,192,T] for enc_q and `ids_slice` [B] injected."""

@@ -1393,12 +1393,52 @@ def check_side_streams():
     return out
 
 
+def check_normalize_token():
+    """SURVEY 8 row f3 (token half): SynthesizerTrn.extract_latent + the 6-name2semantic.tsv writer on the GPU vs the golden
+    the REFERENCE produced (tests/golden/extract_latent.json, oracle/pin_against_reference.py --extract-latent).  Bit-exact."""
+    import tempfile
+    from easevoice_trainer_b200 import normalize_token as nt
+    out = []
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "extract_latent.json")))
+    net_g, _, PG, _ = _load_models(gold["g_seed"], 4321)
+    g = _gen(gold["ssl_seed"])
+    feats = []
+    for case in gold["cases"]:
+        ssl = torch.randn(1, 768, case["T"], generator=g)
+        feats.append(ssl)
+        codes = net_g.extract_latent(ssl.to(DEV))
+        ok = tuple(codes.shape) == (1, 1, case["T"] // 2) and codes.dtype == torch.int64
+        out.append((f"extract_latent T={case['T']}: shape / dtype of the reference contract", 0.0 if ok else 1.0, 0.5))
+        out.append((f"extract_latent T={case['T']}: token mismatches vs the reference golden",
+                    float(sum(int(a != b) for a, b in zip(codes[0, 0].cpu().tolist(), case["codes"]))), 0.5))
+    toks = nt.extract_tokens(net_g, feats, max_batch=3)
+    out.append(("extract_tokens (zero-padded batches of 3): token mismatches vs the golden",
+                float(sum(int(a != b) for t, c in zip(toks, gold["cases"]) for a, b in zip(t, c["codes"])) +
+                      sum(abs(len(t) - len(c["codes"])) for t, c in zip(toks, gold["cases"]))), 0.5))
+    with tempfile.TemporaryDirectory() as d:
+        hub = os.path.join(d, "4-cnhubert")
+        os.makedirs(hub)
+        names = [f"utt{i}.wav" for i in range(len(feats))]
+        for n, f in zip(names, feats):
+            torch.save(f, os.path.join(hub, n + ".pt"))
+        lst = os.path.join(d, "refinements.list")
+        with open(lst, "w", encoding="utf8") as f:
+            f.write("".join(f"/some/dir/{n}|zh|text\n" for n in names))
+        tsv = os.path.join(d, "6-name2semantic.tsv")
+        n_written = nt.write_semantic_tsv(lst, hub, tsv, net_g)
+        lines = open(tsv, encoding="utf8").read().split("\n")
+        good = n_written == len(names) and lines[0] == "item_name\tsemantic_audio" and lines[-1] == "" and all(
+            lines[1 + i] == names[i] + "\t" + " ".join(str(v) for v in gold["cases"][i]["codes"]) for i in range(len(names)))
+        out.append(("6-name2semantic.tsv written from 4-cnhubert/*.pt == the reference's lines", 0.0 if good else 1.0, 0.5))
+    return out
+
+
 ALL = [check_conv, check_conv_transpose, check_elementwise, check_attention, check_vq_losses_optim, check_mel,
        lambda: check_s2("small"), lambda: check_s2("ragged"), check_api_layouts,
        check_gpt_kernels, check_scaled_adam, lambda: check_gpt("small"), lambda: check_gpt("ragged"),
        check_gpt_dpo_and_trainer, check_gemm_tma, check_vocoder_cfg5,
        lambda: check_s2_full("cfg3"), lambda: check_s2_full("cfg3r"), lambda: check_gpt_full("cfg2"),
-       check_sovits_train_e2e, check_stft, check_fused_dropout, check_side_streams]
+       check_sovits_train_e2e, check_stft, check_fused_dropout, check_side_streams, check_normalize_token]
 NAMES = ["conv", "conv_transpose", "elementwise", "attention", "vq_losses_optim", "mel", "s2_small", "s2_ragged", "api",
          "gpt_kernels", "scaled_adam", "gpt_small", "gpt_ragged", "gpt_dpo_trainer", "gemm_tma", "vocoder_cfg5",
-         "s2_cfg3", "s2_cfg3r", "gpt_cfg2", "sovits_train_e2e", "stft_mrstft", "fused_dropout", "side_streams"]
+         "s2_cfg3", "s2_cfg3r", "gpt_cfg2", "sovits_train_e2e", "stft_mrstft", "fused_dropout", "side_streams", "normalize_token"]

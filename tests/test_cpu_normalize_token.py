@@ -1,0 +1,67 @@
+"""Normalize.token (token half): the oracle restatement of extract_latent reproduces the golden produced by the
+reference (oracle/pin_against_reference.py --extract-latent), and the TSV writer keeps the reference's file format
+(normalize.py:195-211).  The model call of the writer is GPU-only; here it is replaced by the oracle to test the host logic."""
+import json
+import os
+
+import torch
+
+from oracle import s2_oracle
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _golden():
+    return json.load(open(os.path.join(ROOT, "tests", "golden", "extract_latent.json")))
+
+
+def test_oracle_extract_latent_matches_reference_golden():
+    gold = _golden()
+    P = s2_oracle.init_params(s2_oracle.generator_param_spec(), gold["g_seed"])
+    g = torch.Generator().manual_seed(gold["ssl_seed"])
+    for case in gold["cases"]:
+        ssl = torch.randn(1, 768, case["T"], generator=g)
+        codes = s2_oracle.extract_latent(P, ssl)
+        assert codes.shape == (1, 1, case["T"] // 2) and codes.dtype == torch.int64
+        assert codes[0, 0].tolist() == case["codes"]
+
+
+class _OracleVQ:
+    """stands in for models.SynthesizerTrn in the host-logic test: same extract_latent contract, computed by the oracle"""
+
+    def __init__(self, P):
+        self.P = P
+
+    def parameters(self):
+        return iter([torch.zeros(1)])
+
+    def extract_latent(self, x, lengths=None):
+        codes = s2_oracle.extract_latent(self.P, x[:, :, :x.shape[2] // 2 * 2])
+        if lengths is not None:
+            keep = torch.arange(codes.shape[2])[None, :] < (lengths // 2)[:, None]
+            codes = codes * keep[:, None, :]
+        return codes
+
+
+def test_semantic_tsv_writer_format_and_padding_invariance(tmp_path):
+    from easevoice_trainer_b200 import normalize_token as nt
+    gold = _golden()
+    P = s2_oracle.init_params(s2_oracle.generator_param_spec(), gold["g_seed"])
+    g = torch.Generator().manual_seed(gold["ssl_seed"])
+    hub = tmp_path / "4-cnhubert"
+    hub.mkdir()
+    names = ["a.wav", "b.wav", "c.wav", "d.wav"]
+    for n, case in zip(names, gold["cases"]):
+        torch.save(torch.randn(1, 768, case["T"], generator=g), str(hub / (n + ".pt")))
+    ref_list = tmp_path / "refinements.list"
+    # the second entry has no feature file (skipped like the reference does), quotes and a directory part are stripped
+    ref_list.write_text('"/data/denoise/a.wav"|zh|x\nmissing.wav|zh|y\nb.wav|en|z\n c.wav |zh|w\nd.wav|zh|v\n', encoding="utf8")
+    out = tmp_path / "6-name2semantic.tsv"
+    n = nt.write_semantic_tsv(str(ref_list), str(hub), str(out), _OracleVQ(P), max_batch=3)
+    assert n == 4
+    lines = out.read_text(encoding="utf8").split("\n")
+    assert lines[0] == "item_name\tsemantic_audio" and lines[-1] == ""
+    got = {l.split("\t")[0]: [int(v) for v in l.split("\t")[1].split(" ")] for l in lines[1:-1]}
+    assert list(got) == names                                  # file order = list order
+    for nme, case in zip(names, gold["cases"]):
+        assert got[nme] == case["codes"]                       # batched + zero-padded == one file at a time (the golden)
