@@ -527,6 +527,56 @@ class SynthesizerTrn(ParamTree):
         return cf(r["y_hat"]), commit, r["ids_slice"], y_mask, y_mask, lat, cf(r["quantized"])
 
 
+    def _flow_reverse(self, z, lengths, ge):
+        """ResidualCouplingBlock(reverse=True), models.py:316-319: Flip, then the mean-only coupling inverted
+        (modules.py:459-462: x1 = (x1 - m) * mask), flows 3..0."""
+        half = self.inter_channels // 2
+        for f in reversed(range(4)):
+            p = f"flow.flows.{2 * f}"
+            z = ops.flip_channels(z)
+            x0, x1 = z[:, :, :half], z[:, :, half:]
+            h = ops.linear(x0, self.w(p + ".pre"), self.b(p + ".pre"), out_len=lengths)
+            h = self._wn_stack(p + ".enc", h, lengths, ge, 4)
+            m = ops.linear(h, self.w(p + ".post"), self.b(p + ".post"), out_len=lengths)
+            x1 = ops.add(x1, m, 1.0, -1.0, length=lengths)
+            z = torch.cat([x0, x1], dim=-1)
+        return z
+
+    @torch.no_grad()
+    def decode(self, codes, text, refer, noise_scale=0.5, speed=1, noise=None):
+        """Reference contract (models.py:973-1013; the vocoder call of `TTS`, inference/tts.py): codes int64 [1, 1, T]
+        (n_q, batch, frames at 25 Hz), text int64 [1, X], refer = reference spectrogram [1, 1025, Tr] or a list of them
+        (their style vectors are averaged) -> waveform [1, 1, 2 T * hop].  `noise` [1, 192, 2T] replaces the internal normal
+        draw (tests); speed != 1 (linear resampling of the prior, models.py:246-248) is not implemented and raises."""
+        if speed != 1:
+            raise NotImplementedError("SynthesizerTrn.decode: speed != 1 is not implemented on the sm_100a path")
+        was_training = self.training
+        self.eval()
+        try:
+            refers = refer if isinstance(refer, (list, tuple)) else [refer]
+            dev = codes.device
+            ges = []
+            for r in refers:
+                rl = torch.full((r.shape[0],), r.shape[2], device=dev, dtype=torch.int32)
+                ges.append(self._ref_enc(ops.to_channels_last(r.float(), pad_to=4), rl))
+            ge = ges[0] if len(ges) == 1 else torch.stack(ges, 0).mean(0)
+            B, T = codes.shape[1], codes.shape[2]
+            lengths = torch.full((B,), 2 * T, device=dev, dtype=torch.int32)
+            text_len = torch.full((B,), text.shape[-1], device=dev, dtype=torch.int32)
+            embed = self.P("quantizer.vq.layers.0._codebook.embed")
+            quantized = ops.embedding(embed, codes[0].contiguous(), rep=2)       # quantizer.decode + nearest x2
+            stats = self._enc_p(quantized, lengths, text, text_len, ge)          # [B, 2T, 2 * 192] = [m_p | logs_p]
+            if noise is None:
+                noise = ops.randn((B, 2 * T, self.inter_channels), "decode.noise", device=dev)
+            else:
+                noise = ops.to_channels_last(noise.float())
+            z_p = ops.reparam(stats, noise * float(noise_scale), lengths)        # m_p + noise * exp(logs_p) * noise_scale
+            z = self._flow_reverse(z_p, lengths, ge)
+            o = self._generator(ops.rowmask(z, lengths), ge)
+            return ops.to_channels_first(o)
+        finally:
+            self.train(was_training)
+
     @torch.no_grad()
     def extract_latent(self, x, lengths=None):
         """Reference contract (models.py:1015-1018; the one model call of Normalize.token, normalize.py:203):

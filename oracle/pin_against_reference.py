@@ -369,12 +369,45 @@ def pin_extract_latent(models):
     return {"cases": [c["T"] for c in gold["cases"]], "identical": True}
 
 
+def pin_decode(models):
+    """Reference SynthesizerTrn.decode (models.py:973-1013) vs the oracle with torch.randn_like replaced by a seeded tensor;
+    writes tests/golden/decode.pt (inputs are regenerated from seeds, the golden holds the reference waveform)."""
+    m = dict(s2_oracle.S2_MODEL)
+    net_g = models.SynthesizerTrn(1025, 32, n_speakers=300, **m)
+    PG = s2_oracle.init_params(s2_oracle.generator_param_spec(), 1234)
+    net_g.load_state_dict(PG)
+    net_g.eval()
+    cfg = dict(g_seed=1234, seed=91, T=24, X=15, Tr=(60, 37), noise_scale=0.5)
+    g = torch.Generator().manual_seed(cfg["seed"])
+    codes = torch.randint(0, 1024, (1, 1, cfg["T"]), generator=g)
+    text = torch.randint(0, 300, (1, cfg["X"]), generator=g)
+    refers = [torch.rand(1, 1025, tr, generator=g) * 2.0 for tr in cfg["Tr"]]
+    noise = torch.randn(1, 192, 2 * cfg["T"], generator=g)
+    orig = torch.randn_like
+    torch.randn_like = lambda t, **kw: noise.to(t.dtype)
+    try:
+        with torch.no_grad():
+            ref = net_g.decode(codes, text, refers, noise_scale=cfg["noise_scale"])
+    finally:
+        torch.randn_like = orig
+    with torch.no_grad():
+        ora = s2_oracle.decode(PG, codes, text, refers, noise, cfg["noise_scale"])
+    assert ref.shape == ora.shape == (1, 1, 2 * cfg["T"] * 640), (ref.shape, ora.shape)
+    err = maxdiff(ref, ora)
+    assert err < 2e-5, err
+    torch.save({"cfg": cfg, "wave": ref.clone()}, os.path.join(GOLD, "decode.pt"))
+    return {"max_abs_diff_oracle_vs_reference": err, "samples": int(ref.numel()), "rms": float(ref.pow(2).mean().sqrt())}
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     mp, models, losses, commons = import_reference()
     if "--extract-latent" in sys.argv:   # only the Normalize.token golden (seconds)
         print(pin_extract_latent(models))
+        return
+    if "--decode" in sys.argv:           # only the TTS vocoder-call golden (seconds)
+        print(pin_decode(models))
         return
     if "--full" in sys.argv:          # the benchmarked shapes (minutes of CPU time): python oracle/pin_against_reference.py --full
         mp.mel_basis.clear()
@@ -389,6 +422,7 @@ def main():
     report["s2"] = pin_s2(models, losses, commons)
     report["gpt"] = pin_gpt()
     report["extract_latent"] = pin_extract_latent(models)
+    report["decode"] = pin_decode(models)
     with open(os.path.join(GOLD, "pin_report.json"), "w") as f:
         json.dump(report, f, indent=1)
     print("PIN OK")

@@ -388,6 +388,54 @@ def flow_forward(P, pfx, x, x_mask, g, hidden=192):
     return x
 
 
+def flow_reverse(P, pfx, x, x_mask, g, hidden=192):
+    """ResidualCouplingBlock(reverse=True), models.py:316-319: the flows in reverse order, i.e. Flip first, then the
+    mean-only coupling inverted, modules.py:459-462: x1 = (x1 - m) * exp(-0) * mask, x0 passes through."""
+    half = x.shape[1] // 2
+    for f in reversed(range(4)):
+        p = f"{pfx}.flows.{2 * f}"
+        x = x.flip(1)
+        x0, x1 = x[:, :half], x[:, half:]
+        h = conv1d(P, p + ".pre", x0) * x_mask
+        h = wn_stack(P, p + ".enc", h, x_mask, g, hidden, 5, 4)
+        m = conv1d(P, p + ".post", h) * x_mask
+        x1 = (x1 - m) * x_mask
+        x = torch.cat([x0, x1], 1)
+    return x
+
+
+def text_encoder(P, quantized, y_mask, text, t_mask, ge, m=S2_MODEL):
+    """TextEncoder.forward at speed == 1, models.py:228-251 -> (m_p, logs_p)."""
+    q = conv1d(P, "enc_p.ssl_proj", quantized * y_mask) * y_mask
+    q = attn_encoder(P, "enc_p.encoder_ssl", q * y_mask, y_mask, m["n_layers"] // 2)
+    t = F.embedding(text, P["enc_p.text_embedding.weight"]).transpose(1, 2)
+    t = attn_encoder(P, "enc_p.encoder_text", t * t_mask, t_mask, m["n_layers"])
+    q = mrte(P, "enc_p.mrte", q, y_mask, t, t_mask, ge)
+    q = attn_encoder(P, "enc_p.encoder2", q * y_mask, y_mask, m["n_layers"] // 2)
+    stats = conv1d(P, "enc_p.proj", q) * y_mask
+    return stats.split(m["inter_channels"], dim=1)
+
+
+def decode(P, codes, text, refers, noise, noise_scale=0.5, m=S2_MODEL):
+    """SynthesizerTrn.decode, models.py:973-1013 (the vocoder call of TTS, inference/tts.py), speed == 1, dropout off:
+    codes [1, 1, T] int64, text [1, X] int64, refers = list of reference spectrograms [1, 1025, Tr], noise [1, 192, 2T]
+    (stands for torch.randn_like) -> waveform [1, 1, 2T * 640]."""
+    ges = []
+    for r in refers:
+        rm = torch.ones(1, 1, r.shape[2], dtype=r.dtype)
+        ges.append(mel_style_encoder(P, "ref_enc", r[:, :704] * rm, rm))
+    ge = torch.stack(ges, 0).mean(0)
+    T2 = codes.shape[2] * 2
+    y_mask = torch.ones(1, 1, T2)
+    t_mask = torch.ones(1, 1, text.shape[1])
+    embed = P["quantizer.vq.layers.0._codebook.embed"]
+    quantized = F.embedding(codes[0], embed).transpose(1, 2).repeat_interleave(2, dim=2)   # quantizer.decode + nearest x2
+    m_p, logs_p = text_encoder(P, quantized, y_mask, text, t_mask, ge, m)
+    z_p = m_p + noise * torch.exp(logs_p) * noise_scale
+    z = flow_reverse(P, "flow", z_p, y_mask, ge)
+    return generator(P, "dec", z * y_mask, ge, m)
+
+
 def slice_segments(x, ids, size):
     """commons.py:42-48."""
     return torch.stack([x[i, :, int(ids[i]):int(ids[i]) + size] for i in range(x.shape[0])])

@@ -1433,12 +1433,47 @@ def check_normalize_token():
     return out
 
 
+def check_decode():
+    """SURVEY 8 row f4 (vocoder half): SynthesizerTrn.decode -- quantizer.decode, prior encoder, flow in REVERSE, generator --
+    vs the waveform the reference produced with the same injected noise (tests/golden/decode.pt,
+    oracle/pin_against_reference.py --decode) and vs the oracle."""
+    out = []
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "decode.pt"), weights_only=False)
+    c = gold["cfg"]
+    net_g, _, PG, _ = _load_models(c["g_seed"], 4321)
+    g = _gen(c["seed"])
+    codes = torch.randint(0, 1024, (1, 1, c["T"]), generator=g)
+    text = torch.randint(0, 300, (1, c["X"]), generator=g)
+    refers = [torch.rand(1, 1025, tr, generator=g) * 2.0 for tr in c["Tr"]]
+    noise = torch.randn(1, 192, 2 * c["T"], generator=g)
+    with torch.no_grad():
+        ora = s2_oracle.decode(PG, codes, text, refers, noise, c["noise_scale"])
+    out.append(("decode: oracle vs reference golden waveform", rel(ora, gold["wave"]), 1e-5))
+    o = net_g.decode(codes.to(DEV), text.to(DEV), [r.to(DEV) for r in refers], noise_scale=c["noise_scale"], noise=noise.to(DEV))
+    out.append(("decode: output shape [1, 1, 2T * 640]", 0.0 if tuple(o.shape) == (1, 1, 2 * c["T"] * 640) else 1.0, 0.5))
+    out.append(("decode: waveform vs reference golden (rel-L2)", rel(o, gold["wave"]), TOL_NET))
+    out.append(("decode: waveform vs oracle (rel-L2)", rel(o, ora), TOL_NET))
+    o1 = net_g.decode(codes.to(DEV), text.to(DEV), refers[0].to(DEV), noise_scale=c["noise_scale"], noise=noise.to(DEV))
+    with torch.no_grad():
+        ora1 = s2_oracle.decode(PG, codes, text, refers[:1], noise, c["noise_scale"])
+    out.append(("decode: single reference spectrogram (tensor, not list) vs oracle", rel(o1, ora1), TOL_NET))
+    o2 = net_g.decode(codes.to(DEV), text.to(DEV), refers[0].to(DEV))          # internal noise: finite, right shape, not the seeded one
+    ok = bool(torch.isfinite(o2).all()) and tuple(o2.shape) == tuple(o1.shape) and float((o2 - o1).abs().max()) > 0.0
+    out.append(("decode: internal normal draw when no noise is given", 0.0 if ok else 1.0, 0.5))
+    try:
+        net_g.decode(codes.to(DEV), text.to(DEV), refers[0].to(DEV), speed=1.2)
+        out.append(("decode: speed != 1 raises", 1.0, 0.5))
+    except NotImplementedError:
+        out.append(("decode: speed != 1 raises", 0.0, 0.5))
+    return out
+
+
 ALL = [check_conv, check_conv_transpose, check_elementwise, check_attention, check_vq_losses_optim, check_mel,
        lambda: check_s2("small"), lambda: check_s2("ragged"), check_api_layouts,
        check_gpt_kernels, check_scaled_adam, lambda: check_gpt("small"), lambda: check_gpt("ragged"),
        check_gpt_dpo_and_trainer, check_gemm_tma, check_vocoder_cfg5,
        lambda: check_s2_full("cfg3"), lambda: check_s2_full("cfg3r"), lambda: check_gpt_full("cfg2"),
-       check_sovits_train_e2e, check_stft, check_fused_dropout, check_side_streams, check_normalize_token]
+       check_sovits_train_e2e, check_stft, check_fused_dropout, check_side_streams, check_normalize_token, check_decode]
 NAMES = ["conv", "conv_transpose", "elementwise", "attention", "vq_losses_optim", "mel", "s2_small", "s2_ragged", "api",
          "gpt_kernels", "scaled_adam", "gpt_small", "gpt_ragged", "gpt_dpo_trainer", "gemm_tma", "vocoder_cfg5",
-         "s2_cfg3", "s2_cfg3r", "gpt_cfg2", "sovits_train_e2e", "stft_mrstft", "fused_dropout", "side_streams", "normalize_token"]
+         "s2_cfg3", "s2_cfg3r", "gpt_cfg2", "sovits_train_e2e", "stft_mrstft", "fused_dropout", "side_streams", "normalize_token", "decode"]

@@ -65,3 +65,20 @@ def test_semantic_tsv_writer_format_and_padding_invariance(tmp_path):
     assert list(got) == names                                  # file order = list order
     for nme, case in zip(names, gold["cases"]):
         assert got[nme] == case["codes"]                       # batched + zero-padded == one file at a time (the golden)
+
+
+def test_oracle_decode_matches_reference_golden():
+    """SURVEY 8 row f4 (vocoder half): the oracle restatement of SynthesizerTrn.decode (flow reversed) reproduces the waveform
+    of the reference (oracle/pin_against_reference.py --decode) from the same seeds."""
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "decode.pt"), weights_only=False)
+    c = gold["cfg"]
+    P = s2_oracle.init_params(s2_oracle.generator_param_spec(), c["g_seed"])
+    g = torch.Generator().manual_seed(c["seed"])
+    codes = torch.randint(0, 1024, (1, 1, c["T"]), generator=g)
+    text = torch.randint(0, 300, (1, c["X"]), generator=g)
+    refers = [torch.rand(1, 1025, tr, generator=g) * 2.0 for tr in c["Tr"]]
+    noise = torch.randn(1, 192, 2 * c["T"], generator=g)
+    with torch.no_grad():
+        w = s2_oracle.decode(P, codes, text, refers, noise, c["noise_scale"])
+    assert w.shape == gold["wave"].shape
+    assert float((w - gold["wave"]).abs().max()) < 2e-5
