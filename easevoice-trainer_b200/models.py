@@ -358,8 +358,9 @@ class SynthesizerTrn(ParamTree):
         x = ops.linear(x, self.w(pfx + ".fc.fc"), self.b(pfx + ".fc.fc"))
         return ops.masked_mean(x, length).unsqueeze(1)
 
-    def _enc_p(self, quantized, length, text, text_len, ge):
-        """TextEncoder.forward, models.py:228-251."""
+    def _enc_p(self, quantized, length, text, text_len, ge, speed=1):
+        """TextEncoder.forward, models.py:228-251.  speed != 1 (inference only, models.py:246-248): the encoder output is
+        resampled linearly to int(T / speed) + 1 frames before the projection; returns (stats, new_length) in that case."""
         y = ops.linear(ops.rowmask(quantized, length), self.w("enc_p.ssl_proj"), self.b("enc_p.ssl_proj"), out_len=length)
         y = self._attn_encoder("enc_p.encoder_ssl", y, length, self.n_layers // 2)
         t = ops.embedding(self.P("enc_p.text_embedding.weight"), text)
@@ -380,6 +381,14 @@ class SynthesizerTrn(ParamTree):
         x = ops.rowmask(ops.add_bvec(ops.add(a, ssl_enc), ge), length)
         y = ops.linear(x, self.w(m + ".c_post"), self.b(m + ".c_post"))
         y = self._attn_encoder("enc_p.encoder2", y, length, self.n_layers // 2)
+        if speed != 1:
+            # F.interpolate(y, size, mode="linear") along time, and the (all-ones) mask by nearest: rows are full length here
+            # because decode() runs one utterance at a time (y_lengths = [2T], models.py:995)
+            assert bool((length == y.shape[1]).all()), "speed != 1 needs unpadded rows"
+            Tn = int(y.shape[1] / speed) + 1
+            y = torch.nn.functional.interpolate(y.transpose(1, 2), size=Tn, mode="linear").transpose(1, 2).contiguous()
+            length = torch.full_like(length, Tn)
+            return ops.linear(y, self.w("enc_p.proj"), self.b("enc_p.proj"), out_len=length), length
         stats = ops.linear(y, self.w("enc_p.proj"), self.b("enc_p.proj"), out_len=length)
         return stats
 
@@ -546,10 +555,9 @@ class SynthesizerTrn(ParamTree):
     def decode(self, codes, text, refer, noise_scale=0.5, speed=1, noise=None):
         """Reference contract (models.py:973-1013; the vocoder call of `TTS`, inference/tts.py): codes int64 [1, 1, T]
         (n_q, batch, frames at 25 Hz), text int64 [1, X], refer = reference spectrogram [1, 1025, Tr] or a list of them
-        (their style vectors are averaged) -> waveform [1, 1, 2 T * hop].  `noise` [1, 192, 2T] replaces the internal normal
-        draw (tests); speed != 1 (linear resampling of the prior, models.py:246-248) is not implemented and raises."""
-        if speed != 1:
-            raise NotImplementedError("SynthesizerTrn.decode: speed != 1 is not implemented on the sm_100a path")
+        (their style vectors are averaged) -> waveform [1, 1, F * hop] with F = 2T frames, or int(2T / speed) + 1 when
+        speed != 1 (linear resampling of the prior encoder output, models.py:246-248).  `noise` [1, 192, F] replaces the
+        internal normal draw (tests)."""
         was_training = self.training
         self.eval()
         try:
@@ -565,9 +573,14 @@ class SynthesizerTrn(ParamTree):
             text_len = torch.full((B,), text.shape[-1], device=dev, dtype=torch.int32)
             embed = self.P("quantizer.vq.layers.0._codebook.embed")
             quantized = ops.embedding(embed, codes[0].contiguous(), rep=2)       # quantizer.decode + nearest x2
-            stats = self._enc_p(quantized, lengths, text, text_len, ge)          # [B, 2T, 2 * 192] = [m_p | logs_p]
+            if speed != 1:
+                if B != 1:
+                    raise ValueError("SynthesizerTrn.decode: speed != 1 takes one utterance at a time, like the reference")
+                stats, lengths = self._enc_p(quantized, lengths, text, text_len, ge, speed)
+            else:
+                stats = self._enc_p(quantized, lengths, text, text_len, ge)      # [B, F, 2 * 192] = [m_p | logs_p]
             if noise is None:
-                noise = ops.randn((B, 2 * T, self.inter_channels), "decode.noise", device=dev)
+                noise = ops.randn((B, stats.shape[1], self.inter_channels), "decode.noise", device=dev)
             else:
                 noise = ops.to_channels_last(noise.float())
             z_p = ops.reparam(stats, noise * float(noise_scale), lengths)        # m_p + noise * exp(logs_p) * noise_scale

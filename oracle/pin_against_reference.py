@@ -395,8 +395,24 @@ def pin_decode(models):
     assert ref.shape == ora.shape == (1, 1, 2 * cfg["T"] * 640), (ref.shape, ora.shape)
     err = maxdiff(ref, ora)
     assert err < 2e-5, err
-    torch.save({"cfg": cfg, "wave": ref.clone()}, os.path.join(GOLD, "decode.pt"))
-    return {"max_abs_diff_oracle_vs_reference": err, "samples": int(ref.numel()), "rms": float(ref.pow(2).mean().sqrt())}
+    # speed != 1: the prior is resampled to int(2T / speed) + 1 frames (models.py:246-248)
+    cfg["speed"] = 1.25
+    Fs = int(2 * cfg["T"] / cfg["speed"]) + 1
+    noise_s = torch.randn(1, 192, Fs, generator=g)
+    torch.randn_like = lambda t, **kw: noise_s.to(t.dtype)
+    try:
+        with torch.no_grad():
+            ref_s = net_g.decode(codes, text, refers, noise_scale=cfg["noise_scale"], speed=cfg["speed"])
+    finally:
+        torch.randn_like = orig
+    with torch.no_grad():
+        ora_s = s2_oracle.decode(PG, codes, text, refers, noise_s, cfg["noise_scale"], speed=cfg["speed"])
+    assert ref_s.shape == ora_s.shape == (1, 1, Fs * 640), (ref_s.shape, ora_s.shape)
+    err_s = maxdiff(ref_s, ora_s)
+    assert err_s < 2e-5, err_s
+    torch.save({"cfg": cfg, "wave": ref.clone(), "wave_speed": ref_s.clone()}, os.path.join(GOLD, "decode.pt"))
+    return {"max_abs_diff_oracle_vs_reference": err, "max_abs_diff_speed_1.25": err_s, "samples": int(ref.numel()),
+            "rms": float(ref.pow(2).mean().sqrt())}
 
 
 def main():

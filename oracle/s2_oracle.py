@@ -404,22 +404,26 @@ def flow_reverse(P, pfx, x, x_mask, g, hidden=192):
     return x
 
 
-def text_encoder(P, quantized, y_mask, text, t_mask, ge, m=S2_MODEL):
-    """TextEncoder.forward at speed == 1, models.py:228-251 -> (m_p, logs_p)."""
+def text_encoder(P, quantized, y_mask, text, t_mask, ge, m=S2_MODEL, speed=1):
+    """TextEncoder.forward, models.py:228-251 -> (m_p, logs_p, y_mask); speed != 1 resamples the encoder output, :246-248."""
     q = conv1d(P, "enc_p.ssl_proj", quantized * y_mask) * y_mask
     q = attn_encoder(P, "enc_p.encoder_ssl", q * y_mask, y_mask, m["n_layers"] // 2)
     t = F.embedding(text, P["enc_p.text_embedding.weight"]).transpose(1, 2)
     t = attn_encoder(P, "enc_p.encoder_text", t * t_mask, t_mask, m["n_layers"])
     q = mrte(P, "enc_p.mrte", q, y_mask, t, t_mask, ge)
     q = attn_encoder(P, "enc_p.encoder2", q * y_mask, y_mask, m["n_layers"] // 2)
+    if speed != 1:
+        q = F.interpolate(q, size=int(q.shape[-1] / speed) + 1, mode="linear")
+        y_mask = F.interpolate(y_mask, size=q.shape[-1], mode="nearest")
     stats = conv1d(P, "enc_p.proj", q) * y_mask
-    return stats.split(m["inter_channels"], dim=1)
+    m_p, logs_p = stats.split(m["inter_channels"], dim=1)
+    return m_p, logs_p, y_mask
 
 
-def decode(P, codes, text, refers, noise, noise_scale=0.5, m=S2_MODEL):
-    """SynthesizerTrn.decode, models.py:973-1013 (the vocoder call of TTS, inference/tts.py), speed == 1, dropout off:
-    codes [1, 1, T] int64, text [1, X] int64, refers = list of reference spectrograms [1, 1025, Tr], noise [1, 192, 2T]
-    (stands for torch.randn_like) -> waveform [1, 1, 2T * 640]."""
+def decode(P, codes, text, refers, noise, noise_scale=0.5, m=S2_MODEL, speed=1):
+    """SynthesizerTrn.decode, models.py:973-1013 (the vocoder call of TTS, inference/tts.py), dropout off:
+    codes [1, 1, T] int64, text [1, X] int64, refers = list of reference spectrograms [1, 1025, Tr], noise [1, 192, F]
+    (stands for torch.randn_like; F = 2T, or int(2T / speed) + 1) -> waveform [1, 1, F * 640]."""
     ges = []
     for r in refers:
         rm = torch.ones(1, 1, r.shape[2], dtype=r.dtype)
@@ -430,7 +434,7 @@ def decode(P, codes, text, refers, noise, noise_scale=0.5, m=S2_MODEL):
     t_mask = torch.ones(1, 1, text.shape[1])
     embed = P["quantizer.vq.layers.0._codebook.embed"]
     quantized = F.embedding(codes[0], embed).transpose(1, 2).repeat_interleave(2, dim=2)   # quantizer.decode + nearest x2
-    m_p, logs_p = text_encoder(P, quantized, y_mask, text, t_mask, ge, m)
+    m_p, logs_p, y_mask = text_encoder(P, quantized, y_mask, text, t_mask, ge, m, speed)
     z_p = m_p + noise * torch.exp(logs_p) * noise_scale
     z = flow_reverse(P, "flow", z_p, y_mask, ge)
     return generator(P, "dec", z * y_mask, ge, m)

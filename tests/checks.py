@@ -1460,11 +1460,14 @@ def check_decode():
     o2 = net_g.decode(codes.to(DEV), text.to(DEV), refers[0].to(DEV))          # internal noise: finite, right shape, not the seeded one
     ok = bool(torch.isfinite(o2).all()) and tuple(o2.shape) == tuple(o1.shape) and float((o2 - o1).abs().max()) > 0.0
     out.append(("decode: internal normal draw when no noise is given", 0.0 if ok else 1.0, 0.5))
-    try:
-        net_g.decode(codes.to(DEV), text.to(DEV), refers[0].to(DEV), speed=1.2)
-        out.append(("decode: speed != 1 raises", 1.0, 0.5))
-    except NotImplementedError:
-        out.append(("decode: speed != 1 raises", 0.0, 0.5))
+    # speed != 1: the prior encoder output is resampled to int(2T / speed) + 1 frames (models.py:246-248)
+    Fs = int(2 * c["T"] / c["speed"]) + 1
+    noise_s = torch.randn(1, 192, Fs, generator=g)
+    os_ = net_g.decode(codes.to(DEV), text.to(DEV), [r.to(DEV) for r in refers], noise_scale=c["noise_scale"], speed=c["speed"],
+                       noise=noise_s.to(DEV))
+    out.append((f"decode speed={c['speed']}: output shape [1, 1, (int(2T / speed) + 1) * 640]",
+                0.0 if tuple(os_.shape) == (1, 1, Fs * 640) else 1.0, 0.5))
+    out.append((f"decode speed={c['speed']}: waveform vs reference golden (rel-L2)", rel(os_, gold["wave_speed"]), TOL_NET))
     return out
 
 

@@ -82,3 +82,9 @@ def test_oracle_decode_matches_reference_golden():
         w = s2_oracle.decode(P, codes, text, refers, noise, c["noise_scale"])
     assert w.shape == gold["wave"].shape
     assert float((w - gold["wave"]).abs().max()) < 2e-5
+    Fs = int(2 * c["T"] / c["speed"]) + 1
+    noise_s = torch.randn(1, 192, Fs, generator=g)
+    with torch.no_grad():
+        ws = s2_oracle.decode(P, codes, text, refers, noise_s, c["noise_scale"], speed=c["speed"])
+    assert ws.shape == gold["wave_speed"].shape == (1, 1, Fs * 640)
+    assert float((ws - gold["wave_speed"]).abs().max()) < 2e-5
