@@ -273,6 +273,46 @@ __global__ void sadam_update_kernel(float* __restrict__ p, float* __restrict__ g
   }
 }
 
+// ---- KV-cache attention of one new token (T2SBlock.decode_next_token, t2s_model.py:203-221) --------------------------------
+// Cache rows are the in_proj outputs [q | k | v] (3 * H * 32 floats, row pitch ld) of every position so far; the query is the
+// q block of the LAST row.  One CTA per (head, batch item): each warp walks a quarter of the keys with an online softmax
+// (lane d owns dimension d of q, of the running output and of the dot-product reduction), the four partial states are merged
+// through shared memory.  Exact fp32 -- the sampled token must not depend on operand rounding.
+__global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restrict__ qkv, long long sb, int ld, int n, int H, float scale,
+                                                           float* __restrict__ out, int ldo) {
+  const int h = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* base = qkv + (long long)b * sb;
+  const int D = H * 32;
+  const float q = base[(long long)(n - 1) * ld + h * 32 + lane] * scale;
+  float m = -INFINITY, l = 0.f, acc = 0.f;
+  for (int j = warp; j < n; j += 4) {
+    const float* row = base + (long long)j * ld;
+    float s = q * row[D + h * 32 + lane];
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mn = fmaxf(m, s);
+    const float c = expf(m - mn), p = expf(s - mn);           // m = -inf on the first key: c = 0
+    l = l * c + p;
+    acc = acc * c + p * row[2 * D + h * 32 + lane];
+    m = mn;
+  }
+  __shared__ float sm_m[4], sm_l[4], sm_a[4][32];
+  if (lane == 0) { sm_m[warp] = m; sm_l[warp] = l; }
+  sm_a[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    float M = fmaxf(fmaxf(sm_m[0], sm_m[1]), fmaxf(sm_m[2], sm_m[3]));
+    float L = 0.f, A = 0.f;
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+      const float c = (sm_m[w] == -INFINITY) ? 0.f : expf(sm_m[w] - M);
+      L += sm_l[w] * c;
+      A += sm_a[w][lane] * c;
+    }
+    out[(long long)b * ldo + h * 32 + lane] = A / L;
+  }
+}
+
 }  // namespace
 }  // namespace evk
 
@@ -339,4 +379,12 @@ extern "C" int evk_scaled_adam(float* p, float* g, float* delta, float* v, const
   sadam_update_kernel<<<nchunks, 256, 0, st>>>(p, g, delta, v, (const long long*)chunks, (const long long*)numel, coef, glob, gscale, beta1, beta2, eps, scalar_max,
                                                zero_grad);
   return check_launch("sadam_update");
+}
+
+extern "C" int evk_attn_decode(const float* qkv, int64_t batch_stride, int32_t ld, int32_t n_keys, int32_t B, int32_t H, float scale,
+                               float* out, int32_t ldo, cudaStream_t st) {
+  EVK_REQUIRE(qkv && out && B >= 1 && H >= 1 && n_keys >= 1, EVK_ERR_ARG, "attn_decode: bad arguments");
+  EVK_REQUIRE(ld >= 3 * H * 32 && ldo >= H * 32, EVK_ERR_ARG, "attn_decode: row pitch %d / %d too small for %d heads of 32", ld, ldo, H);
+  attn_decode_kernel<<<dim3(H, B), 128, 0, st>>>(qkv, batch_stride, ld, n_keys, H, scale, out, ldo);
+  return check_launch("attn_decode");
 }

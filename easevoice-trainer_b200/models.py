@@ -105,7 +105,20 @@ class ParamTree(nn.Module):
         rec = getattr(self, "_recording", None)
         if rec is not None and all(r[0] != key for r in rec):
             rec.append((key, v, g, need_pb, pad0, pad1, torch.is_grad_enabled() and not self._frozen))
-        return ops.pack_weight(fz(v), fz(g) if g is not None else None, need_pb, pad0, pad1)
+        pw = ops.pack_weight(fz(v), fz(g) if g is not None else None, need_pb, pad0, pad1)
+        if act is not None and getattr(self, "_memo_pack", False):
+            act[key] = pw                      # inference: static weights are packed once and kept (see packed_for_inference)
+        return pw
+
+    def packed_for_inference(self):
+        """-> dict used as `self._active` during inference loops: every packed weight is produced on first use and reused until
+        a parameter changes (sum of the parameters' version counters)."""
+        ver = sum(int(p._version) for p in self.parameters()) + sum(int(b._version) for b in self.buffers())
+        cache = self.__dict__.get("_infer_pack")
+        if cache is None or cache[0] != ver:
+            cache = (ver, {})
+            self.__dict__["_infer_pack"] = cache
+        return cache[1]
 
     def b(self, pfx, pad=0):
         if not self.has(pfx + ".bias"):

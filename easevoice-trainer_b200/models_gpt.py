@@ -167,6 +167,121 @@ class Text2SemanticDecoder(ParamTree):
         return loss, out2[1]
 
 
+    # ---- inference: KV-cache decoding -------------------------------------------------------------------
+    @staticmethod
+    def logits_to_probs(logits, previous_tokens=None, temperature=1.0, top_k=None, top_p=None, repetition_penalty=1.0):
+        """utils.py:109-145 on a [1, V] row of logits (torch ops on the device: a 1 025-element row per token is not a kernel
+        problem).  Same order of operations: repetition penalty, nucleus cut, temperature, top-k cut, softmax."""
+        if previous_tokens is not None and repetition_penalty != 1.0:
+            previous_tokens = previous_tokens.long()
+            score = torch.gather(logits, dim=1, index=previous_tokens)
+            score = torch.where(score < 0, score * repetition_penalty, score / repetition_penalty)
+            logits.scatter_(dim=1, index=previous_tokens, src=score)   # IN PLACE, like the reference: the caller's EOS test (argmax of
+            #                                                            the same tensor) therefore sees the penalised logits
+        if top_p is not None and top_p < 1.0:
+            sorted_logits, sorted_indices = torch.sort(logits, descending=True)
+            cum = torch.cumsum(torch.softmax(sorted_logits, dim=-1), dim=-1)
+            remove = cum > top_p
+            remove[:, 0] = False
+            logits = logits.masked_fill(remove.scatter(dim=1, index=sorted_indices, src=remove), -float("inf"))
+        logits = logits / max(temperature, 1e-5)
+        if top_k is not None:
+            v, _ = torch.topk(logits, min(top_k, logits.size(-1)))
+            logits = torch.where(logits < v[:, -1].unsqueeze(-1), -float("inf"), logits)
+        return torch.softmax(logits, dim=-1)
+
+    def _infer_layer(self, i, h, cache, n_prev, X=None, xl=None, yl=None):
+        """One post-LN block in inference.  Prompt pass (X given): h [1, L, D], prefix-LM attention, cache rows 0..L-1 filled
+        (T2SBlock.process_prompt, t2s_model.py:121-185).  Token pass: h [1, 1, D], its in_proj row is appended to the cache
+        and attends every cached position (decode_next_token, :187-221)."""
+        p = f"h.layers.{i}."
+        H = self.num_head
+        qkv = ops.linear(h, self.w(p + "self_attn.in_proj", suffix="_weight"), self.P(p + "self_attn.in_proj_bias"))
+        L = qkv.shape[1]
+        cache[:, n_prev:n_prev + L].copy_(qkv)
+        if X is not None:
+            a = ops.flash_attention(qkv, heads=H, prefix=X, xlen=xl, ylen=yl, p_drop=0.0, tag=f"gpt.infer{i}")
+        else:
+            a = ops.attn_decode(cache, n_prev + 1, H)
+        a = ops.linear(a, self.w(p + "self_attn.out_proj"), self.b(p + "self_attn.out_proj"))
+        h = ops.layernorm(h, self.P(p + "norm1.weight"), self.P(p + "norm1.bias"), res=a)
+        f = ops.linear(h, self.w(p + "linear1"), self.b(p + "linear1"), act=ops.ACT_RELU)
+        f = ops.linear(f, self.w(p + "linear2"), self.b(p + "linear2"))
+        return ops.layernorm(h, self.P(p + "norm2.weight"), self.P(p + "norm2.bias"), res=f)
+
+    @torch.no_grad()
+    def infer_panel_naive(self, x, x_lens, prompts, bert_feature, top_k=-100, top_p=100, early_stop_num=-1, temperature=1.0,
+                          repetition_penalty=1.35, max_steps=1500, trace=None, **kwargs):
+        """t2s_model.py:762-867: one utterance (x [1, X] phoneme ids, bert_feature [1, 1024, X], prompts [1, Yp] semantic
+        tokens of the reference audio) -> (y[:, :-1] = prompt + generated tokens, index of the last generated token).
+        The prompt pass runs the training forward's kernels and fills a per-layer cache of in_proj rows; every further token is
+        24 x (6 Linear launches on a one-row operand + one KV-cache attention + two LayerNorms).  Sampling follows utils.py:102-157
+        (exponential-race multinomial on the device).  `trace` (list) receives the [1, V] logits of every step (tests).
+        Prompt-free decoding (prompts = None) is not implemented on this path."""
+        if prompts is None:
+            raise NotImplementedError("infer_panel: prompt-free decoding is not implemented on the sm_100a path")
+        assert x.shape[0] == 1 and prompts.shape[0] == 1, "one utterance at a time, like infer_panel_naive"
+        was_training = self.training
+        self.eval()
+        self._active, self._memo_pack = self.packed_for_inference(), True
+        try:
+            dev = x.device
+            D, V = self.model_dim, self.vocab_size
+            X, Yp = x.shape[1], prompts.shape[1]
+            y = prompts.to(torch.int64)
+            xe = self._embed_text(x, bert_feature, False)
+            ye = ops.embedding(self.P("ar_audio_embedding.word_embeddings.weight"), y)
+            pe = self.pe(max(X, Yp + max_steps + 2), dev)
+            h = ops.gpt_embed(xe, ye, self.P("ar_text_position.alpha"), self.P("ar_audio_position.alpha"), pe)
+            L0 = X + Yp
+            caches = [torch.empty((1, L0 + max_steps + 1, 3 * D), device=dev, dtype=torch.float32) for _ in range(self.num_layers)]
+            xl = torch.full((1,), X, device=dev, dtype=torch.int64)
+            yl = torch.full((1,), Yp, device=dev, dtype=torch.int64)
+            for i in range(self.num_layers):
+                h = self._infer_layer(i, h, caches[i], 0, X, xl, yl)
+            n = L0
+            Vp = (V + 3) // 4 * 4
+            head = self.w("ar_predict_layer", pad0=Vp)
+            emb = self.P("ar_audio_embedding.word_embeddings.weight")
+            a_audio = self.P("ar_audio_position.alpha")
+            prefix_len = Yp
+            last = h[:, -1:].contiguous()
+            stop = False
+            idx = 0
+            for idx in range(max_steps):
+                logits = ops.linear(last, head)[:, 0, :V]                        # [1, V]
+                if trace is not None:
+                    trace.append(logits.clone())
+                if idx < 11:                                                     # at least 10 tokens before EOS may win (:835-836)
+                    logits = logits[:, :-1]
+                probs = self.logits_to_probs(logits, y, temperature=temperature, top_k=top_k, top_p=top_p,
+                                             repetition_penalty=repetition_penalty)
+                q = torch.empty_like(probs).exponential_(1)
+                samples = torch.argmax(probs / q, dim=-1, keepdim=True).to(torch.int64)
+                y = torch.cat([y, samples], dim=1)
+                if early_stop_num != -1 and (y.shape[1] - prefix_len) > early_stop_num:
+                    stop = True
+                if int(torch.argmax(logits, dim=-1)[0]) == self.EOS or int(samples[0, 0]) == self.EOS:
+                    stop = True
+                if stop:
+                    break
+                # next input: embedding of the sampled token at position Yp + idx (t2s_model.py:861-862, x_scale = 1)
+                last = (emb[y[:, -1:]] + a_audio * pe[Yp + idx]).contiguous()
+                for i in range(self.num_layers):
+                    last = self._infer_layer(i, last, caches[i], n)
+                n += 1
+            return y[:, :-1], idx - 1
+        finally:
+            self._active, self._memo_pack = None, False
+            self.train(was_training)
+
+    def infer_panel(self, x, x_lens, prompts, bert_feature, top_k=-100, top_p=100, early_stop_num=-1, temperature=1.0,
+                    repetition_penalty=1.35, **kwargs):
+        """t2s_model.py:869-882."""
+        return self.infer_panel_naive(x, x_lens, prompts, bert_feature, top_k, top_p, early_stop_num, temperature,
+                                      repetition_penalty, **kwargs)
+
+
 def make_reject_y(y_o, y_lens, generator=None):
     """utils.py:195-232: per item, duplicate a random span of the PADDED row (the reference's `randint(0, 1)` always picks
     the repeat branch); rows are re-padded with 0 to the longest result.  Host-side integer work, as in the reference."""

@@ -1844,6 +1844,17 @@ class _CeFn(torch.autograd.Function):
         return dl, None, None, None, None
 
 
+def attn_decode(cache, n_keys, heads):
+    """cache [B, Lmax, 3 * heads * 32] = in_proj rows [q | k | v] of the positions so far -> attention output of the query in row
+    n_keys - 1 over keys 0 .. n_keys - 1: [B, 1, heads * 32].  No gradient (KV-cache decoding)."""
+    assert cache.dim() == 3 and cache.stride(2) == 1 and cache.shape[2] == 3 * heads * 32 and 1 <= n_keys <= cache.shape[1]
+    B = cache.shape[0]
+    out = torch.empty((B, 1, heads * 32), device=cache.device, dtype=torch.float32)
+    _call("evk_attn_decode", _p(cache), cache.stride(0), cache.stride(1), n_keys, B, heads, ctypes.c_float(1.0 / math.sqrt(32.0)),
+          _p(out), heads * 32)
+    return out
+
+
 def ce_sum_topk(logits, targets, topk=3, ignore_index=1024, V=None):
     """-> (sum cross-entropy (differentiable), device float32 [2] = (loss, top-k accuracy ignoring ignore_index)).
     V: number of real classes when the last dim of `logits` is zero-padded."""

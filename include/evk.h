@@ -375,6 +375,11 @@ int evk_sinepos_bwd(const float* dy, int32_t ldy, int64_t dy_sb, const float* pe
  * out2[0] = sum_r (lse_r - logit_r[target_r]); out2[1] = #hits / #valid, hit = fewer than top_k logits strictly above
  * the target's.  lse/nll: [rows] scratch kept for the backward; flags: [rows] bytes.
  * bwd: dl[r][c] = gscale[r / rows_per_g] * (softmax(logits_r)[c] - [c == target_r]). */
+/* KV-cache attention of one new token -- T2SBlock.decode_next_token (t2s_model.py:203-221), F.scaled_dot_product_attention
+ * without mask.  qkv: the in_proj outputs [q | k | v] (3 * H * 32 floats per row, pitch ld, batch stride `batch_stride`) of
+ * the n_keys positions so far; the query is the q block of row n_keys - 1.  out [B, H * 32] (pitch ldo).  Exact fp32. */
+int evk_attn_decode(const float* qkv, int64_t batch_stride, int32_t ld, int32_t n_keys, int32_t B, int32_t H, float scale,
+                    float* out, int32_t ldo, evk_stream_t stream);
 int evk_ce_fwd(const float* logits, int32_t ld, const int64_t* targets, int32_t rows, int32_t V, int32_t topk,
                int64_t ignore_index, float* lse, float* nll, uint8_t* flags, float* out2, evk_stream_t stream);
 int evk_ce_bwd(const float* logits, int32_t ld, const int64_t* targets, const float* lse, const float* gscale,

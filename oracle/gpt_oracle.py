@@ -116,6 +116,74 @@ def forward_old(P, x, x_lens, y, y_lens, bert, m=GPT_MODEL, taps=None):
     return loss, acc, logits, targets
 
 
+def logits_to_probs(logits, previous_tokens=None, temperature=1.0, top_k=None, top_p=None, repetition_penalty=1.0):
+    """utils.py:109-145.  The repetition penalty is written into `logits` IN PLACE (scatter_), as in the reference."""
+    if previous_tokens is not None and repetition_penalty != 1.0:
+        previous_tokens = previous_tokens.long()
+        score = torch.gather(logits, dim=1, index=previous_tokens)
+        score = torch.where(score < 0, score * repetition_penalty, score / repetition_penalty)
+        logits.scatter_(dim=1, index=previous_tokens, src=score)
+    if top_p is not None and top_p < 1.0:
+        sl, si = torch.sort(logits, descending=True)
+        remove = torch.cumsum(torch.softmax(sl, dim=-1), dim=-1) > top_p
+        remove[:, 0] = False
+        logits = logits.masked_fill(remove.scatter(dim=1, index=si, src=remove), -float("inf"))
+    logits = logits / max(temperature, 1e-5)
+    if top_k is not None:
+        v, _ = torch.topk(logits, min(top_k, logits.size(-1)))
+        logits = torch.where(logits < v[:, -1].unsqueeze(-1), -float("inf"), logits)
+    return torch.softmax(logits, dim=-1)
+
+
+def infer_panel(P, x, bert, prompts, top_k=-100, top_p=100, early_stop_num=-1, temperature=1.0, repetition_penalty=1.35,
+                m=GPT_MODEL, max_steps=1500, trace=None):
+    """Text2SemanticDecoder.infer_panel_naive, t2s_model.py:762-867, B = 1, prompts given.  No KV cache: every step re-runs
+    the stack on the whole sequence under the prefix-LM mask (text rows see text only, audio rows see text + earlier audio),
+    which is what process_prompt + decode_next_token compute incrementally.  -> (y[:, :-1], idx - 1); `trace` receives the raw
+    [1, V] logits of every step."""
+    D, H = m["hidden_dim"], m["head"]
+    dk = D // H
+    X = x.shape[1]
+    y = prompts.long()
+    Yp = y.shape[1]
+    xe = F.embedding(x, P["ar_text_embedding.word_embeddings.weight"]) + F.linear(bert.transpose(1, 2), P["bert_proj.weight"], P["bert_proj.bias"])
+    pe = sine_pe(max(X, Yp + max_steps + 2), D)
+    xe = xe + P["ar_text_position.alpha"] * pe[:X]
+    stop, idx = False, 0
+    for idx in range(max_steps):
+        Y = y.shape[1]
+        ye = F.embedding(y, P["ar_audio_embedding.word_embeddings.weight"]) + P["ar_audio_position.alpha"] * pe[:Y]
+        h = torch.cat([xe, ye], 1)
+        mask = prefix_lm_mask(torch.tensor([X]), torch.tensor([Y]), X, Y)
+        add = torch.zeros(mask.shape).masked_fill(mask, float("-inf")).unsqueeze(1)
+        L = X + Y
+        for i in range(m["n_layer"]):
+            p = f"h.layers.{i}."
+            qkv = F.linear(h, P[p + "self_attn.in_proj_weight"], P[p + "self_attn.in_proj_bias"])
+            q, k, v = [t.view(1, L, H, dk).transpose(1, 2) for t in qkv.split(D, dim=-1)]
+            att = torch.softmax(q @ k.transpose(-2, -1) / math.sqrt(dk) + add, dim=-1) @ v
+            att = F.linear(att.transpose(1, 2).reshape(1, L, D), P[p + "self_attn.out_proj.weight"], P[p + "self_attn.out_proj.bias"])
+            h = F.layer_norm(h + att, (D,), P[p + "norm1.weight"], P[p + "norm1.bias"], 1e-5)
+            ff = F.linear(torch.relu(F.linear(h, P[p + "linear1.weight"], P[p + "linear1.bias"])), P[p + "linear2.weight"], P[p + "linear2.bias"])
+            h = F.layer_norm(h + ff, (D,), P[p + "norm2.weight"], P[p + "norm2.bias"], 1e-5)
+        logits = F.linear(h[:, -1], P["ar_predict_layer.weight"])
+        if trace is not None:
+            trace.append(logits.clone())
+        if idx < 11:
+            logits = logits[:, :-1]
+        probs = logits_to_probs(logits, y, temperature=temperature, top_k=top_k, top_p=top_p, repetition_penalty=repetition_penalty)
+        q = torch.empty_like(probs).exponential_(1)
+        samples = torch.argmax(probs / q, dim=-1, keepdim=True).long()
+        y = torch.cat([y, samples], dim=1)
+        if early_stop_num != -1 and (y.shape[1] - Yp) > early_stop_num:
+            stop = True
+        if int(torch.argmax(logits, dim=-1)[0]) == m["EOS"] or int(samples[0, 0]) == m["EOS"]:
+            stop = True
+        if stop:
+            break
+    return y[:, :-1], idx - 1
+
+
 def forward_dpo(P, x, x_lens, y, y_lens, bert, reject_y, reject_lens, m=GPT_MODEL, beta=0.2):
     """t2s_model.py:393-429 with the rejected batch given (make_reject_y draws it at random, utils.py:195-232);
     dpo_loss / get_batch_logps: utils.py:160-192 (reference_free=True)."""

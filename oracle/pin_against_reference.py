@@ -226,13 +226,8 @@ GPT_CASES = (("small", 3, 3, 12, 20, False), ("ragged", 2, 4, 9, 17, True))
 GPT_FULL_CASES = (("cfg2", 24, 4, 256, 1024, True),)
 
 
-def pin_gpt(cases=None, adam=True):
-    """Stage-1 AR GPT: forward_old loss/acc/grads and ScaledAdam trajectories vs the reference classes.
-
-    torchmetrics is absent from this image: MulticlassAccuracy(top_k=3, average="micro", ignore_index=EOS) is stubbed
-    with its published semantics (a sample counts when the target is among the k largest logits; samples whose target is
-    ignore_index are dropped), so the accuracy value is pinned against that restatement only.
-    """
+def stub_torchmetrics():
+    """torchmetrics is absent from this image; see pin_gpt."""
     tm = types.ModuleType("torchmetrics")
     tmc = types.ModuleType("torchmetrics.classification")
 
@@ -250,6 +245,16 @@ def pin_gpt(cases=None, adam=True):
     tm.classification = tmc
     sys.modules["torchmetrics"] = tm
     sys.modules["torchmetrics.classification"] = tmc
+
+
+def pin_gpt(cases=None, adam=True):
+    """Stage-1 AR GPT: forward_old loss/acc/grads and ScaledAdam trajectories vs the reference classes.
+
+    torchmetrics is absent from this image: MulticlassAccuracy(top_k=3, average="micro", ignore_index=EOS) is stubbed
+    with its published semantics (a sample counts when the target is among the k largest logits; samples whose target is
+    ignore_index are dropped), so the accuracy value is pinned against that restatement only.
+    """
+    stub_torchmetrics()
     from src.easevoice.soundstorm.auto_reg.models.t2s_model import Text2SemanticDecoder
     from src.easevoice.soundstorm.auto_reg.modules.optim import ScaledAdam
     res = {}
@@ -415,12 +420,68 @@ def pin_decode(models):
             "rms": float(ref.pow(2).mean().sqrt())}
 
 
+def pin_infer_panel():
+    """Reference Text2SemanticDecoder.infer_panel_naive (t2s_model.py:762-867, KV cache, torch SDPA) vs the oracle (full
+    recompute under the prefix-LM mask), greedy (top_k = 1: the multinomial draw is then deterministic), repetition penalty
+    1.35, bounded by early_stop_num.  Token sequences must be IDENTICAL and per-step logits equal to fp32 noise.  Writes
+    tests/golden/infer_panel.json (tokens, logits of selected steps, top-2 margins)."""
+    stub_torchmetrics()
+    import src.easevoice.soundstorm.auto_reg.models.t2s_model as t2s_mod
+    m = dict(gpt_oracle.GPT_MODEL, n_layer=3)
+    ref = t2s_mod.Text2SemanticDecoder({"model": m}).eval()
+    P = gpt_oracle.init_params(gpt_oracle.gpt_param_spec(m), 14)
+    P["ar_text_position.alpha"].fill_(0.8); P["ar_audio_position.alpha"].fill_(1.3)
+    ref.load_state_dict(P)
+    cfg = dict(n_layer=3, param_seed=14, seed=23, X=21, Yp=17, early_stop_num=40, top_k=1, repetition_penalty=1.35, temperature=1.0)
+    g = torch.Generator().manual_seed(cfg["seed"])
+    x = torch.randint(0, m["phoneme_vocab_size"], (1, cfg["X"]), generator=g)
+    bert = torch.randn(1, 1024, cfg["X"], generator=g)
+    prompts = torch.randint(0, 1024, (1, cfg["Yp"]), generator=g)
+    ref_logits = []
+    orig_sample = t2s_mod.sample
+
+    def spy(logits, previous_tokens=None, **kw):
+        ref_logits.append(logits.clone())
+        return orig_sample(logits, previous_tokens, **kw)
+    t2s_mod.sample = spy
+    try:
+        with torch.no_grad():
+            y_ref, idx_ref = ref.infer_panel_naive(x, torch.tensor([cfg["X"]]), prompts, bert, top_k=cfg["top_k"], top_p=100,
+                                                   early_stop_num=cfg["early_stop_num"], temperature=cfg["temperature"],
+                                                   repetition_penalty=cfg["repetition_penalty"])
+    finally:
+        t2s_mod.sample = orig_sample
+    tr = []
+    with torch.no_grad():
+        y_ora, idx_ora = gpt_oracle.infer_panel(P, x, bert, prompts, top_k=cfg["top_k"], top_p=100, early_stop_num=cfg["early_stop_num"],
+                                                temperature=cfg["temperature"], repetition_penalty=cfg["repetition_penalty"], m=m, trace=tr)
+    assert torch.equal(y_ref.long(), y_ora.long()) and int(idx_ref) == int(idx_ora), (y_ref, y_ora, idx_ref, idx_ora)
+    assert len(tr) == len(ref_logits)
+    # the spy sees the logits AFTER the idx < 11 truncation: compare on the common columns
+    err = max(maxdiff(a, b[:, :a.shape[1]]) for a, b in zip(ref_logits, tr))
+    assert err < 2e-4, err
+    margins = []
+    for a in ref_logits:
+        t2 = a[0].topk(2).values
+        margins.append(float(t2[0] - t2[1]))
+    gold = {"cfg": cfg, "tokens": y_ref[0].tolist(), "idx": int(idx_ref), "top2_margin": margins,
+            "logits_step": {str(s): tr[s][0].tolist() for s in (0, 1, 12, len(tr) - 1)}}
+    with open(os.path.join(GOLD, "infer_panel.json"), "w") as f:
+        json.dump(gold, f)
+    return {"steps": len(tr), "generated": len(gold["tokens"]) - cfg["Yp"], "max_logit_diff_oracle_vs_reference": err,
+            "min_top2_margin": min(margins)}
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
     mp, models, losses, commons = import_reference()
     if "--extract-latent" in sys.argv:   # only the Normalize.token golden (seconds)
         print(pin_extract_latent(models))
+        return
+    if "--infer-panel" in sys.argv:      # only the AR decoding golden (needs the torchmetrics stub of pin_gpt: run after it)
+        stub_torchmetrics()
+        print(pin_infer_panel())
         return
     if "--decode" in sys.argv:           # only the TTS vocoder-call golden (seconds)
         print(pin_decode(models))
@@ -439,6 +500,7 @@ def main():
     report["gpt"] = pin_gpt()
     report["extract_latent"] = pin_extract_latent(models)
     report["decode"] = pin_decode(models)
+    report["infer_panel"] = pin_infer_panel()
     with open(os.path.join(GOLD, "pin_report.json"), "w") as f:
         json.dump(report, f, indent=1)
     print("PIN OK")

@@ -1471,12 +1471,73 @@ def check_decode():
     return out
 
 
+def check_infer_panel():
+    """SURVEY 8 row f4 (AR half): Text2SemanticDecoder.infer_panel -- prompt pass on the training kernels + KV-cache decoding
+    (evk_attn_decode) -- greedy, vs the token sequence and logits the REFERENCE decoded (tests/golden/infer_panel.json)."""
+    from easevoice_trainer_b200.models_gpt import Text2SemanticDecoder
+    from oracle import gpt_oracle
+    out = []
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "infer_panel.json")))
+    c = gold["cfg"]
+    m = dict(gpt_oracle.GPT_MODEL, n_layer=c["n_layer"])
+    P = gpt_oracle.init_params(gpt_oracle.gpt_param_spec(m), c["param_seed"])
+    P["ar_text_position.alpha"].fill_(0.8); P["ar_audio_position.alpha"].fill_(1.3)
+    net = Text2SemanticDecoder({"model": m})
+    net.load_state_dict(P)
+    net = net.to(DEV).eval()
+    g = _gen(c["seed"])
+    x = torch.randint(0, m["phoneme_vocab_size"], (1, c["X"]), generator=g)
+    bert = torch.randn(1, 1024, c["X"], generator=g)
+    prompts = torch.randint(0, 1024, (1, c["Yp"]), generator=g)
+    # ---- the KV-cache attention kernel alone vs torch
+    gg = _gen(5)
+    cache = torch.randn(2, 70, 3 * 512, generator=gg).to(DEV)
+    for n in (1, 2, 37, 70):
+        a = ops_mod().attn_decode(cache, n, 16)
+        q = cache[:, n - 1, :512].view(2, 16, 1, 32).double().cpu()
+        k = cache[:, :n, 512:1024].reshape(2, n, 16, 32).permute(0, 2, 1, 3).double().cpu()
+        v = cache[:, :n, 1024:].reshape(2, n, 16, 32).permute(0, 2, 1, 3).double().cpu()
+        ref = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(32.0), -1) @ v).permute(0, 2, 1, 3).reshape(2, 1, 512)
+        out.append((f"attn_decode n_keys={n} vs float64 softmax(q k^T / sqrt(32)) v", rel(a, ref), 2e-6))
+    # ---- greedy decoding
+    tr = []
+    y, idx = net.infer_panel(x.to(DEV), torch.tensor([c["X"]], device=DEV), prompts.to(DEV), bert.to(DEV), top_k=c["top_k"], top_p=100,
+                             early_stop_num=c["early_stop_num"], temperature=c["temperature"],
+                             repetition_penalty=c["repetition_penalty"], trace=tr)
+    toks = y[0].cpu().tolist()
+    ref_toks = gold["tokens"]
+    first_bad = next((i for i, (a, b) in enumerate(zip(toks, ref_toks)) if a != b), None)
+    if first_bad is None and len(toks) == len(ref_toks):
+        out.append(("infer_panel greedy: token sequence == the reference's (prompt + 40 generated)", 0.0, 0.5))
+        out.append(("infer_panel: index of the last generated token", abs(int(idx) - gold["idx"]), 0.5))
+    else:
+        # a TF32 Linear stack may flip an argmax only where the reference's own top-2 margin is inside the rounding noise
+        step = (first_bad if first_bad is not None else min(len(toks), len(ref_toks))) - c["Yp"]
+        margin = gold["top2_margin"][step] if 0 <= step < len(gold["top2_margin"]) else 1e9
+        out.append((f"infer_panel greedy: first divergence at step {step} has a reference top-2 margin {margin:.2e} < 2e-2", margin, 2e-2))
+    for s_, refl in gold["logits_step"].items():
+        s_i = int(s_)
+        if s_i < len(tr) and (first_bad is None or s_i <= first_bad - c["Yp"]):
+            out.append((f"infer_panel logits of step {s_i} vs reference (rel-L2)", rel(tr[s_i][0], torch.tensor(refl)), TOL_NET))
+    # sampling path (top_k = 5, temperature 0.8): runs, stops at early_stop_num, tokens in range
+    y2, idx2 = net.infer_panel(x.to(DEV), torch.tensor([c["X"]], device=DEV), prompts.to(DEV), bert.to(DEV), top_k=5, top_p=0.9,
+                               early_stop_num=12, temperature=0.8)
+    ok = y2.shape[1] <= c["Yp"] + 13 and int(y2.max()) <= 1024 and torch.equal(y2[:, :c["Yp"]].cpu(), prompts)
+    out.append(("infer_panel sampling (top_k 5, top_p 0.9, T 0.8, early stop 12): prompt kept, length bounded, ids in range", 0.0 if ok else 1.0, 0.5))
+    return out
+
+
+def ops_mod():
+    from easevoice_trainer_b200 import ops
+    return ops
+
+
 ALL = [check_conv, check_conv_transpose, check_elementwise, check_attention, check_vq_losses_optim, check_mel,
        lambda: check_s2("small"), lambda: check_s2("ragged"), check_api_layouts,
        check_gpt_kernels, check_scaled_adam, lambda: check_gpt("small"), lambda: check_gpt("ragged"),
        check_gpt_dpo_and_trainer, check_gemm_tma, check_vocoder_cfg5,
        lambda: check_s2_full("cfg3"), lambda: check_s2_full("cfg3r"), lambda: check_gpt_full("cfg2"),
-       check_sovits_train_e2e, check_stft, check_fused_dropout, check_side_streams, check_normalize_token, check_decode]
+       check_sovits_train_e2e, check_stft, check_fused_dropout, check_side_streams, check_normalize_token, check_decode, check_infer_panel]
 NAMES = ["conv", "conv_transpose", "elementwise", "attention", "vq_losses_optim", "mel", "s2_small", "s2_ragged", "api",
          "gpt_kernels", "scaled_adam", "gpt_small", "gpt_ragged", "gpt_dpo_trainer", "gemm_tma", "vocoder_cfg5",
-         "s2_cfg3", "s2_cfg3r", "gpt_cfg2", "sovits_train_e2e", "stft_mrstft", "fused_dropout", "side_streams", "normalize_token", "decode"]
+         "s2_cfg3", "s2_cfg3r", "gpt_cfg2", "sovits_train_e2e", "stft_mrstft", "fused_dropout", "side_streams", "normalize_token", "decode", "infer_panel"]

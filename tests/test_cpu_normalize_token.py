@@ -88,3 +88,25 @@ def test_oracle_decode_matches_reference_golden():
         ws = s2_oracle.decode(P, codes, text, refers, noise_s, c["noise_scale"], speed=c["speed"])
     assert ws.shape == gold["wave_speed"].shape == (1, 1, Fs * 640)
     assert float((ws - gold["wave_speed"]).abs().max()) < 2e-5
+
+
+def test_oracle_infer_panel_matches_reference_golden():
+    """SURVEY 8 row f4 (AR half): the oracle restatement of infer_panel_naive (no cache: full recompute under the prefix-LM mask)
+    reproduces the greedy token sequence the reference decoded with its KV cache (oracle/pin_against_reference.py --infer-panel)."""
+    from oracle import gpt_oracle
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "infer_panel.json")))
+    c = gold["cfg"]
+    m = dict(gpt_oracle.GPT_MODEL, n_layer=c["n_layer"])
+    P = gpt_oracle.init_params(gpt_oracle.gpt_param_spec(m), c["param_seed"])
+    P["ar_text_position.alpha"].fill_(0.8); P["ar_audio_position.alpha"].fill_(1.3)
+    g = torch.Generator().manual_seed(c["seed"])
+    x = torch.randint(0, m["phoneme_vocab_size"], (1, c["X"]), generator=g)
+    bert = torch.randn(1, 1024, c["X"], generator=g)
+    prompts = torch.randint(0, 1024, (1, c["Yp"]), generator=g)
+    tr = []
+    with torch.no_grad():
+        y, idx = gpt_oracle.infer_panel(P, x, bert, prompts, top_k=c["top_k"], top_p=100, early_stop_num=c["early_stop_num"],
+                                        temperature=c["temperature"], repetition_penalty=c["repetition_penalty"], m=m, trace=tr)
+    assert y[0].tolist() == gold["tokens"] and int(idx) == gold["idx"]
+    for s_, ref in gold["logits_step"].items():
+        assert float((tr[int(s_)][0] - torch.tensor(ref)).abs().max()) < 2e-4
