@@ -278,8 +278,9 @@ __global__ void sadam_update_kernel(float* __restrict__ p, float* __restrict__ g
 // q block of the LAST row.  One CTA per (head, batch item): each warp walks a quarter of the keys with an online softmax
 // (lane d owns dimension d of q, of the running output and of the dot-product reduction), the four partial states are merged
 // through shared memory.  Exact fp32 -- the sampled token must not depend on operand rounding.
-__global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restrict__ qkv, long long sb, int ld, int n, int H, float scale,
-                                                           float* __restrict__ out, int ldo) {
+__global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restrict__ qkv, long long sb, int ld, int n, const int* __restrict__ n_dev,
+                                                           int H, float scale, float* __restrict__ out, int ldo) {
+  if (n_dev) n = *n_dev + 1;                                     // graph replay: keys 0 .. *n_dev (the row just appended)
   const int h = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* base = qkv + (long long)b * sb;
   const int D = H * 32;
@@ -313,6 +314,13 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restric
   }
 }
 
+// cache[b][*pos][0 .. W) = row[b][0 .. W): the position comes from device memory so that the step can be a replayed CUDA graph
+__global__ void cache_append_kernel(const float* __restrict__ row, int ldr, float* __restrict__ cache, long long sb, int ld,
+                                    const int* __restrict__ pos, int W) {
+  const int b = blockIdx.y;
+  float* dst = cache + (long long)b * sb + (long long)(*pos) * ld;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < W; i += gridDim.x * blockDim.x) dst[i] = row[(long long)b * ldr + i];
+}
 }  // namespace
 }  // namespace evk
 
@@ -385,6 +393,21 @@ extern "C" int evk_attn_decode(const float* qkv, int64_t batch_stride, int32_t l
                                float* out, int32_t ldo, cudaStream_t st) {
   EVK_REQUIRE(qkv && out && B >= 1 && H >= 1 && n_keys >= 1, EVK_ERR_ARG, "attn_decode: bad arguments");
   EVK_REQUIRE(ld >= 3 * H * 32 && ldo >= H * 32, EVK_ERR_ARG, "attn_decode: row pitch %d / %d too small for %d heads of 32", ld, ldo, H);
-  attn_decode_kernel<<<dim3(H, B), 128, 0, st>>>(qkv, batch_stride, ld, n_keys, H, scale, out, ldo);
+  attn_decode_kernel<<<dim3(H, B), 128, 0, st>>>(qkv, batch_stride, ld, n_keys, nullptr, H, scale, out, ldo);
   return check_launch("attn_decode");
+}
+
+extern "C" int evk_attn_decode_dev(const float* qkv, int64_t batch_stride, int32_t ld, const int32_t* n_prev_dev, int32_t B, int32_t H,
+                                   float scale, float* out, int32_t ldo, cudaStream_t st) {
+  EVK_REQUIRE(qkv && out && n_prev_dev && B >= 1 && H >= 1, EVK_ERR_ARG, "attn_decode_dev: bad arguments");
+  EVK_REQUIRE(ld >= 3 * H * 32 && ldo >= H * 32, EVK_ERR_ARG, "attn_decode_dev: row pitch %d / %d too small for %d heads of 32", ld, ldo, H);
+  attn_decode_kernel<<<dim3(H, B), 128, 0, st>>>(qkv, batch_stride, ld, 0, n_prev_dev, H, scale, out, ldo);
+  return check_launch("attn_decode_dev");
+}
+
+extern "C" int evk_cache_append(const float* row, int32_t ldr, float* cache, int64_t batch_stride, int32_t ld, const int32_t* pos_dev,
+                                int32_t B, int32_t W, cudaStream_t st) {
+  EVK_REQUIRE(row && cache && pos_dev && B >= 1 && W >= 1 && W <= ld && W <= ldr, EVK_ERR_ARG, "cache_append: bad arguments");
+  cache_append_kernel<<<dim3(cdiv(W, 256), B), 256, 0, st>>>(row, ldr, cache, batch_stride, ld, pos_dev, W);
+  return check_launch("cache_append");
 }

@@ -15,11 +15,15 @@ dropouts even though configs/gpt.yaml says `dropout: 0` (t2s_model.py:276-293); 
 (default 0.1) and can be set to 0 for parity runs.
 """
 import math
+import os
 
 import torch
 
 from . import ops
 from .models import ParamTree
+
+
+INFER_GRAPH = os.environ.get("EVK_INFER_GRAPH", "1") != "0"      # token step of infer_panel as one replayed CUDA graph
 
 
 def sine_table(length, dim):
@@ -198,16 +202,54 @@ class Text2SemanticDecoder(ParamTree):
         H = self.num_head
         qkv = ops.linear(h, self.w(p + "self_attn.in_proj", suffix="_weight"), self.P(p + "self_attn.in_proj_bias"))
         L = qkv.shape[1]
-        cache[:, n_prev:n_prev + L].copy_(qkv)
-        if X is not None:
+        if torch.is_tensor(n_prev):                                # device-side position: the step is a replayed CUDA graph
+            a = ops.attn_decode_dev(cache, n_prev, H, qkv)
+        elif X is not None:
+            cache[:, n_prev:n_prev + L].copy_(qkv)
             a = ops.flash_attention(qkv, heads=H, prefix=X, xlen=xl, ylen=yl, p_drop=0.0, tag=f"gpt.infer{i}")
         else:
+            cache[:, n_prev:n_prev + L].copy_(qkv)
             a = ops.attn_decode(cache, n_prev + 1, H)
         a = ops.linear(a, self.w(p + "self_attn.out_proj"), self.b(p + "self_attn.out_proj"))
         h = ops.layernorm(h, self.P(p + "norm1.weight"), self.P(p + "norm1.bias"), res=a)
         f = ops.linear(h, self.w(p + "linear1"), self.b(p + "linear1"), act=ops.ACT_RELU)
         f = ops.linear(f, self.w(p + "linear2"), self.b(p + "linear2"))
         return ops.layernorm(h, self.P(p + "norm2.weight"), self.P(p + "norm2.bias"), res=f)
+
+    def _infer_state(self, dev, need_rows):
+        """Per-layer caches of in_proj rows + the static buffers / graph of the token step, kept across calls while the
+        parameters (version counters) and the capacity allow."""
+        ver = sum(int(p._version) for p in self.parameters())
+        st = self.__dict__.get("_infer_st")
+        if st is None or st["ver"] != ver or st["dev"] != dev or st["rows"] < need_rows:
+            rows = (need_rows + 511) // 512 * 512
+            D, Vp = self.model_dim, (self.vocab_size + 3) // 4 * 4
+            st = dict(ver=ver, dev=dev, rows=rows, graph=None,
+                      caches=[torch.empty((1, rows, 3 * D), device=dev, dtype=torch.float32) for _ in range(self.num_layers)],
+                      n=torch.zeros(1, device=dev, dtype=torch.int32), x=torch.zeros((1, 1, D), device=dev, dtype=torch.float32),
+                      logits=torch.zeros((1, 1, Vp), device=dev, dtype=torch.float32))
+            self.__dict__["_infer_st"] = st
+        return st
+
+    def _capture_token_step(self, st, head):
+        def step():
+            h = st["x"]
+            for i in range(self.num_layers):
+                h = self._infer_layer(i, h, st["caches"][i], st["n"])
+            st["logits"].copy_(ops.linear(h, head))
+            st["n"].add_(1)
+        n0 = st["n"].clone()
+        side = torch.cuda.Stream(device=st["dev"])
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                              # warm-up outside capture (allocator, lazy inits)
+            step()
+        torch.cuda.current_stream().wait_stream(side)
+        st["n"].copy_(n0)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            step()
+        st["n"].copy_(n0)                                          # capture does not execute: the position is still n0
+        st["graph"] = g
 
     @torch.no_grad()
     def infer_panel_naive(self, x, x_lens, prompts, bert_feature, top_k=-100, top_p=100, early_stop_num=-1, temperature=1.0,
@@ -234,7 +276,8 @@ class Text2SemanticDecoder(ParamTree):
             pe = self.pe(max(X, Yp + max_steps + 2), dev)
             h = ops.gpt_embed(xe, ye, self.P("ar_text_position.alpha"), self.P("ar_audio_position.alpha"), pe)
             L0 = X + Yp
-            caches = [torch.empty((1, L0 + max_steps + 1, 3 * D), device=dev, dtype=torch.float32) for _ in range(self.num_layers)]
+            st = self._infer_state(dev, L0 + max_steps + 1)
+            caches = st["caches"]
             xl = torch.full((1,), X, device=dev, dtype=torch.int64)
             yl = torch.full((1,), Yp, device=dev, dtype=torch.int64)
             for i in range(self.num_layers):
@@ -245,11 +288,16 @@ class Text2SemanticDecoder(ParamTree):
             emb = self.P("ar_audio_embedding.word_embeddings.weight")
             a_audio = self.P("ar_audio_position.alpha")
             prefix_len = Yp
-            last = h[:, -1:].contiguous()
             stop = False
             idx = 0
+            use_graph = INFER_GRAPH
+            if use_graph:
+                st["n"].fill_(n)
+                st["logits"].copy_(ops.linear(h[:, -1:].contiguous(), head))
+            else:
+                last = h[:, -1:].contiguous()
             for idx in range(max_steps):
-                logits = ops.linear(last, head)[:, 0, :V]                        # [1, V]
+                logits = (st["logits"].clone() if use_graph else ops.linear(last, head))[:, 0, :V]      # [1, V]
                 if trace is not None:
                     trace.append(logits.clone())
                 if idx < 11:                                                     # at least 10 tokens before EOS may win (:835-836)
@@ -267,9 +315,17 @@ class Text2SemanticDecoder(ParamTree):
                     break
                 # next input: embedding of the sampled token at position Yp + idx (t2s_model.py:861-862, x_scale = 1)
                 last = (emb[y[:, -1:]] + a_audio * pe[Yp + idx]).contiguous()
-                for i in range(self.num_layers):
-                    last = self._infer_layer(i, last, caches[i], n)
-                n += 1
+                if use_graph:
+                    # the whole 24-layer token step (+ the vocabulary projection) is ONE graph replay; the position lives in
+                    # device memory (st["n"], advanced inside the graph), the token embedding is the only input
+                    st["x"].copy_(last)
+                    if st["graph"] is None:
+                        self._capture_token_step(st, head)
+                    st["graph"].replay()
+                else:
+                    for i in range(self.num_layers):
+                        last = self._infer_layer(i, last, caches[i], n)
+                    n += 1
             return y[:, :-1], idx - 1
         finally:
             self._active, self._memo_pack = None, False

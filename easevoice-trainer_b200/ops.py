@@ -1855,6 +1855,19 @@ def attn_decode(cache, n_keys, heads):
     return out
 
 
+def attn_decode_dev(cache, n_prev_dev, heads, row):
+    """Graph-replayable token step: append `row` [B, 1, 3 * heads * 32] at index *n_prev_dev (int32 device scalar) of the cache
+    and attend rows 0 .. *n_prev_dev.  -> [B, 1, heads * 32]."""
+    assert cache.dim() == 3 and cache.stride(2) == 1 and cache.shape[2] == 3 * heads * 32 and n_prev_dev.dtype == torch.int32
+    B, W = cache.shape[0], cache.shape[2]
+    row = row.contiguous()
+    _call("evk_cache_append", _p(row), W, _p(cache), cache.stride(0), cache.stride(1), _p(n_prev_dev), B, W)
+    out = torch.empty((B, 1, heads * 32), device=cache.device, dtype=torch.float32)
+    _call("evk_attn_decode_dev", _p(cache), cache.stride(0), cache.stride(1), _p(n_prev_dev), B, heads,
+          ctypes.c_float(1.0 / math.sqrt(32.0)), _p(out), heads * 32)
+    return out
+
+
 def ce_sum_topk(logits, targets, topk=3, ignore_index=1024, V=None):
     """-> (sum cross-entropy (differentiable), device float32 [2] = (loss, top-k accuracy ignoring ignore_index)).
     V: number of real classes when the last dim of `logits` is zero-padded."""

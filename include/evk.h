@@ -380,6 +380,12 @@ int evk_sinepos_bwd(const float* dy, int32_t ldy, int64_t dy_sb, const float* pe
  * the n_keys positions so far; the query is the q block of row n_keys - 1.  out [B, H * 32] (pitch ldo).  Exact fp32. */
 int evk_attn_decode(const float* qkv, int64_t batch_stride, int32_t ld, int32_t n_keys, int32_t B, int32_t H, float scale,
                     float* out, int32_t ldo, evk_stream_t stream);
+/* The same with the position in DEVICE memory (a decode step replayed as a CUDA graph): *n_prev_dev = rows already in the cache
+ * before this token; evk_cache_append writes the token's row at that index, evk_attn_decode_dev attends rows 0 .. *n_prev_dev. */
+int evk_attn_decode_dev(const float* qkv, int64_t batch_stride, int32_t ld, const int32_t* n_prev_dev, int32_t B, int32_t H,
+                        float scale, float* out, int32_t ldo, evk_stream_t stream);
+int evk_cache_append(const float* row, int32_t ldr, float* cache, int64_t batch_stride, int32_t ld, const int32_t* pos_dev,
+                     int32_t B, int32_t W, evk_stream_t stream);
 int evk_ce_fwd(const float* logits, int32_t ld, const int64_t* targets, int32_t rows, int32_t V, int32_t topk,
                int64_t ignore_index, float* lse, float* nll, uint8_t* flags, float* out2, evk_stream_t stream);
 int evk_ce_bwd(const float* logits, int32_t ld, const int64_t* targets, const float* lse, const float* gscale,
