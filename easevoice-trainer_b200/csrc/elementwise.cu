@@ -28,6 +28,7 @@ __global__ void unary_kernel(int op, float alpha, const float* __restrict__ x, i
       case 1: o = v > 0.f ? v : v * alpha; break;
       case 2: o = tanhf(v); break;
       case 3: o = v * tanhf(softplusf_(v)); break;
+      case 6: o = 0.5f * v * (1.f + erff(v * 0.70710678118654752f)); break;     // exact (erf) GELU: HuBERT feature extractor / FFN, forward only
       default: o = fmaxf(v, 0.f); break;
     }
     y[r * ldy + c] = o;
@@ -466,7 +467,7 @@ using namespace evk;
 
 extern "C" int evk_unary(int32_t op, float alpha, const float* x, int32_t ldx, float* y, int32_t ldy, int64_t rows,
                          int32_t C, evk_stream_t stream) {
-  EVK_REQUIRE(x && y && op >= 0 && op <= 4, EVK_ERR_ARG, "unary: bad arguments");
+  EVK_REQUIRE(x && y && ((op >= 0 && op <= 4) || op == 6), EVK_ERR_ARG, "unary: bad arguments");
   if (rows * C == 0) return EVK_OK;
   unary_kernel<<<grid1d(rows * C), 256, 0, ST>>>(op, alpha, x, ldx, y, ldy, rows, C);
   return check_launch("unary");

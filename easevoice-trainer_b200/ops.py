@@ -16,7 +16,7 @@ from . import lib as L
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_TANH = 0, 1, 2, 3
 USE_TMA_STRIDED = True   # strided conv forward: phase-split input + stride-1 multi-source tap sum on the TMA kernel
 USE_TMA_WGRAD = True     # weight gradients of tap-free layers: transposes + split-K TMA/tcgen05 GEMM
-UN_SCALE, UN_LRELU, UN_TANH, UN_MISH, UN_RELU, UN_TANH_FROM_OUT = 0, 1, 2, 3, 4, 5
+UN_SCALE, UN_LRELU, UN_TANH, UN_MISH, UN_RELU, UN_TANH_FROM_OUT, UN_GELU = 0, 1, 2, 3, 4, 5, 6
 
 _launches = 0          # number of libevk kernel-launching calls (bench.py reports it)
 
@@ -784,6 +784,26 @@ def mish(x):
 
 def scale(x, alpha):
     return _UnaryFn.apply(x, UN_SCALE, alpha)
+
+
+def gelu(x):
+    """exact (erf) GELU, inference only (HuBERT): no gradient."""
+    x = _cl(x.detach())
+    rows, C, ld = _rows(x)
+    y = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    _call("evk_unary", UN_GELU, ctypes.c_float(0.0), _p(x), ld, _p(y), C, rows, C)
+    return y
+
+
+def instnorm_cl(x, gamma, beta, eps=1e-5, gelu_after=False):
+    """GroupNorm(C, C) over time of a channels-last [B, T, C] tensor (+ optional exact GELU); inference only."""
+    x = _cl(x.detach())
+    B, T, C = x.shape
+    _, _, ld = _rows(x)
+    y = torch.empty((B, T, C), device=x.device, dtype=torch.float32)
+    _call("evk_instnorm_cl", _p(x), ld, _p(gamma.detach().contiguous()), _p(beta.detach().contiguous()), ctypes.c_float(eps),
+          1 if gelu_after else 0, _p(y), C, B, T, C)
+    return y
 
 
 def _axpby_raw(a, alpha, b=None, beta=0.0, c=None, gamma=0.0, length=None, T=0):

@@ -165,7 +165,13 @@ int evk_spec_to_mel(const float* spec, int64_t rows, int32_t ld_spec, int32_t n_
 /* ------------------------------------------------------------------------------------------
  * Element-wise / row-wise kernels (all tensors are [rows][C] views with explicit pitches)
  * ------------------------------------------------------------------------------------------ */
-/* generic unary map y = f(x); op: 0 copy*alpha, 1 lrelu(alpha), 2 tanh, 3 mish, 4 relu.  bwd: dx = dy*f'(x) */
+/* generic unary map y = f(x); op: 0 copy*alpha, 1 lrelu(alpha), 2 tanh, 3 mish, 4 relu, 6 gelu (exact erf form, forward only).
+ * bwd: dx = dy*f'(x) (op 5 there: tanh with the derivative taken from the saved OUTPUT) */
+/* GroupNorm with one channel per group over the time axis of a channels-last tensor (torch.nn.GroupNorm(C, C) of the HuBERT
+ * feature extractor, transformers modeling_hubert.py HubertGroupNormConvLayer): y[b][t][c] = (x - mean_t) * rsqrt(var_t + eps)
+ * * gamma[c] + beta[c], biased variance; optional exact GELU applied to the result (act_gelu != 0).  Forward only. */
+int evk_instnorm_cl(const float* x, int32_t ldx, const float* gamma, const float* beta, float eps, int32_t act_gelu, float* y,
+                    int32_t ldy, int32_t B, int32_t T, int32_t C, evk_stream_t stream);
 int evk_unary(int32_t op, float alpha, const float* x, int32_t ldx, float* y, int32_t ldy, int64_t rows, int32_t C,
               evk_stream_t stream);
 int evk_unary_bwd(int32_t op, float alpha, const float* x, int32_t ldx, const float* dy, int32_t lddy, float* dx,

@@ -472,9 +472,44 @@ def pin_infer_panel():
             "min_top2_margin": min(margins)}
 
 
+def pin_hubert():
+    """transformers.HubertModel (the class behind the reference's CNHubert, cnhubert.py:14-33; called as
+    `model.model(wav16k)["last_hidden_state"]`, normalize.py:166-168) vs oracle/hubert_oracle.py, same seeded weights:
+    a 2-layer model on 1 s + the full 12-layer model on 0.5 s of audio.  Writes tests/golden/hubert.pt."""
+    from transformers import HubertConfig, HubertModel
+    from oracle import hubert_oracle as ho
+    gold = {"cases": []}
+    res = {}
+    for tag, layers, L, seed in (("l2", 2, 16000, 41), ("base", 12, 8000, 42)):
+        m = dict(ho.HUBERT_BASE, layers=layers)
+        P = ho.init_params(ho.param_spec(m), seed)
+        ref = HubertModel(HubertConfig(num_hidden_layers=layers)).eval()
+        sd = ref.state_dict()
+        assert {k: tuple(v.shape) for k, v in sd.items() if k != "masked_spec_embed"} == ho.param_spec(m), "state_dict contract"
+        ref.load_state_dict(dict(P, masked_spec_embed=sd["masked_spec_embed"]))
+        g = torch.Generator().manual_seed(seed + 100)
+        wav = torch.randn(1, L, generator=g) * 0.3
+        with torch.no_grad():
+            o_ref = ref(wav)["last_hidden_state"]
+            o_ora = ho.forward(P, wav, m)
+        err = maxdiff(o_ref, o_ora)
+        assert o_ref.shape == o_ora.shape and err < 5e-5, (tag, o_ref.shape, o_ora.shape, err)
+        res[tag] = {"frames": int(o_ref.shape[1]), "max_abs_diff_oracle_vs_transformers": err, "out_rms": float(o_ref.pow(2).mean().sqrt())}
+        gold["cases"].append({"tag": tag, "layers": layers, "L": L, "param_seed": seed, "wav_seed": seed + 100, "wav_scale": 0.3,
+                              "out": o_ref.clone()})
+    import transformers
+    gold["transformers"] = transformers.__version__
+    torch.save(gold, os.path.join(GOLD, "hubert.pt"))
+    return res
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.manual_seed(0)
+    if "--hubert" in sys.argv:           # only the Normalize.ssl model golden; before the librosa stub (transformers probes it)
+        print(pin_hubert())
+        return
+    hub = pin_hubert() if len(sys.argv) == 1 else None
     mp, models, losses, commons = import_reference()
     if "--extract-latent" in sys.argv:   # only the Normalize.token golden (seconds)
         print(pin_extract_latent(models))
@@ -501,6 +536,7 @@ def main():
     report["extract_latent"] = pin_extract_latent(models)
     report["decode"] = pin_decode(models)
     report["infer_panel"] = pin_infer_panel()
+    report["hubert"] = hub
     with open(os.path.join(GOLD, "pin_report.json"), "w") as f:
         json.dump(report, f, indent=1)
     print("PIN OK")

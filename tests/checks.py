@@ -1532,12 +1532,55 @@ def ops_mod():
     return ops
 
 
+def check_hubert():
+    """SURVEY 8 row f3 (ssl half): the HuBERT forward of Normalize.ssl on the library's kernels vs the output transformers'
+    HubertModel produced from the same seeded weights (tests/golden/hubert.pt, oracle/pin_against_reference.py --hubert)."""
+    from easevoice_trainer_b200 import hubert, ops
+    from oracle import hubert_oracle as ho
+    out = []
+    g = _gen(3)
+    x = torch.randn(2, 301, 70, generator=g) * 2.0 + 0.5
+    gm, bt = 1.0 + 0.1 * torch.randn(70, generator=g), 0.1 * torch.randn(70, generator=g)
+    ref = torch.nn.functional.group_norm(x.transpose(1, 2).double(), 70, gm.double(), bt.double(), 1e-5).transpose(1, 2)
+    out.append(("instnorm_cl vs GroupNorm(C, C) (float64)", rel(ops.instnorm_cl(x.to(DEV), gm.to(DEV), bt.to(DEV)), ref), 2e-6))
+    out.append(("instnorm_cl + GELU", rel(ops.instnorm_cl(x.to(DEV), gm.to(DEV), bt.to(DEV), gelu_after=True),
+                                          torch.nn.functional.gelu(ref)), 2e-6))
+    out.append(("gelu (erf) vs float64", rel(ops.gelu(x.to(DEV)), torch.nn.functional.gelu(x.double())), 1e-6))
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "hubert.pt"), weights_only=False)
+    for c in gold["cases"]:
+        m = dict(ho.HUBERT_BASE, layers=c["layers"])
+        P = ho.init_params(ho.param_spec(m), c["param_seed"])
+        net = hubert.HubertModel({"num_hidden_layers": c["layers"]})
+        net.load_state_dict(P)
+        net = net.to(DEV).eval()
+        wav = torch.randn(1, c["L"], generator=_gen(c["wav_seed"])) * c["wav_scale"]
+        o = net(wav.to(DEV))["last_hidden_state"]
+        out.append((f"hubert[{c['tag']}] output shape", 0.0 if tuple(o.shape) == tuple(c["out"].shape) else 1.0, 0.5))
+        out.append((f"hubert[{c['tag']}] last_hidden_state vs transformers golden (rel-L2)", rel(o, c["out"]), TOL_NET))
+        if c["tag"] == "l2":
+            taps = {}
+            with torch.no_grad():
+                ho.forward(P, wav, m, taps=taps)
+            # the feature extractor alone (7 strided convs + GroupNorm + GELU): recomputed through the public pieces
+            net._active, net._memo_pack = net.packed_for_inference(), True
+            try:
+                xx = ops.pad_channels(wav.to(DEV).unsqueeze(-1).contiguous(), 4)
+                for i, (k, st) in enumerate(zip(net.cfg["conv_kernel"], net.cfg["conv_stride"])):
+                    xx = ops.conv(xx, net.w(f"feature_extractor.conv_layers.{i}.conv", need_pb=False, pad1=4 if i == 0 else 0), None, stride=st)
+                    xx = ops.instnorm_cl(xx, net.P("feature_extractor.conv_layers.0.layer_norm.weight"),
+                                         net.P("feature_extractor.conv_layers.0.layer_norm.bias"), 1e-5, gelu_after=True) if i == 0 else ops.gelu(xx)
+            finally:
+                net._active, net._memo_pack = None, False
+            out.append(("hubert[l2] feature extractor output vs oracle (rel-L2)", rel(xx, taps["features"]), TOL_NET))
+    return out
+
+
 ALL = [check_conv, check_conv_transpose, check_elementwise, check_attention, check_vq_losses_optim, check_mel,
        lambda: check_s2("small"), lambda: check_s2("ragged"), check_api_layouts,
        check_gpt_kernels, check_scaled_adam, lambda: check_gpt("small"), lambda: check_gpt("ragged"),
        check_gpt_dpo_and_trainer, check_gemm_tma, check_vocoder_cfg5,
        lambda: check_s2_full("cfg3"), lambda: check_s2_full("cfg3r"), lambda: check_gpt_full("cfg2"),
-       check_sovits_train_e2e, check_stft, check_fused_dropout, check_side_streams, check_normalize_token, check_decode, check_infer_panel]
+       check_sovits_train_e2e, check_stft, check_fused_dropout, check_side_streams, check_normalize_token, check_decode, check_infer_panel, check_hubert]
 NAMES = ["conv", "conv_transpose", "elementwise", "attention", "vq_losses_optim", "mel", "s2_small", "s2_ragged", "api",
          "gpt_kernels", "scaled_adam", "gpt_small", "gpt_ragged", "gpt_dpo_trainer", "gemm_tma", "vocoder_cfg5",
-         "s2_cfg3", "s2_cfg3r", "gpt_cfg2", "sovits_train_e2e", "stft_mrstft", "fused_dropout", "side_streams", "normalize_token", "decode", "infer_panel"]
+         "s2_cfg3", "s2_cfg3r", "gpt_cfg2", "sovits_train_e2e", "stft_mrstft", "fused_dropout", "side_streams", "normalize_token", "decode", "infer_panel", "hubert"]

@@ -110,3 +110,18 @@ def test_oracle_infer_panel_matches_reference_golden():
     assert y[0].tolist() == gold["tokens"] and int(idx) == gold["idx"]
     for s_, ref in gold["logits_step"].items():
         assert float((tr[int(s_)][0] - torch.tensor(ref)).abs().max()) < 2e-4
+
+
+def test_oracle_hubert_matches_transformers_golden():
+    """SURVEY 8 row f3 (ssl half): the oracle restatement of the HuBERT forward reproduces what transformers.HubertModel produced
+    from the same seeded weights (oracle/pin_against_reference.py --hubert); when transformers is importable the model itself is
+    re-run as well."""
+    from oracle import hubert_oracle as ho
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "hubert.pt"), weights_only=False)
+    c = gold["cases"][0]                                        # 2 layers, 1 s of audio
+    m = dict(ho.HUBERT_BASE, layers=c["layers"])
+    P = ho.init_params(ho.param_spec(m), c["param_seed"])
+    wav = torch.randn(1, c["L"], generator=torch.Generator().manual_seed(c["wav_seed"])) * c["wav_scale"]
+    with torch.no_grad():
+        o = ho.forward(P, wav, m)
+    assert o.shape == c["out"].shape and float((o - c["out"]).abs().max()) < 5e-5
