@@ -314,6 +314,70 @@ __global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restric
   }
 }
 
+// Skinny product of the AR token step:  y[r][n] = act(sum_c x[r][c] * W[n][c] + bias[n]),  R <= 4 rows.
+// A one-row "GEMM" is a stream over the weight matrix (12.6 MB per GPT layer): through the 128-row tensor-core tiles it ran on
+// N/128 = 4..16 CTAs with one barrier round trip per 32 channels (25..100 us per Linear, 9.3 ms per token).  Here KS warps share
+// one output column (each takes every KS-th float4 group of the weight row: 512-byte coalesced warp loads, four in flight), the x
+// rows sit in shared memory, products are exact fp32 FMAs (the sampled token must not depend on operand rounding).
+template <int R>
+__global__ void __launch_bounds__(256) gemv_rows_kernel(const float* __restrict__ x, int ldx, int rows, const float* __restrict__ W, int ldw,
+                                                        const float* __restrict__ bias, float* __restrict__ y, int ldy, int N, int C,
+                                                        int KS, int act, float slope) {
+  extern __shared__ __align__(16) float gv_x[];                   // [R][C] then [8][R] partial sums
+  float* part = gv_x + R * C;
+  for (int i = threadIdx.x; i < R * C; i += blockDim.x) {
+    const int r = i / C, c = i - r * C;
+    gv_x[i] = r < rows ? x[(size_t)r * ldx + c] : 0.f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per = 8 / KS;                                          // output columns per CTA
+  const int n = blockIdx.x * per + warp / KS, ks = warp % KS;
+  float acc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = 0.f;
+  if (n < N) {
+    const float4* wr = reinterpret_cast<const float4*>(W + (size_t)n * ldw);
+    const int C4 = C >> 2, step = 32 * KS;
+    int c4 = ks * 32 + lane;
+    for (; c4 + 3 * step < C4; c4 += 4 * step) {
+      float4 w[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) w[u] = __ldg(wr + c4 + u * step);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float4 xv = reinterpret_cast<const float4*>(gv_x + r * C)[c4 + u * step];
+          acc[r] = fmaf(w[u].x, xv.x, fmaf(w[u].y, xv.y, fmaf(w[u].z, xv.z, fmaf(w[u].w, xv.w, acc[r]))));
+        }
+    }
+    for (; c4 < C4; c4 += step) {
+      const float4 w = __ldg(wr + c4);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float4 xv = reinterpret_cast<const float4*>(gv_x + r * C)[c4];
+        acc[r] = fmaf(w.x, xv.x, fmaf(w.y, xv.y, fmaf(w.z, xv.z, fmaf(w.w, xv.w, acc[r]))));
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) acc[r] = warp_sum(acc[r]);
+  if (lane == 0) {
+#pragma unroll
+    for (int r = 0; r < R; ++r) part[warp * R + r] = acc[r];
+  }
+  __syncthreads();
+  if (ks == 0 && n < N && lane < rows && lane < R) {
+    float v = 0.f;
+    for (int k = 0; k < KS; ++k) v += part[(warp + k) * R + lane];
+    if (bias) v += bias[n];
+    if (act == EVK_ACT_RELU) v = fmaxf(v, 0.f);
+    else if (act == EVK_ACT_LRELU) v = v > 0.f ? v : v * slope;
+    y[(size_t)lane * ldy + n] = v;
+  }
+}
+
 // cache[b][*pos][0 .. W) = row[b][0 .. W): the position comes from device memory so that the step can be a replayed CUDA graph
 __global__ void cache_append_kernel(const float* __restrict__ row, int ldr, float* __restrict__ cache, long long sb, int ld,
                                     const int* __restrict__ pos, int W) {
@@ -387,6 +451,25 @@ extern "C" int evk_scaled_adam(float* p, float* g, float* delta, float* v, const
   sadam_update_kernel<<<nchunks, 256, 0, st>>>(p, g, delta, v, (const long long*)chunks, (const long long*)numel, coef, glob, gscale, beta1, beta2, eps, scalar_max,
                                                zero_grad);
   return check_launch("sadam_update");
+}
+
+extern "C" int evk_gemv_rows(const float* x, int32_t ldx, int32_t rows, const float* W, int32_t ldw, const float* bias, float* y,
+                             int32_t ldy, int32_t N, int32_t C, int32_t act, float slope, cudaStream_t st) {
+  EVK_REQUIRE(x && W && y && rows >= 1 && rows <= 4 && N >= 1 && C >= 4, EVK_ERR_ARG, "gemv_rows: bad arguments (rows=%d N=%d C=%d)", rows, N, C);
+  EVK_REQUIRE(C % 4 == 0 && ldw % 4 == 0 && ldw >= C && ((uintptr_t)W % 16) == 0 && ldx >= C && ldy >= N, EVK_ERR_ARG,
+              "gemv_rows: C and the weight pitch must be multiples of 4, W 16-byte aligned");
+  EVK_REQUIRE(act == EVK_ACT_NONE || act == EVK_ACT_RELU || act == EVK_ACT_LRELU, EVK_ERR_UNSUPPORTED, "gemv_rows: activation %d", act);
+  const int R = rows == 1 ? 1 : (rows == 2 ? 2 : 4);
+  EVK_REQUIRE((size_t)R * C * 4 <= 40 * 1024, EVK_ERR_UNSUPPORTED, "gemv_rows: %d rows of %d channels exceed the staging buffer", R, C);
+  int KS = 1;
+  while (KS < 8 && (long long)N * KS < 148 * 8 && C / 4 >= 64 * KS) KS *= 2;      // enough warps to cover the chip, >= 2 float4 groups per lane
+  const int per = 8 / KS;
+  const size_t smem = ((size_t)R * C + 8 * R) * sizeof(float);
+  const int grid = cdiv(N, per);
+  if (R == 1) gemv_rows_kernel<1><<<grid, 256, smem, st>>>(x, ldx, rows, W, ldw, bias, y, ldy, N, C, KS, act, slope);
+  else if (R == 2) gemv_rows_kernel<2><<<grid, 256, smem, st>>>(x, ldx, rows, W, ldw, bias, y, ldy, N, C, KS, act, slope);
+  else gemv_rows_kernel<4><<<grid, 256, smem, st>>>(x, ldx, rows, W, ldw, bias, y, ldy, N, C, KS, act, slope);
+  return check_launch("gemv_rows");
 }
 
 extern "C" int evk_attn_decode(const float* qkv, int64_t batch_stride, int32_t ld, int32_t n_keys, int32_t B, int32_t H, float scale,

@@ -101,17 +101,36 @@ class HubertModel(ParamTree):
         return net.to(device).eval()
 
     # ---- forward ------------------------------------------------------------------------------------------------------------
+    POS_PIECE = 48           # taps per launch of the positional conv (the descriptor holds EVK_MAX_TAPS = 48 tap offsets)
+
     def _pos_weight(self):
-        """weight_norm(dim=2) folded once per parameter version: w[:, :, k] = g[k] * v[:, :, k] / ||v[:, :, k]||_F"""
+        """weight_norm(dim=2) folded once per parameter version: w[:, :, k] = g[k] * v[:, :, k] / ||v[:, :, k]||_F.
+        The k = 128 kernel is packed as ceil(128 / 48) tap pieces (one launch each, chained through the residual input)."""
         g = self.P("encoder.pos_conv_embed.conv.parametrizations.weight.original0")
         v = self.P("encoder.pos_conv_embed.conv.parametrizations.weight.original1")
         key = (int(g._version), int(v._version), str(v.device))
         c = self.__dict__.get("_posw")
         if c is None or c[0] != key:
-            w = (v * (g / v.norm(p=2, dim=(0, 1), keepdim=True))).contiguous()
-            c = (key, ops.pack_weight(w, None, need_pb=False))
+            w = v * (g / v.norm(p=2, dim=(0, 1), keepdim=True))
+            K = w.shape[2]
+            pieces = [(a, min(K, a + self.POS_PIECE)) for a in range(0, K, self.POS_PIECE)]
+            c = (key, [(a, b, ops.pack_weight(w[:, :, a:b].contiguous(), None, need_pb=False)) for a, b in pieces])
             self.__dict__["_posw"] = c
         return c[1]
+
+    def _pos_conv(self, h):
+        """HubertPositionalConvEmbedding (modeling_hubert.py): grouped Conv1d(k = 128, pad = 64) + HubertSamePadLayer (drops the
+        last output when k is even) + GELU.  out[t] = sum_q w[q] x[t + q - 64], t < T: every tap piece reads its own window of
+        the zero-padded input and adds to the previous piece's output in the epilogue."""
+        c = self.cfg
+        K, T = c["num_conv_pos_embeddings"], h.shape[1]
+        xp = torch.nn.functional.pad(h, (0, 0, K // 2, K // 2 - (1 if K % 2 == 0 else 0)))      # exactly the rows outputs 0..T-1 read
+        pos = None
+        for a, b, wp in self._pos_weight():
+            xin = xp[:, a:a + T + (b - a) - 1].contiguous()
+            pos = ops.conv(xin, wp, self.P("encoder.pos_conv_embed.conv.bias") if pos is None else None, pad=0,
+                           groups=c["num_conv_pos_embedding_groups"], res=pos)
+        return ops.gelu(pos)
 
     @torch.no_grad()
     def forward(self, input_values):
@@ -133,12 +152,7 @@ class HubertModel(ParamTree):
             eps = c["layer_norm_eps"]
             x = ops.layernorm(x, self.P("feature_projection.layer_norm.weight"), self.P("feature_projection.layer_norm.bias"), eps=eps)
             h = ops.linear(x, self.w("feature_projection.projection", need_pb=False), self.b("feature_projection.projection"))
-            K = c["num_conv_pos_embeddings"]
-            pos = ops.conv(h, self._pos_weight(), self.P("encoder.pos_conv_embed.conv.bias"), pad=K // 2,
-                           groups=c["num_conv_pos_embedding_groups"])
-            if K % 2 == 0:
-                pos = pos[:, :-1]                                                # HubertSamePadLayer
-            pos = ops.gelu(pos)
+            pos = self._pos_conv(h)
             h = ops.layernorm(h, self.P("encoder.layer_norm.weight"), self.P("encoder.layer_norm.bias"), res=pos, eps=eps)
             H = c["num_attention_heads"]
             scale = (c["hidden_size"] // H) ** -0.5

@@ -7,6 +7,7 @@ width P passed explicitly.  Lengths are int32 device tensors [B].
 Nothing here falls back to torch math: if the library or the GPU is missing, `lib.init()` raises.
 """
 import ctypes
+import os
 import math
 
 import torch
@@ -680,9 +681,31 @@ def fused_dropout_ok(x, w, act):
     return w.Q == 1 and rows >= 512 and C >= 64 and C % 4 == 0 and N >= 64 and N % 4 == 0 and x.data_ptr() % 16 == 0
 
 
+USE_GEMV = os.environ.get("EVK_GEMV", "1") != "0"     # skinny (<= 4 rows, no-grad) Linear launches stream the weight once (evk_gemv_rows)
+
+
+def _gemv_rows(x, w, bias, act, slope):
+    """The token step of the KV-cache decode: [..., C] with <= 4 rows in total -> [..., N], exact fp32, one pass over PA[0]."""
+    C = x.shape[-1]
+    x2 = x.reshape(-1, C)
+    if x2.stride(1) != 1:
+        x2 = x2.contiguous()
+    rows, N = x2.shape[0], w.pa.shape[1]
+    y = torch.empty(x.shape[:-1] + (N,), device=x.device, dtype=torch.float32)
+    _call_f("evk_gemv_rows", 2.0 * rows * N * C, _p(x2), x2.stride(0), rows, _p(w.pa), w.pa.shape[2], _p(bias), _p(y), N, N, C,
+            int(act), ctypes.c_float(float(slope)))
+    return y
+
+
 def linear(x, w: PackedW, bias=None, act=ACT_NONE, slope=0.0, out_len=None, in_len=None, res=None, drop=None):
     """nn.Linear / 1x1 conv on [B, T, C] or [rows, C].  drop = (p, tag): dropout_p(relu(x W^T + b)) with the dropout applied in
     the GEMM epilogue when fused_dropout_ok (else as a separate kernel)."""
+    if (USE_GEMV and not torch.is_grad_enabled() and w.Q == 1 and res is None and out_len is None and in_len is None
+            and (drop is None or drop[0] <= 0.0) and act in (ACT_NONE, ACT_RELU, ACT_LRELU)):
+        C = x.shape[-1]
+        rows = x.numel() // max(C, 1)
+        if 1 <= rows <= 4 and C >= 4 and C % 4 == 0 and C <= w.pa.shape[2] and (1 if rows == 1 else 2 if rows == 2 else 4) * C <= 10240:
+            return _gemv_rows(x, w, bias, act, slope)
     if drop is not None and drop[0] > 0.0:
         if fused_dropout_ok(x, w, act) and out_len is None and in_len is None and res is None:
             cfg = (w.Q, 1, 0, 1, 1, 1, act, slope, None, None, (float(drop[0]), stream_id(drop[1])))

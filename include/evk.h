@@ -386,6 +386,11 @@ int evk_sinepos_bwd(const float* dy, int32_t ldy, int64_t dy_sb, const float* pe
  * the n_keys positions so far; the query is the q block of row n_keys - 1.  out [B, H * 32] (pitch ldo).  Exact fp32. */
 int evk_attn_decode(const float* qkv, int64_t batch_stride, int32_t ld, int32_t n_keys, int32_t B, int32_t H, float scale,
                     float* out, int32_t ldo, evk_stream_t stream);
+/* Skinny Linear of the KV-cache token step (decode_next_token, t2s_model.py:187-221: one new row per utterance):
+ * y[r][n] = act(sum_c x[r][c] * W[n][c] + bias[n]) for rows <= 4; W = the packed forward operand PA[0] ([N][ldw], row n = output
+ * channel n).  Exact fp32 FMAs, one pass over W.  act: EVK_ACT_NONE / RELU / LRELU. */
+int evk_gemv_rows(const float* x, int32_t ldx, int32_t rows, const float* W, int32_t ldw, const float* bias, float* y,
+                  int32_t ldy, int32_t N, int32_t C, int32_t act, float slope, evk_stream_t stream);
 /* The same with the position in DEVICE memory (a decode step replayed as a CUDA graph): *n_prev_dev = rows already in the cache
  * before this token; evk_cache_append writes the token's row at that index, evk_attn_decode_dev attends rows 0 .. *n_prev_dev. */
 int evk_attn_decode_dev(const float* qkv, int64_t batch_stride, int32_t ld, const int32_t* n_prev_dev, int32_t B, int32_t H,

@@ -1499,6 +1499,23 @@ def check_infer_panel():
         v = cache[:, :n, 1024:].reshape(2, n, 16, 32).permute(0, 2, 1, 3).double().cpu()
         ref = (torch.softmax(q @ k.transpose(-1, -2) / math.sqrt(32.0), -1) @ v).permute(0, 2, 1, 3).reshape(2, 1, 512)
         out.append((f"attn_decode n_keys={n} vs float64 softmax(q k^T / sqrt(32)) v", rel(a, ref), 2e-6))
+    # ---- the skinny Linear of the token step (evk_gemv_rows: exact fp32 over the packed, TF32-rounded weight) vs float64
+    o = ops_mod()
+    for rows, N, C, act in ((1, 1536, 512, o.ACT_NONE), (1, 512, 2048, o.ACT_NONE), (1, 2048, 512, o.ACT_RELU), (3, 1028, 512, o.ACT_NONE),
+                            (4, 96, 64, o.ACT_LRELU), (2, 513, 260, o.ACT_NONE)):
+        wv = (torch.randn(N, C, 1, generator=gg) / math.sqrt(C)).to(DEV)
+        bv = torch.randn(N, generator=gg).to(DEV)
+        xv = torch.randn(1, rows, C, generator=gg).to(DEV)
+        pw = o.pack_weight(wv, None, need_pb=False)
+        with torch.no_grad():
+            yv = o.linear(xv, pw, bv, act=act, slope=0.1)
+        wr = pw.pa[0, :N, :C].double().cpu()                     # the operand the kernel reads (rounded to TF32 at pack time)
+        ref = xv[0].double().cpu() @ wr.t() + bv.double().cpu()
+        ref = torch.relu(ref) if act == o.ACT_RELU else (torch.where(ref > 0, ref, 0.1 * ref) if act == o.ACT_LRELU else ref)
+        out.append((f"gemv_rows rows={rows} N={N} C={C} act={act} vs float64 on the packed weight", rel(yv[0], ref), 2e-6))
+        out.append((f"gemv_rows rows={rows} N={N} C={C} vs the unrounded weight (TF32 weight rounding only)",
+                    rel(yv[0], torch.relu(xv[0].double().cpu() @ wv[:, :, 0].double().cpu().t() + bv.double().cpu()) if act == o.ACT_RELU else
+                        (lambda r: torch.where(r > 0, r, 0.1 * r) if act == o.ACT_LRELU else r)(xv[0].double().cpu() @ wv[:, :, 0].double().cpu().t() + bv.double().cpu())), TOL_TC))
     # ---- greedy decoding
     tr = []
     y, idx = net.infer_panel(x.to(DEV), torch.tensor([c["X"]], device=DEV), prompts.to(DEV), bert.to(DEV), top_k=c["top_k"], top_p=100,
