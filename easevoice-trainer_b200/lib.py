@@ -81,6 +81,8 @@ def init():
         rc = lib.evk_init()
         if rc != 0:
             raise RuntimeError(f"evk_init failed ({rc}): {last_error()}")
+        if os.environ.get("EVK_FLASH_TC") is not None:       # developer A/B switch: attention kernel family (csrc/flash_tc.cu)
+            lib.evk_set_flash_tc(1 if os.environ["EVK_FLASH_TC"] != "0" else 0, -1.0)
         _inited = True
     return lib
 

@@ -371,6 +371,12 @@ int evk_flash_attn_bwd(const float* q, const float* k, const float* v, int32_t l
                        const float* lse, const float* dout, int32_t lddo, float* delta, float* dq, float* dk, float* dv,
                        int32_t lddq, int32_t B, int32_t H, int32_t L, int32_t X, int32_t dkdim, const int64_t* xlen,
                        const int64_t* ylen, float scale, float p_drop, const uint64_t* rng, uint64_t sid, evk_stream_t stream);
+/* Kernel family behind evk_flash_attn_fwd / _bwd: 1 (default) = tcgen05 / TMEM kernels (csrc/flash_tc.cu), 0 = the mma.sync
+ * kernels (csrc/flash.cu; always used in the 3xTF32 test mode).  trunc_comp >= 0 sets the relative compensation per raw
+ * (truncated) TF32 operand, < 0 keeps it.  Forward and backward of one step must run on the same family (their S differ by the
+ * compensation factor). */
+int evk_set_flash_tc(int32_t on, float trunc_comp);
+int evk_get_flash_tc(void);
 /* SinePositionalEmbedding with learnable alpha (embedding.py:36-81): y[b][t] = x[b][t] + alpha[0] * pe[t]; *_sb are batch
  * strides in floats so y can be a row range of the concatenated [B, X+Y, D] sequence.  bwd: dalpha[0] += <dy, pe>. */
 int evk_sinepos_add(const float* x, int32_t ldx, int64_t x_sb, const float* pe, int32_t ldpe, const float* alpha, float* y,

@@ -86,7 +86,7 @@ with torch.no_grad():
     cpu_s = time.perf_counter() - t0
 print(json.dumps(dict(metric="Text2SemanticDecoder.infer_panel (KV-cache AR decoding), one utterance", unit="semantic-tokens/s",
                       value=new / gpu_s, generated=new, seconds=gpu_s, ms_per_token=gpu_s / max(new, 1) * 1e3,
-                      config=dict(layers=24, X=X, prompt=Yp, top_k=15, top_p=1, temperature=1.0, launch_mode="eager"),
+                      config=dict(layers=24, X=X, prompt=Yp, top_k=15, top_p=1, temperature=1.0, launch_mode="graph" if __import__("easevoice_trainer_b200.models_gpt", fromlist=["x"]).INFER_GRAPH else "eager"),
                       note="prompt pass included in the time; 25 tokens = 1 s of audio",
                       cpu_baseline=dict(value=n_cpu / cpu_s, unit="semantic-tokens/s", cores=threads, kind="port",
                                         sample=f"prompt pass + {n_cpu} greedy tokens, torch CPU ops, KV cache as t2s_model.py:121-221"))))
