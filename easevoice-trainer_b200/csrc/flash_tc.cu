@@ -39,7 +39,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
+#ifdef FT_TESTWAIT
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+#endif
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(done)
@@ -95,6 +99,22 @@ __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::be
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 
+#ifdef FT_PROFILE
+// developer build only (tools/exp/ft_profile.py): cycle counters of the forward kernel's phases as thread 0 sees them, summed
+// over all CTAs.  slots: 0 stage+sync, 1 issue S, 2 wait S, 3 prefetch issue, 4 tcgen05.ld S, 5 softmax + P stores, 6 fence+sync,
+// 7 issue PV, 8 wait PV, 9 ld O + accumulate, 10 tiles, 11 kernel
+__device__ unsigned long long g_ft_prof[16];
+#define FT_DECL() unsigned long long ft_acc[12] = {0ull}; long long ft_t = clock64(); const long long ft_t0 = ft_t
+#define FT_MARK(i) do { if (threadIdx.x == 0) { const long long ft_n = clock64(); ft_acc[i] += (unsigned long long)(ft_n - ft_t); ft_t = ft_n; } } while (0)
+#define FT_INC(i) ft_acc[i] += 1ull
+#define FT_FLUSH() do { if (threadIdx.x == 0) { ft_acc[11] = (unsigned long long)(clock64() - ft_t0); for (int ft_i = 0; ft_i < 12; ++ft_i) atomicAdd(&g_ft_prof[ft_i], ft_acc[ft_i]); } } while (0)
+#else
+#define FT_DECL()
+#define FT_MARK(i)
+#define FT_INC(i)
+#define FT_FLUSH()
+#endif
+
 template <int COLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* slot) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(slot)), "n"(COLS) : "memory");
@@ -143,6 +163,32 @@ __device__ __forceinline__ void store_t(uint8_t* s, const float4 (&v)[ROWS / 16]
   }
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ float selp_f(float a, float b, bool c) {   // c ? a : b as ONE select (a nested ?: chain became divergent branches)
+  float r;
+  asm("{\n.reg .pred p;\nsetp.ne.b32 p, %3, 0;\nselp.f32 %0, %1, %2, p;\n}\n" : "=f"(r) : "f"(a), "f"(b), "r"((int)c));
+  return r;
+}
+// rotate (a0..a3) left by rot (0..3) with two select stages
+__device__ __forceinline__ void rot4(float (&a)[4], int rot) {
+  const bool r0 = rot & 1, r1 = rot & 2;
+  const float b0 = selp_f(a[1], a[0], r0), b1 = selp_f(a[2], a[1], r0), b2 = selp_f(a[3], a[2], r0), b3 = selp_f(a[0], a[3], r0);
+  a[0] = selp_f(b2, b0, r1); a[1] = selp_f(b3, b1, r1); a[2] = selp_f(b0, b2, r1); a[3] = selp_f(b1, b3, r1);
+}
+
 // every (query i0 .. i0 + NQ - 1, key j0 .. j0 + NK - 1) pair visible?  (tile-level mask skip, as flash.cu)
 template <int NK>
 __device__ __forceinline__ bool tile_full_tc(int i0, int j0, int X, int xl, int yl) {
@@ -164,7 +210,12 @@ constexpr int DQ_SMEM = 2 * P128 + 2 * P64 + T64 + A64;                // 94 208
 constexpr int DKV_SMEM = 2 * P128 + 4 * P32 + 2 * A32;                 // 86 016
 
 // ------------------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 3) flash_tc_fwd_kernel(FlashArgs a, float comp2) {
+#ifdef FT_PROFILE
+#define FT_MINB 2
+#else
+#define FT_MINB 3
+#endif
+__global__ void __launch_bounds__(128, FT_MINB) flash_tc_fwd_kernel(FlashArgs a, float comp2) {
   extern __shared__ __align__(128) uint8_t fsm[];
   uint8_t *sQ = fsm, *sK = sQ + P128, *sV = sK + P64, *sP = sV + T64;
   __shared__ __align__(8) uint64_t bar_s, bar_o;
@@ -210,28 +261,36 @@ __global__ void __launch_bounds__(128, 3) flash_tc_fwd_kernel(FlashArgs a, float
 #pragma unroll
   for (int c = 0; c < 32; ++c) acc[c] = 0.f;
 
+  FT_DECL();
   for (int kt = 0; kt < nt; ++kt) {
     const int j0 = kt * 64;
+    FT_MARK(11);
+    FT_INC(10);
     store_t<64>(sV, vt);                                             // P V of the previous tile has completed (bar_o below)
     cp_async_wait<0>();
     fence_async_smem();
     fence_before();
     __syncthreads();
+    FT_MARK(0);
     if (tid == 0) {
       fence_after();
       mma_panels(tmem, aQ, QP, aK, KP, 4, idesc_n(64), false);       // S = Q K^T
       umma_commit(&bar_s);
     }
+    FT_MARK(1);
     mbar_wait(&bar_s, (uint32_t)(kt & 1));
     fence_after();
+    FT_MARK(2);
     if (kt + 1 < nt) {                                               // the K panels are free again: next tile in flight under the softmax
       stage_rows<64, KP>(sK, K, a.ld, j0 + 64, L);
       load_t<64>(vt, V, a.ld, j0 + 64, L);
     }
     cp_async_commit();
+    FT_MARK(3);
     float s[64];
     tmem_ld32(tS, s);
     tmem_ld32(tS + 32, s + 32);
+    FT_MARK(4);
     float rmax = -INFINITY;
     if (tile_full_tc<64>(i0, j0, X, xl, yl)) {                       // CTA-uniform
 #pragma unroll
@@ -268,21 +327,27 @@ __global__ void __launch_bounds__(128, 3) flash_tc_fwd_kernel(FlashArgs a, float
       *reinterpret_cast<float4*>(sP + ((size_t)c4 * QP + tid) * 16) = make_float4(p[0], p[1], p[2], p[3]);
     }
     l = l * corr + rs;
+    FT_MARK(5);
     fence_async_smem();
     fence_before();
     __syncthreads();
+    FT_MARK(6);
     if (tid == 0) {
       fence_after();
       mma_panels(tmem + 64, aP, QP, aV, TP, 8, idesc_n(32), false);  // O_tile = P V
       umma_commit(&bar_o);
     }
+    FT_MARK(7);
     mbar_wait(&bar_o, (uint32_t)(kt & 1));
     fence_after();
+    FT_MARK(8);
     float o[32];
     tmem_ld32(tO, o);
 #pragma unroll
     for (int c = 0; c < 32; ++c) acc[c] = fmaf(acc[c], corr, o[c]);
+    FT_MARK(9);
   }
+  FT_FLUSH();
   if (i < L) {
     const float inv = l > 0.f ? comp2 / l : 0.f;
     float* O = a.o + ((size_t)b * L + i) * a.ldo + (size_t)h * DK;
@@ -296,6 +361,230 @@ __global__ void __launch_bounds__(128, 3) flash_tc_fwd_kernel(FlashArgs a, float
   if (warp == 0) {
     fence_after();
     tmem_free<128>(tmem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
+// Forward, warp-specialised (v2).  The single-stage kernel above spends 40 % of a tile waiting for its own operand staging and
+// the rest in one serial chain (tools/exp/ft_profile.py, profiles/r2_flash_tc.md); here the roles run concurrently:
+//   warps 0-3 / 4-7 : softmax groups A / B, one query row per thread (CTA = 256 queries = two 128-row UMMA tiles sharing every
+//                     K / V stage).  S(kt) arrives in one of two TMEM buffers, so the tensor core computes S(kt+1) during softmax(kt).
+//   warps 8-11      : producers; warp w fills ring stage w with tiles kt = w, w+4, ...: K rows by cp.async, V transposed through
+//                     registers, 16 + 16 loads in flight per lane.
+//   warps 12 / 13   : MMA issue for group A / B (warp-uniform loops, one elected lane issues -- as gemm_tma.cu).
+// mbarriers: kv_full[s] (32 producer lanes) / kv_empty[s] (2 commits), s_full[g][2] (commit), p_full[g] (128 softmax threads: P
+// written, S and O_tile of the previous tile consumed), o_full[g] (commit: O_tile ready, P buffer free).
+constexpr int NS2 = 4;
+constexpr int STAGE2 = P64 + T64;                                   // 17 920
+constexpr int FWD2_SMEM = 2 * P128 + NS2 * STAGE2 + 2 * A64;        // 173 056
+constexpr int FWD2_THREADS = 448;
+
+__global__ void __launch_bounds__(FWD2_THREADS, 1) flash_tc_fwd2_kernel(FlashArgs a, float comp2) {
+  extern __shared__ __align__(128) uint8_t fsm[];
+  uint8_t* sQ = fsm;                                                // [2][P128]
+  uint8_t* ring = sQ + 2 * P128;                                    // [NS2][K panels P64 | V^T panels T64]
+  uint8_t* sP = ring + NS2 * STAGE2;                                // [2][A64]
+  __shared__ __align__(8) uint64_t q_full, kv_full[NS2], kv_empty[NS2], s_full[2][2], p_full[2], o_full[2];
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.z, h = blockIdx.y, i0 = (int)(gridDim.x - 1 - blockIdx.x) * 256;
+  const int L = a.L, X = a.X;
+  const int xl = (int)a.xlen[b], yl = (int)a.ylen[b];
+  const size_t boff = (size_t)b * L * a.ld + (size_t)h * DK;
+  const float *Q = a.q + boff, *K = a.k + boff, *V = a.v + boff;
+
+  if (tid == 0) {
+    mbar_init(&q_full, 128);
+    for (int s = 0; s < NS2; ++s) { mbar_init(&kv_full[s], 32); mbar_init(&kv_empty[s], 2); }
+    for (int g = 0; g < 2; ++g) { mbar_init(&s_full[g][0], 1); mbar_init(&s_full[g][1], 1); mbar_init(&p_full[g], 128); mbar_init(&o_full[g], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 12) tmem_alloc<512>(&tmem_slot);
+  int jend = max(X, min(i0 + 256, L));
+  jend = min(jend, X + yl);
+  jend = max(jend, min(X, L));
+  const int nt = (jend + 63) >> 6;
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp < 8) {
+    // ---------------- softmax groups ----------------
+    const int g = warp >> 2, r = (warp & 3) * 32 + lane;             // row of the group's 128-row tile = TMEM lane
+    const int i = i0 + g * 128 + r;
+    const uint32_t tg = tmem + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(g * 192);     // S0 +0, S1 +64, O_tile +128
+    uint8_t* myP = sP + g * A64;
+    const DropKey dkey = drop_key(a);
+    const float sl2 = a.scale * LOG2E * comp2;
+    const uint32_t z = (uint32_t)(b * a.H + h), Lh = (uint32_t)(L + 1) >> 1;
+    const uint32_t rowh = drop_row(dkey, z * Lh + ((uint32_t)i >> 1));
+    const int ig0 = i0 + g * 128;                                    // first row of the group: tile-level mask test
+    float m = -INFINITY, l = 0.f, corr_prev = 0.f;
+    float acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+    for (int kt = 0; kt < nt; ++kt) {
+      const int j0 = kt * 64;
+      mbar_wait(&s_full[g][kt & 1], (uint32_t)((kt >> 1) & 1));
+      fence_after();
+      float s[64];
+      tmem_ld32(tg + (uint32_t)((kt & 1) * 64), s);
+      tmem_ld32(tg + (uint32_t)((kt & 1) * 64 + 32), s + 32);
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      if (tile_full_tc<64>(ig0, j0, X, xl, yl)) {                    // warp-group uniform
+#pragma unroll
+        for (int c = 0; c < 64; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], s[c]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) {
+          s[c] = allowed(i, j0 + c, X, xl, yl) ? s[c] : -INFINITY;
+          mx4[c & 3] = fmaxf(mx4[c & 3], s[c]);
+        }
+      }
+      const float rmax = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      const float mx = fmaxf(m, rmax * sl2);
+      const float e = (mx == -INFINITY) ? 0.f : mx;
+      const float corr = ex2(m - e);
+      m = mx;
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        s[c] = ex2(fmaf(s[c], sl2, -e));
+        rs4[c & 3] += s[c];
+      }
+      l = l * corr + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
+      if (dkey.thr) {
+#pragma unroll
+        for (int c = 0; c < 64; c += 2) {
+          bool k0, k1;
+          drop_pair(dkey, rowh, i, j0 + c, k0, k1);
+          s[c] = k0 ? s[c] * dkey.inv : 0.f;
+          s[c + 1] = k1 ? s[c + 1] * dkey.inv : 0.f;
+        }
+      }
+      if (kt > 0) {                                                  // O_tile(kt-1) ready, P buffer free
+        mbar_wait(&o_full[g], (uint32_t)((kt - 1) & 1));
+        fence_after();
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          float o[16];
+          {
+            uint32_t rr[16];
+            asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                         : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]), "=r"(rr[8]),
+                           "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
+                         : "r"(tg + 128u + (uint32_t)(16 * hf)));
+            asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+            for (int c = 0; c < 16; ++c) o[c] = __uint_as_float(rr[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) acc[16 * hf + c] = fmaf(acc[16 * hf + c], corr_prev, o[c]);
+        }
+      }
+#pragma unroll
+      for (int c4 = 0; c4 < 16; ++c4)
+        *reinterpret_cast<float4*>(myP + ((size_t)c4 * QP + r) * 16) = make_float4(s[4 * c4], s[4 * c4 + 1], s[4 * c4 + 2], s[4 * c4 + 3]);
+      corr_prev = corr;
+      fence_async_smem();
+      fence_before();
+      mbar_arrive(&p_full[g]);
+    }
+    if (nt > 0) {
+      mbar_wait(&o_full[g], (uint32_t)((nt - 1) & 1));
+      fence_after();
+      float o[32];
+      tmem_ld32(tg + 128u, o);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) acc[c] = fmaf(acc[c], corr_prev, o[c]);
+    }
+    if (i < L) {
+      const float inv = l > 0.f ? comp2 / l : 0.f;
+      float* O = a.o + ((size_t)b * L + i) * a.ldo + (size_t)h * DK;
+#pragma unroll
+      for (int c = 0; c < 32; c += 4)
+        *reinterpret_cast<float4*>(O + c) = make_float4(acc[c] * inv, acc[c + 1] * inv, acc[c + 2] * inv, acc[c + 3] * inv);
+      a.lse[(size_t)z * L + i] = m + log2f(l);
+    }
+  } else if (warp < 12) {
+    // ---------------- producers ----------------
+    const int pw = warp - 8, pt = tid - 256;
+    for (int c = pt; c < 256 * 8; c += 128) {                        // both Q tiles
+      const int rr = c >> 3, j = c & 7, row = i0 + rr;
+      cp_async16(sQ + (size_t)(rr >> 7) * P128 + ((size_t)j * QP + (rr & 127)) * 16, Q + (size_t)(row < L ? row : 0) * a.ld + j * 4, row < L ? 16 : 0);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    fence_async_smem();
+    mbar_arrive(&q_full);
+    const int rot = (lane >> 3) & 3;
+    uint8_t* sKs = ring + (size_t)pw * STAGE2;
+    uint8_t* sVs = sKs + P64;
+    for (int kt = pw, n = 0; kt < nt; kt += NS2, ++n) {
+      const int j0 = kt * 64;
+      if (n > 0) mbar_wait(&kv_empty[pw], (uint32_t)((n - 1) & 1));
+      float4 v[16];
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const int c = lane + 32 * it, rr = c >> 3, j = c & 7, row = j0 + rr;
+        cp_async16(sKs + ((size_t)j * KP + rr) * 16, K + (size_t)(row < L ? row : 0) * a.ld + j * 4, row < L ? 16 : 0);
+      }
+      cp_async_commit();
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {                              // token chunk it: lane = (kk = lane & 3, dq = lane >> 2)
+        const int row = j0 + 4 * it + (lane & 3);
+        v[it] = row < L ? __ldg(reinterpret_cast<const float4*>(V + (size_t)row * a.ld + 4 * (lane >> 2))) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        float x[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+        rot4(x, rot);                                                // x[e] = component (e + rot) & 3
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          *reinterpret_cast<float*>(sVs + ((size_t)it * TP + 4 * (lane >> 2) + ((e + rot) & 3)) * 16 + (lane & 3) * 4) = x[e];
+      }
+      cp_async_wait<0>();
+      fence_async_smem();
+      mbar_arrive(&kv_full[pw]);
+    }
+  } else {
+    // ---------------- MMA issue, one warp per group ----------------
+    const int g = warp - 12;
+    const bool leader = elect_one();
+    const uint32_t aQ = smem_u32(sQ + (size_t)g * P128), aP = smem_u32(sP + (size_t)g * A64), aR = smem_u32(ring);
+    const uint32_t tS = tmem + (uint32_t)(g * 192), tO = tS + 128;
+    mbar_wait(&q_full, 0);
+    fence_after();
+    for (int kt = 0; kt <= nt; ++kt) {
+      if (kt < nt) {
+        const int st = kt % NS2;
+        mbar_wait(&kv_full[st], (uint32_t)((kt / NS2) & 1));
+        fence_after();
+        if (leader) {
+          mma_panels(tS + (uint32_t)((kt & 1) * 64), aQ, QP, aR + (uint32_t)(st * STAGE2), KP, 4, idesc_n(64), false);      // S = Q K^T
+          umma_commit(&s_full[g][kt & 1]);
+        }
+        __syncwarp();
+      }
+      if (kt > 0) {
+        const int t = kt - 1, st = t % NS2;
+        mbar_wait(&p_full[g], (uint32_t)(t & 1));
+        fence_after();
+        if (leader) {
+          mma_panels(tO, aP, QP, aR + (uint32_t)(st * STAGE2 + P64), TP, 8, idesc_n(32), false);                            // O_tile = P V
+          umma_commit(&o_full[g]);
+          umma_commit(&kv_empty[st]);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 12) {
+    fence_after();
+    tmem_free<512>(tmem);
   }
 }
 
@@ -607,7 +896,16 @@ static float comp2_now() { const float c = 1.f + g_flash_comp; return c * c; }
 int flash_tc_fwd_try(const FlashArgs& a, cudaStream_t st) {
   if (!g_flash_tc || (a.ld % 4) || (a.ldo % 4) || ((uintptr_t)a.o % 16)) return 1;
   static bool attr = false;
-  if (!attr) { if (int rc = set_smem(flash_tc_fwd_kernel, FWD_SMEM)) return rc; attr = true; }
+  if (!attr) {
+    if (int rc = set_smem(flash_tc_fwd_kernel, FWD_SMEM)) return rc;
+    if (int rc = set_smem(flash_tc_fwd2_kernel, FWD2_SMEM)) return rc;
+    attr = true;
+  }
+  if (g_flash_tc >= 2) {
+    dim3 grid2(cdiv(a.L, 256), a.H, a.B);
+    flash_tc_fwd2_kernel<<<grid2, FWD2_THREADS, FWD2_SMEM, st>>>(a, comp2_now());
+    return check_launch("flash_tc_fwd2");
+  }
   dim3 grid(cdiv(a.L, 128), a.H, a.B);
   flash_tc_fwd_kernel<<<grid, 128, FWD_SMEM, st>>>(a, comp2_now());
   return check_launch("flash_tc_fwd");
@@ -631,8 +929,16 @@ int flash_tc_bwd_try(const FlashArgs& a, cudaStream_t st) {
 }  // namespace evk
 
 extern "C" int evk_set_flash_tc(int32_t on, float trunc_comp) {
-  evk::g_flash_tc = on ? 1 : 0;
+  evk::g_flash_tc = on < 0 ? 0 : on;         // 0 off, 1 single-stage kernels, 2 warp-specialised forward
   if (trunc_comp >= 0.f) evk::g_flash_comp = trunc_comp;
   return 0;
 }
 extern "C" int evk_get_flash_tc(void) { return evk::g_flash_tc; }
+
+#ifdef FT_PROFILE
+extern "C" int evk_ft_prof_read(unsigned long long* host, int reset) {
+  if (host) cudaMemcpyFromSymbol(host, evk::g_ft_prof, sizeof(evk::g_ft_prof));
+  if (reset) { static unsigned long long z[16]; cudaMemcpyToSymbol(evk::g_ft_prof, z, sizeof(z)); }
+  return 0;
+}
+#endif

@@ -20,6 +20,25 @@ USE_TMA_WGRAD = True     # weight gradients of tap-free layers: transposes + spl
 UN_SCALE, UN_LRELU, UN_TANH, UN_MISH, UN_RELU, UN_TANH_FROM_OUT, UN_GELU = 0, 1, 2, 3, 4, 5, 6
 
 _launches = 0          # number of libevk kernel-launching calls (bench.py reports it)
+USE_NVTX = os.environ.get("EVK_NVTX", "0") != "0"
+
+
+class nvtx_range:
+    """NVTX range around a phase of a step when EVK_NVTX=1 (off: a no-op context manager, nothing on the hot path)."""
+    __slots__ = ("name",)
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if USE_NVTX:
+            torch.cuda.nvtx.range_push(self.name)
+        return self
+
+    def __exit__(self, *exc):
+        if USE_NVTX:
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 def launches():

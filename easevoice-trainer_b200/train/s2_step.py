@@ -270,23 +270,28 @@ class S2Step:
     #   A: G forward, features, D forward, D backward -> flat D grads          | all-reduce(D grads)
     #   B: D AdamW, D forward (updated weights), G backward -> flat G grads    | all-reduce(G grads)
     #   C: G AdamW, RNG advance
+    # EVK_NVTX=1 brackets the phases with NVTX ranges (ncu --nvtx --nvtx-include "s2/d_backward/" ... selects a phase's kernels).
     def _seg_a(self, batch, noise=None, ids_slice=None):
-        r = self.losses(batch, noise, ids_slice)
-        loss_d = self.d_loss(r)
-        with ops.grad_pool():
+        with ops.nvtx_range("s2/forward"):
+            r = self.losses(batch, noise, ids_slice)
+            loss_d = self.d_loss(r)
+        with ops.nvtx_range("s2/d_backward"), ops.grad_pool():
             self.opt_d.set_grads(torch.autograd.grad(loss_d, self.opt_d.params, allow_unused=True))
         return r, loss_d
 
     def _seg_b(self, r):
-        self.opt_d.step(1.0 / self.world)
-        loss_g, parts = self.g_loss(r)
-        with ops.grad_pool():
+        with ops.nvtx_range("s2/d_adamw"):
+            self.opt_d.step(1.0 / self.world)
+        with ops.nvtx_range("s2/g_loss_forward"):
+            loss_g, parts = self.g_loss(r)
+        with ops.nvtx_range("s2/g_backward"), ops.grad_pool():
             self.opt_g.set_grads(torch.autograd.grad(loss_g, self.opt_g.params, allow_unused=True))
         return loss_g, parts
 
     def _seg_c(self):
-        self.opt_g.step(1.0 / self.world)
-        ops.advance_rng()
+        with ops.nvtx_range("s2/g_adamw"):
+            self.opt_g.step(1.0 / self.world)
+            ops.advance_rng()
 
     @staticmethod
     def _outputs(loss_d, loss_g, parts, opt_d, opt_g):

@@ -24,7 +24,7 @@ def rel(a, b):
 
 
 def run(qkv, dout, H, X, xl, yl, p, tc):
-    L_.evk_set_flash_tc(1 if tc else 0, -1.0)
+    L_.evk_set_flash_tc(int(tc), -1.0)
     q = qkv.clone().requires_grad_(True)
     o = ops.flash_attention(q, heads=H, prefix=X, xlen=xl, ylen=yl, p_drop=p, tag="ab")
     o.backward(dout)
@@ -54,7 +54,8 @@ def ref64(qkv, dout, H, X, xl, yl):
     return o.detach(), x.grad.detach()
 
 
-out = dict(parity=[], timing={})
+TC = int(os.environ.get("AB_TC", "2"))          # kernel generation under test (1: single-stage, 2: warp-specialised forward)
+out = dict(parity=[], timing={}, tc=TC)
 g = torch.Generator().manual_seed(11)
 cases = [  # B, H, X, Y, xlens, ylens, p_drop
     (2, 4, 12, 20, [12, 7], [20, 13], 0.0),
@@ -70,8 +71,8 @@ for (B, H, X, Y, xls, yls, p) in cases:
     dout = torch.randn(B, L, H * 32, generator=g).to(dev)
     xl = torch.tensor(xls, device=dev, dtype=torch.int64)
     yl = torch.tensor(yls, device=dev, dtype=torch.int64)
-    o0, g0 = run(qkv, dout, H, X, xl, yl, p, tc=False)
-    o1, g1 = run(qkv, dout, H, X, xl, yl, p, tc=True)
+    o0, g0 = run(qkv, dout, H, X, xl, yl, p, tc=0)
+    o1, g1 = run(qkv, dout, H, X, xl, yl, p, tc=TC)
     D = H * 32
     row = dict(case=f"B{B} H{H} X{X} Y{Y} p{p}", o=rel(o1, o0), dq=rel(g1[..., :D], g0[..., :D]), dk=rel(g1[..., D:2 * D], g0[..., D:2 * D]),
                dv=rel(g1[..., 2 * D:], g0[..., 2 * D:]), finite=bool(torch.isfinite(o1).all() and torch.isfinite(g1).all()))
@@ -96,7 +97,7 @@ if "--no-time" not in sys.argv:
     xl = torch.full((B,), X, device=dev, dtype=torch.int64)
     yl = torch.full((B,), Y, device=dev, dtype=torch.int64)
     pairs = B * H * (X * L + Y * (Y + 1) // 2)
-    for tc in (0, 1):
+    for tc in (0, 1, 2):
         for p in (0.0, 0.1):
             L_.evk_set_flash_tc(tc, -1.0)
             q = qkv.clone().requires_grad_(True)
