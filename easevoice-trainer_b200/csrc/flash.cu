@@ -134,8 +134,8 @@ __global__ void __launch_bounds__(128, 5) flash_fwd_kernel(FlashArgs a) {
   float qa[4][4];
   load_a_frags(qa, Q, a.ld, i0 + warp * 16, L);
   const int ra = i0 + warp * 16 + gq, rb = ra + 8;
-  const uint32_t z = (uint32_t)(b * a.H + h), Lh = (uint32_t)(L + 1) >> 1;
-  const uint32_t rha = drop_row(dkey, z * Lh + ((uint32_t)ra >> 1)), rhb = drop_row(dkey, z * Lh + ((uint32_t)rb >> 1));
+  const uint32_t z = (uint32_t)(b * a.H + h);
+  const uint32_t rha = drop_row(dkey, z * (uint32_t)L + (uint32_t)ra), rhb = drop_row(dkey, z * (uint32_t)L + (uint32_t)rb);
 
   float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
   float acc[4][4];
@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(128, 5) flash_fwd_kernel(FlashArgs a) {
       rs0 += p0 + p1; rs1 += p2 + p3;
       if (dkey.thr) {
         bool k0, k1, k2, k3;
-        drop_pair(dkey, rha, ra, j, k0, k1);
-        drop_pair(dkey, rhb, rb, j, k2, k3);
+        drop_pair(dkey, rha, j, k0, k1);
+        drop_pair(dkey, rhb, j, k2, k3);
         p0 = k0 ? p0 * dkey.inv : 0.f;
         p1 = k1 ? p1 * dkey.inv : 0.f;
         p2 = k2 ? p2 * dkey.inv : 0.f;
@@ -250,8 +250,7 @@ __global__ void __launch_bounds__(128, 3) flash_dq_kernel(FlashArgs a) {
   load_a_frags(qa, Q, a.ld, i0 + warp * 16, L);
   load_a_frags(da, dO, a.lddo, i0 + warp * 16, L);
   const int ra = i0 + warp * 16 + gq, rb = ra + 8;
-  const uint32_t Lh = (uint32_t)(L + 1) >> 1;
-  const uint32_t rha = drop_row(dkey, z * Lh + ((uint32_t)ra >> 1)), rhb = drop_row(dkey, z * Lh + ((uint32_t)rb >> 1));
+  const uint32_t rha = drop_row(dkey, z * (uint32_t)L + (uint32_t)ra), rhb = drop_row(dkey, z * (uint32_t)L + (uint32_t)rb);
   const float* lse = a.lse + (size_t)z * L;
   const float* dl = a.delta + (size_t)z * L;
   const float lse0 = ra < L ? lse[ra] : 0.f, lse1 = rb < L ? lse[rb] : 0.f;
@@ -283,8 +282,8 @@ __global__ void __launch_bounds__(128, 3) flash_dq_kernel(FlashArgs a) {
       const int j = j0 + nt * 8 + 2 * t;
       bool keep[4] = {true, true, true, true};
       if (dkey.thr) {
-        drop_pair(dkey, rha, ra, j, keep[0], keep[1]);
-        drop_pair(dkey, rhb, rb, j, keep[2], keep[3]);
+        drop_pair(dkey, rha, j, keep[0], keep[1]);
+        drop_pair(dkey, rhb, j, keep[2], keep[3]);
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -312,7 +311,7 @@ __global__ void __launch_bounds__(128, 3) flash_dkv_kernel(FlashArgs a) {
   __shared__ __align__(16) float sQ[2][BT * LDT];
   __shared__ __align__(16) float sD[2][BT * LDT];
   __shared__ float sL[2][BT], sDl[2][BT];
-  __shared__ uint32_t sRh[2][BT / 2];                              // dropout hashes of the query-row pairs of the staged tile
+  __shared__ uint32_t sRh[2][BT];                                  // dropout hashes of the query rows of the staged tile
   const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * BT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
   const int L = a.L, X = a.X;
@@ -330,6 +329,8 @@ __global__ void __launch_bounds__(128, 3) flash_dkv_kernel(FlashArgs a) {
   load_a_frags(ka, K, a.ld, j0 + warp * 16, L);
   load_a_frags(va, V, a.ld, j0 + warp * 16, L);
   const int ja = j0 + warp * 16 + gq, jb = ja + 8;
+  const uint32_t cta = drop_col(dkey, ja), ctb = drop_col(dkey, jb);
+  const uint32_t mula = (ja & 1) ? DROP_M2 : DROP_M1, mulb = (jb & 1) ? DROP_M2 : DROP_M1;
   float dk[4][4], dv[4][4];
 #pragma unroll
   for (int n = 0; n < 4; ++n) {
@@ -346,9 +347,10 @@ __global__ void __launch_bounds__(128, 3) flash_dkv_kernel(FlashArgs a) {
       int i = qt * BT + threadIdx.x;
       sL[buf][threadIdx.x] = i < L ? lse[i] : 0.f;
       sDl[buf][threadIdx.x] = i < L ? dl[i] : 0.f;
-    } else if (threadIdx.x < BT + BT / 2) {
+    }
+    if (threadIdx.x >= BT) {                                         // 64 more threads: one query-row hash each
       const int r = threadIdx.x - BT;
-      sRh[buf][r] = drop_row(dkey, z * ((uint32_t)(L + 1) >> 1) + (uint32_t)(qt * (BT / 2) + r));
+      sRh[buf][r] = drop_row(dkey, z * (uint32_t)L + (uint32_t)(qt * BT + r));
     }
   };
   const bool dead = (j0 >= X + yl) && (j0 >= X);   // every key of the tile is padding: gradients are zero
@@ -372,13 +374,11 @@ __global__ void __launch_bounds__(128, 3) flash_dkv_kernel(FlashArgs a) {
         const int ile = nt * 8 + 2 * t;                              // even local query index: rows (ile, ile + 1) share a hash
         bool keep[4] = {true, true, true, true};
         if (dkey.thr) {
-          const uint32_t rowh = sRh[cur][ile >> 1];
-          const uint32_t xa = drop_block(dkey, rowh, (uint32_t)ja >> 1), xb = drop_block(dkey, rowh, (uint32_t)jb >> 1);
-          const uint32_t sa = (ja & 1) ? 16u : 0u, sb = (jb & 1) ? 16u : 0u;
-          keep[0] = ((xa >> sa) & 0xffffu) >= dkey.thr;
-          keep[1] = ((drop_odd(xa) >> sa) & 0xffffu) >= dkey.thr;
-          keep[2] = ((xb >> sb) & 0xffffu) >= dkey.thr;
-          keep[3] = ((drop_odd(xb) >> sb) & 0xffffu) >= dkey.thr;
+          const uint32_t r0 = sRh[cur][ile], r1 = sRh[cur][ile + 1];
+          keep[0] = drop_one(dkey, r0, cta, mula);
+          keep[1] = drop_one(dkey, r1, cta, mula);
+          keep[2] = drop_one(dkey, r0, ctb, mulb);
+          keep[3] = drop_one(dkey, r1, ctb, mulb);
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {

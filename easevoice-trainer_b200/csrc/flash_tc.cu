@@ -108,11 +108,22 @@ __device__ unsigned long long g_ft_prof[16];
 #define FT_MARK(i) do { if (threadIdx.x == 0) { const long long ft_n = clock64(); ft_acc[i] += (unsigned long long)(ft_n - ft_t); ft_t = ft_n; } } while (0)
 #define FT_INC(i) ft_acc[i] += 1ull
 #define FT_FLUSH() do { if (threadIdx.x == 0) { ft_acc[11] = (unsigned long long)(clock64() - ft_t0); for (int ft_i = 0; ft_i < 12; ++ft_i) atomicAdd(&g_ft_prof[ft_i], ft_acc[ft_i]); } } while (0)
+// v2 roles: 0 softmax waits S, 1 ld S + max + exp (+ dropout), 2 waits O_tile, 3 ld O + accumulate, 4 P stores + fence + arrive,
+// 5 MMA waits kv_full, 6 issue S, 7 waits p_full, 8 issue P V, 9 producer waits kv_empty, 10 issue loads, 11 rotate + V^T stores (load
+// latency), 12 cp.async wait + fence + arrive, 13 softmax tiles, 14 kernel, 15 producer tiles
+#define FT2_DECL(cond) const bool ft2_on = (cond); long long ft2_t = clock64(); const long long ft2_t0 = ft2_t; unsigned long long ft2_acc[16] = {0ull}
+#define FT2_MARK(i) do { if (ft2_on) { const long long ft2_n = clock64(); ft2_acc[i] += (unsigned long long)(ft2_n - ft2_t); ft2_t = ft2_n; } } while (0)
+#define FT2_INC(i) ft2_acc[i] += 1ull
+#define FT2_FLUSH(lo, hi, tot) do { if (ft2_on) { if ((tot) >= 0) ft2_acc[(tot) & 15] = (unsigned long long)(clock64() - ft2_t0); for (int ft_i = (lo); ft_i <= (hi); ++ft_i) atomicAdd(&g_ft_prof[ft_i], ft2_acc[ft_i]); if ((tot) >= 0) atomicAdd(&g_ft_prof[(tot) & 15], ft2_acc[(tot) & 15]); } } while (0)
 #else
 #define FT_DECL()
 #define FT_MARK(i)
 #define FT_INC(i)
 #define FT_FLUSH()
+#define FT2_DECL(cond)
+#define FT2_MARK(i)
+#define FT2_INC(i)
+#define FT2_FLUSH(lo, hi, tot)
 #endif
 
 template <int COLS>
@@ -254,8 +265,8 @@ __global__ void __launch_bounds__(128, FT_MINB) flash_tc_fwd_kernel(FlashArgs a,
   const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP);
 
   const int i = i0 + tid;                                            // this thread's query row = TMEM lane
-  const uint32_t z = (uint32_t)(b * a.H + h), Lh = (uint32_t)(L + 1) >> 1;
-  const uint32_t rowh = drop_row(dkey, z * Lh + ((uint32_t)i >> 1));
+  const uint32_t z = (uint32_t)(b * a.H + h);
+  const uint32_t rowh = drop_row(dkey, z * (uint32_t)L + (uint32_t)i);
   float m = -INFINITY, l = 0.f;
   float acc[32];
 #pragma unroll
@@ -319,7 +330,7 @@ __global__ void __launch_bounds__(128, FT_MINB) flash_tc_fwd_kernel(FlashArgs a,
 #pragma unroll
         for (int u = 0; u < 4; u += 2) {
           bool k0, k1;
-          drop_pair(dkey, rowh, i, j0 + 4 * c4 + u, k0, k1);
+          drop_pair(dkey, rowh, j0 + 4 * c4 + u, k0, k1);
           p[u] = k0 ? p[u] * dkey.inv : 0.f;
           p[u + 1] = k1 ? p[u + 1] * dkey.inv : 0.f;
         }
@@ -417,17 +428,21 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1) flash_tc_fwd2_kernel(FlashArg
     uint8_t* myP = sP + g * A64;
     const DropKey dkey = drop_key(a);
     const float sl2 = a.scale * LOG2E * comp2;
-    const uint32_t z = (uint32_t)(b * a.H + h), Lh = (uint32_t)(L + 1) >> 1;
-    const uint32_t rowh = drop_row(dkey, z * Lh + ((uint32_t)i >> 1));
+    const uint32_t z = (uint32_t)(b * a.H + h);
+    const uint32_t rowh = drop_row(dkey, z * (uint32_t)L + (uint32_t)i);
     const int ig0 = i0 + g * 128;                                    // first row of the group: tile-level mask test
     float m = -INFINITY, l = 0.f, corr_prev = 0.f;
     float acc[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+    FT2_DECL(tid == 0);
     for (int kt = 0; kt < nt; ++kt) {
       const int j0 = kt * 64;
+      FT2_MARK(14);
+      FT2_INC(13);
       mbar_wait(&s_full[g][kt & 1], (uint32_t)((kt >> 1) & 1));
       fence_after();
+      FT2_MARK(0);
       float s[64];
       tmem_ld32(tg + (uint32_t)((kt & 1) * 64), s);
       tmem_ld32(tg + (uint32_t)((kt & 1) * 64 + 32), s + 32);
@@ -458,14 +473,16 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1) flash_tc_fwd2_kernel(FlashArg
 #pragma unroll
         for (int c = 0; c < 64; c += 2) {
           bool k0, k1;
-          drop_pair(dkey, rowh, i, j0 + c, k0, k1);
+          drop_pair(dkey, rowh, j0 + c, k0, k1);
           s[c] = k0 ? s[c] * dkey.inv : 0.f;
           s[c + 1] = k1 ? s[c + 1] * dkey.inv : 0.f;
         }
       }
+      FT2_MARK(1);
       if (kt > 0) {                                                  // O_tile(kt-1) ready, P buffer free
         mbar_wait(&o_full[g], (uint32_t)((kt - 1) & 1));
         fence_after();
+        FT2_MARK(2);
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           float o[16];
@@ -483,6 +500,7 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1) flash_tc_fwd2_kernel(FlashArg
           for (int c = 0; c < 16; ++c) acc[16 * hf + c] = fmaf(acc[16 * hf + c], corr_prev, o[c]);
         }
       }
+      FT2_MARK(3);
 #pragma unroll
       for (int c4 = 0; c4 < 16; ++c4)
         *reinterpret_cast<float4*>(myP + ((size_t)c4 * QP + r) * 16) = make_float4(s[4 * c4], s[4 * c4 + 1], s[4 * c4 + 2], s[4 * c4 + 3]);
@@ -490,7 +508,12 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1) flash_tc_fwd2_kernel(FlashArg
       fence_async_smem();
       fence_before();
       mbar_arrive(&p_full[g]);
+      FT2_MARK(4);
     }
+    FT2_FLUSH(0, 4, 14);
+#ifdef FT_PROFILE
+    if (ft2_on) atomicAdd(&g_ft_prof[13], ft2_acc[13]);
+#endif
     if (nt > 0) {
       mbar_wait(&o_full[g], (uint32_t)((nt - 1) & 1));
       fence_after();
@@ -521,9 +544,13 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1) flash_tc_fwd2_kernel(FlashArg
     const int rot = (lane >> 3) & 3;
     uint8_t* sKs = ring + (size_t)pw * STAGE2;
     uint8_t* sVs = sKs + P64;
+    FT2_DECL(tid == 256);
     for (int kt = pw, n = 0; kt < nt; kt += NS2, ++n) {
       const int j0 = kt * 64;
+      FT2_MARK(14);
+      FT2_INC(15);
       if (n > 0) mbar_wait(&kv_empty[pw], (uint32_t)((n - 1) & 1));
+      FT2_MARK(9);
       float4 v[16];
 #pragma unroll
       for (int it = 0; it < 16; ++it) {
@@ -536,6 +563,7 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1) flash_tc_fwd2_kernel(FlashArg
         const int row = j0 + 4 * it + (lane & 3);
         v[it] = row < L ? __ldg(reinterpret_cast<const float4*>(V + (size_t)row * a.ld + 4 * (lane >> 2))) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+      FT2_MARK(10);
 #pragma unroll
       for (int it = 0; it < 16; ++it) {
         float x[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
@@ -544,10 +572,16 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1) flash_tc_fwd2_kernel(FlashArg
         for (int e = 0; e < 4; ++e)
           *reinterpret_cast<float*>(sVs + ((size_t)it * TP + 4 * (lane >> 2) + ((e + rot) & 3)) * 16 + (lane & 3) * 4) = x[e];
       }
+      FT2_MARK(11);
       cp_async_wait<0>();
       fence_async_smem();
       mbar_arrive(&kv_full[pw]);
+      FT2_MARK(12);
     }
+    FT2_FLUSH(9, 12, -1);
+#ifdef FT_PROFILE
+    if (ft2_on) atomicAdd(&g_ft_prof[15], ft2_acc[15]);
+#endif
   } else {
     // ---------------- MMA issue, one warp per group ----------------
     const int g = warp - 12;
@@ -556,29 +590,36 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1) flash_tc_fwd2_kernel(FlashArg
     const uint32_t tS = tmem + (uint32_t)(g * 192), tO = tS + 128;
     mbar_wait(&q_full, 0);
     fence_after();
+    FT2_DECL(warp == 12 && leader);
     for (int kt = 0; kt <= nt; ++kt) {
+      FT2_MARK(14);
       if (kt < nt) {
         const int st = kt % NS2;
         mbar_wait(&kv_full[st], (uint32_t)((kt / NS2) & 1));
         fence_after();
+        FT2_MARK(5);
         if (leader) {
           mma_panels(tS + (uint32_t)((kt & 1) * 64), aQ, QP, aR + (uint32_t)(st * STAGE2), KP, 4, idesc_n(64), false);      // S = Q K^T
           umma_commit(&s_full[g][kt & 1]);
         }
         __syncwarp();
+        FT2_MARK(6);
       }
       if (kt > 0) {
         const int t = kt - 1, st = t % NS2;
         mbar_wait(&p_full[g], (uint32_t)(t & 1));
         fence_after();
+        FT2_MARK(7);
         if (leader) {
           mma_panels(tO, aP, QP, aR + (uint32_t)(st * STAGE2 + P64), TP, 8, idesc_n(32), false);                            // O_tile = P V
           umma_commit(&o_full[g]);
           umma_commit(&kv_empty[st]);
         }
         __syncwarp();
+        FT2_MARK(8);
       }
     }
+    FT2_FLUSH(5, 8, -1);
   }
   fence_before();
   __syncthreads();
@@ -630,8 +671,8 @@ __global__ void __launch_bounds__(128, 2) flash_tc_dq_kernel(FlashArgs a, float 
   const uint32_t aQ = smem_u32(sQ), aD = smem_u32(sD), aK = smem_u32(sK), aV = smem_u32(sV), aKT = smem_u32(sKT), aS = smem_u32(sS);
 
   const int i = i0 + tid;
-  const uint32_t z = (uint32_t)(b * a.H + h), Lh = (uint32_t)(L + 1) >> 1;
-  const uint32_t rowh = drop_row(dkey, z * Lh + ((uint32_t)i >> 1));
+  const uint32_t z = (uint32_t)(b * a.H + h);
+  const uint32_t rowh = drop_row(dkey, z * (uint32_t)L + (uint32_t)i);
   const float lse_i = i < L ? a.lse[(size_t)z * L + i] : 0.f;
   const float del_i = i < L ? a.delta[(size_t)z * L + i] : 0.f;
   const float ginv = dkey.inv * comp2;                               // dP = (dO V^T) * comp2, then the dropout scale
@@ -681,7 +722,7 @@ __global__ void __launch_bounds__(128, 2) flash_tc_dq_kernel(FlashArgs a, float 
           float g0 = dp[c] * ginv, g1 = dp[c + 1] * ginv;
           if (dkey.thr) {
             bool k0, k1;
-            drop_pair(dkey, rowh, i, j, k0, k1);
+            drop_pair(dkey, rowh, j, k0, k1);
             g0 = k0 ? g0 : 0.f;
             g1 = k1 ? g1 : 0.f;
           }
@@ -731,7 +772,7 @@ __global__ void __launch_bounds__(128, 2) flash_tc_dkv_kernel(FlashArgs a, float
   __shared__ __align__(8) uint64_t bar_s, bar_o;
   __shared__ uint32_t tmem_slot;
   __shared__ float sL[32], sDl[32];
-  __shared__ uint32_t sRh[16];
+  __shared__ uint32_t sRh[32];
   const int tid = threadIdx.x, warp = tid >> 5;
   const int b = blockIdx.z, h = blockIdx.y, j0 = blockIdx.x * 128;   // early key tiles (seen by the most queries) first
   const int L = a.L, X = a.X;
@@ -741,7 +782,7 @@ __global__ void __launch_bounds__(128, 2) flash_tc_dkv_kernel(FlashArgs a, float
   const float* dO = a.dout + (size_t)b * L * a.lddo + (size_t)h * DK;
   const DropKey dkey = drop_key(a);
   const float sl2 = a.scale * LOG2E * comp2;
-  const uint32_t z = (uint32_t)(b * a.H + h), Lh = (uint32_t)(L + 1) >> 1;
+  const uint32_t z = (uint32_t)(b * a.H + h);
   const float* lse = a.lse + (size_t)z * L;
   const float* dl = a.delta + (size_t)z * L;
 
@@ -773,7 +814,7 @@ __global__ void __launch_bounds__(128, 2) flash_tc_dkv_kernel(FlashArgs a, float
   const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aQ = smem_u32(sQ), aD = smem_u32(sD), aQT = smem_u32(sQT), aDT = smem_u32(sDT),
                  aPT = smem_u32(sPT), aST = smem_u32(sST);
   const int j = j0 + tid;                                            // this thread's key row = TMEM lane
-  const uint32_t jsh = (j & 1) ? 16u : 0u;
+  const uint32_t colterm = drop_col(dkey, j), colmul = (j & 1) ? DROP_M2 : DROP_M1;
   const float ginv = dkey.inv * comp2;
 
   for (int t = 0; t < nt; ++t) {
@@ -788,8 +829,8 @@ __global__ void __launch_bounds__(128, 2) flash_tc_dkv_kernel(FlashArgs a, float
       const int i = i0 + tid;
       sL[tid] = i < L ? lse[i] : 0.f;
       sDl[tid] = i < L ? dl[i] : 0.f;
-    } else if (tid < 48) {
-      sRh[tid - 32] = drop_row(dkey, z * Lh + (uint32_t)((i0 >> 1) + (tid - 32)));
+    } else if (tid < 64) {
+      sRh[tid - 32] = drop_row(dkey, z * (uint32_t)L + (uint32_t)(i0 + tid - 32));
     }
     cp_async_wait<0>();
     fence_async_smem();
@@ -828,8 +869,7 @@ __global__ void __launch_bounds__(128, 2) flash_tc_dkv_kernel(FlashArgs a, float
         float g0 = dp[c] * ginv, g1 = dp[c + 1] * ginv;
         float q0 = p0 * dkey.inv, q1 = p1 * dkey.inv;
         if (dkey.thr) {
-          const uint32_t xa = drop_block(dkey, sRh[c >> 1], (uint32_t)j >> 1);
-          const bool k0 = ((xa >> jsh) & 0xffffu) >= dkey.thr, k1 = ((drop_odd(xa) >> jsh) & 0xffffu) >= dkey.thr;
+          const bool k0 = drop_one(dkey, sRh[c], colterm, colmul), k1 = drop_one(dkey, sRh[c + 1], colterm, colmul);
           g0 = k0 ? g0 : 0.f; q0 = k0 ? q0 : 0.f;
           g1 = k1 ? g1 : 0.f; q1 = k1 ? q1 : 0.f;
         }

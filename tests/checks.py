@@ -1544,6 +1544,59 @@ def check_infer_panel():
     return out
 
 
+def check_flash_tc():
+    """The tcgen05 / TMEM attention family (csrc/flash_tc.cu: single-stage forward / dq / dkv, warp-specialised forward) vs a float64
+    torch reference and vs the mma.sync family (csrc/flash.cu) on the same inputs and the same dropout stream: full and ragged
+    lengths, no prefix, lengths that are not multiples of any tile, with and without dropout."""
+    from easevoice_trainer_b200 import lib
+    L_ = lib.load()
+    o = ops_mod()
+    out = []
+    g = _gen(11)
+    was = L_.evk_get_flash_tc()
+
+    def run(qkv, dout, H, X, xl, yl, p, tc):
+        L_.evk_set_flash_tc(tc, -1.0)
+        q = qkv.to(DEV).requires_grad_(True)
+        y = o.flash_attention(q, heads=H, prefix=X, xlen=xl.to(DEV), ylen=yl.to(DEV), p_drop=p, tag="chk.tc")
+        y.backward(dout.to(DEV))
+        torch.cuda.synchronize()
+        return y.detach().cpu(), q.grad.detach().cpu()
+
+    try:
+        cases = [(2, 4, 12, 20, [12, 7], [20, 13], 0.0), (2, 16, 256, 300, [256, 190], [300, 211], 0.0),
+                 (3, 8, 100, 413, [100, 64, 1], [413, 129, 300], 0.0), (2, 16, 256, 300, [256, 190], [300, 211], 0.1),
+                 (1, 16, 0, 130, [0], [130], 0.1)]
+        for B, H, X, Y, xls, yls, p in cases:
+            L, D = X + Y, H * 32
+            qkv = torch.randn(B, L, 3 * D, generator=g) * 1.5
+            dout = torch.randn(B, L, D, generator=g)
+            xl, yl = torch.tensor(xls), torch.tensor(yls)
+            o0, g0 = run(qkv, dout, H, X, xl, yl, p, 0)
+            tag = f"B{B} H{H} X{X} Y{Y} p{p}"
+            ref = None
+            if p == 0.0:
+                qr = qkv.double().requires_grad_(True)
+                orf = _sdpa_oracle(qr, H, X, xl, yl)
+                orf.backward(dout.double())
+                ref = (orf.detach(), qr.grad.detach())
+            for tc in (1, 2):
+                o1, g1 = run(qkv, dout, H, X, xl, yl, p, tc)
+                fin = bool(torch.isfinite(o1).all() and torch.isfinite(g1).all())
+                out.append((f"flash_tc[{tc}] {tag} finite", 0.0 if fin else 1.0, 0.5))
+                # the two families differ by rounding (round-to-nearest vs compensated truncation): two TF32-class errors apart
+                out.append((f"flash_tc[{tc}] {tag} out vs mma.sync family", rel(o1, o0), 2 * TOL_TC))
+                for nm, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
+                    out.append((f"flash_tc[{tc}] {tag} {nm} vs mma.sync family", rel(g1[..., sl], g0[..., sl]), 2 * TOL_TC2))
+                if ref is not None:
+                    out.append((f"flash_tc[{tc}] {tag} out vs float64", rel(o1, ref[0]), TOL_TC))
+                    for nm, sl in (("dq", slice(0, D)), ("dk", slice(D, 2 * D)), ("dv", slice(2 * D, 3 * D))):
+                        out.append((f"flash_tc[{tc}] {tag} {nm} vs float64", rel(g1[..., sl], ref[1][..., sl]), TOL_TC2))
+    finally:
+        L_.evk_set_flash_tc(was, -1.0)
+    return out
+
+
 def ops_mod():
     from easevoice_trainer_b200 import ops
     return ops
@@ -1597,7 +1650,7 @@ ALL = [check_conv, check_conv_transpose, check_elementwise, check_attention, che
        check_gpt_kernels, check_scaled_adam, lambda: check_gpt("small"), lambda: check_gpt("ragged"),
        check_gpt_dpo_and_trainer, check_gemm_tma, check_vocoder_cfg5,
        lambda: check_s2_full("cfg3"), lambda: check_s2_full("cfg3r"), lambda: check_gpt_full("cfg2"),
-       check_sovits_train_e2e, check_stft, check_fused_dropout, check_side_streams, check_normalize_token, check_decode, check_infer_panel, check_hubert]
+       check_sovits_train_e2e, check_stft, check_fused_dropout, check_side_streams, check_normalize_token, check_decode, check_infer_panel, check_hubert, check_flash_tc]
 NAMES = ["conv", "conv_transpose", "elementwise", "attention", "vq_losses_optim", "mel", "s2_small", "s2_ragged", "api",
          "gpt_kernels", "scaled_adam", "gpt_small", "gpt_ragged", "gpt_dpo_trainer", "gemm_tma", "vocoder_cfg5",
-         "s2_cfg3", "s2_cfg3r", "gpt_cfg2", "sovits_train_e2e", "stft_mrstft", "fused_dropout", "side_streams", "normalize_token", "decode", "infer_panel", "hubert"]
+         "s2_cfg3", "s2_cfg3r", "gpt_cfg2", "sovits_train_e2e", "stft_mrstft", "fused_dropout", "side_streams", "normalize_token", "decode", "infer_panel", "hubert", "flash_tc"]

@@ -6,7 +6,7 @@ pytestmark = pytest.mark.gpu
 
 GROUPS = ["conv", "conv_transpose", "elementwise", "attention", "vq_losses_optim", "mel", "s2_small", "s2_ragged", "api",
           "gpt_kernels", "scaled_adam", "gpt_small", "gpt_ragged", "gpt_dpo_trainer", "gemm_tma", "vocoder_cfg5",
-          "s2_cfg3", "s2_cfg3r", "gpt_cfg2", "sovits_train_e2e", "stft_mrstft", "fused_dropout", "side_streams", "normalize_token", "decode", "infer_panel", "hubert"]          # the last three: BASELINE configs 3 / 2 at the benchmarked shapes
+          "s2_cfg3", "s2_cfg3r", "gpt_cfg2", "sovits_train_e2e", "stft_mrstft", "fused_dropout", "side_streams", "normalize_token", "decode", "infer_panel", "hubert", "flash_tc"]          # the last three: BASELINE configs 3 / 2 at the benchmarked shapes
 
 
 @pytest.fixture(scope="module")

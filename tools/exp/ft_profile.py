@@ -22,7 +22,11 @@ g = torch.Generator().manual_seed(1)
 qkv = torch.randn(B, L, 3 * H * 32, generator=g).to(dev)
 xl = torch.full((B,), X, device=dev, dtype=torch.int64)
 yl = torch.full((B,), Y, device=dev, dtype=torch.int64)
-L_.evk_set_flash_tc(1, -1.0)
+TC = int(os.environ.get("AB_TC", "1"))
+NAMES2 = ["softmax: wait S", "softmax: ld S+max+exp(+drop)", "softmax: wait O_tile", "softmax: ld O + acc", "softmax: P stores+fence+arrive",
+          "mma: wait kv_full", "mma: issue S", "mma: wait p_full", "mma: issue PV", "prod: wait kv_empty", "prod: issue loads",
+          "prod: rotate + V^T stores", "prod: cp.async wait+fence+arrive"]
+L_.evk_set_flash_tc(TC, -1.0)
 for p in (0.0, 0.1):
     with torch.no_grad():
         for _ in range(2):
@@ -37,6 +41,12 @@ for p in (0.0, 0.1):
         torch.cuda.synchronize()
         raw.evk_ft_prof_read(buf, 0)
     v = list(buf)
+    if TC == 2:
+        tiles, ptiles = max(v[13], 1), max(v[15], 1)
+        print(f"== v2 p_drop={p}: {e0.elapsed_time(e1):.3f} ms, {tiles} (256 x 64) tiles, {v[14] / tiles:.0f} cycles per tile per CTA")
+        for i in range(13):
+            print(f"   {NAMES2[i]:36s} {v[i] / (ptiles if i >= 9 else tiles):8.0f} cycles/tile")
+        continue
     tiles = max(v[10], 1)
     print(f"== {os.path.basename(os.environ['EVK_LIB_PATH'])} p_drop={p}: {e0.elapsed_time(e1):.3f} ms, {tiles} tiles, {v[11] / tiles:.0f} cycles per tile per CTA")
     for i in range(10):
