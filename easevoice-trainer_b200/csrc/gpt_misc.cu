@@ -275,42 +275,71 @@ __global__ void sadam_update_kernel(float* __restrict__ p, float* __restrict__ g
 
 // ---- KV-cache attention of one new token (T2SBlock.decode_next_token, t2s_model.py:203-221) --------------------------------
 // Cache rows are the in_proj outputs [q | k | v] (3 * H * 32 floats, row pitch ld) of every position so far; the query is the
-// q block of the LAST row.  One CTA per (head, batch item): each warp walks a quarter of the keys with an online softmax
-// (lane d owns dimension d of q, of the running output and of the dot-product reduction), the four partial states are merged
-// through shared memory.  Exact fp32 -- the sampled token must not depend on operand rounding.
+// q block of the LAST row.  One CTA per (head, batch item), 128 threads, key-parallel (see the kernel).  Exact fp32 -- the sampled token must not depend on operand rounding.
 __global__ void __launch_bounds__(128) attn_decode_kernel(const float* __restrict__ qkv, long long sb, int ld, int n, const int* __restrict__ n_dev,
                                                            int H, float scale, float* __restrict__ out, int ldo) {
   if (n_dev) n = *n_dev + 1;                                     // graph replay: keys 0 .. *n_dev (the row just appended)
   const int h = blockIdx.x, b = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float* base = qkv + (long long)b * sb;
   const int D = H * 32;
-  const float q = base[(long long)(n - 1) * ld + h * 32 + lane] * scale;
-  float m = -INFINITY, l = 0.f, acc = 0.f;
-  for (int j = warp; j < n; j += 4) {
-    const float* row = base + (long long)j * ld;
-    float s = q * row[D + h * 32 + lane];
+  // Key-parallel: thread t owns keys t, t + 128, ... (the whole 32-float q / k / v rows in registers: no per-key shuffle chain,
+  // every key's loads are independent -> the ~600-cycle L2 latency is paid once per 128 keys instead of once per key), with a
+  // private online softmax; the 128 partial states are merged once at the end.
+  float q[32];
+  {
+    const float4* qp = reinterpret_cast<const float4*>(base + (long long)(n - 1) * ld + h * 32);
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int c = 0; c < 8; ++c) {
+      const float4 t = __ldg(qp + c);
+      q[4 * c] = t.x * scale; q[4 * c + 1] = t.y * scale; q[4 * c + 2] = t.z * scale; q[4 * c + 3] = t.w * scale;
+    }
+  }
+  float m = -INFINITY, l = 0.f, acc[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) acc[c] = 0.f;
+  for (int j = threadIdx.x; j < n; j += 128) {
+    const float4* kp = reinterpret_cast<const float4*>(base + (long long)j * ld + D + h * 32);
+    const float4* vp = reinterpret_cast<const float4*>(base + (long long)j * ld + 2 * D + h * 32);
+    float4 kv[8], vv[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) kv[c] = __ldg(kp + c);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) vv[c] = __ldg(vp + c);
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+      s = fmaf(q[4 * c], kv[c].x, fmaf(q[4 * c + 1], kv[c].y, fmaf(q[4 * c + 2], kv[c].z, fmaf(q[4 * c + 3], kv[c].w, s))));
     const float mn = fmaxf(m, s);
-    const float c = expf(m - mn), p = expf(s - mn);           // m = -inf on the first key: c = 0
-    l = l * c + p;
-    acc = acc * c + p * row[2 * D + h * 32 + lane];
+    const float c0 = expf(m - mn), p = expf(s - mn);             // m = -inf on the first key: c0 = 0
+    l = l * c0 + p;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      acc[4 * c] = fmaf(acc[4 * c], c0, p * vv[c].x); acc[4 * c + 1] = fmaf(acc[4 * c + 1], c0, p * vv[c].y);
+      acc[4 * c + 2] = fmaf(acc[4 * c + 2], c0, p * vv[c].z); acc[4 * c + 3] = fmaf(acc[4 * c + 3], c0, p * vv[c].w);
+    }
     m = mn;
   }
-  __shared__ float sm_m[4], sm_l[4], sm_a[4][32];
-  if (lane == 0) { sm_m[warp] = m; sm_l[warp] = l; }
-  sm_a[warp][lane] = acc;
+  // merge: block maximum, rescale, sum l and the 32 output dimensions over the 128 threads
+  __shared__ float sm_m[4], sm_r[4][33];
+  float M = m;
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+  if (lane == 0) sm_m[warp] = M;
+  __syncthreads();
+  M = fmaxf(fmaxf(sm_m[0], sm_m[1]), fmaxf(sm_m[2], sm_m[3]));
+  const float f = (m == -INFINITY) ? 0.f : expf(m - M);          // threads without a key contribute nothing
+  l = warp_sum(l * f);
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    const float t = warp_sum(acc[c] * f);
+    if (lane == c) sm_r[warp][c] = t;
+  }
+  if (lane == 0) sm_r[warp][32] = l;
   __syncthreads();
   if (warp == 0) {
-    float M = fmaxf(fmaxf(sm_m[0], sm_m[1]), fmaxf(sm_m[2], sm_m[3]));
-    float L = 0.f, A = 0.f;
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-      const float c = (sm_m[w] == -INFINITY) ? 0.f : expf(sm_m[w] - M);
-      L += sm_l[w] * c;
-      A += sm_a[w][lane] * c;
-    }
-    out[(long long)b * ldo + h * 32 + lane] = A / L;
+    const float Ls = sm_r[0][32] + sm_r[1][32] + sm_r[2][32] + sm_r[3][32];
+    const float A = sm_r[0][lane] + sm_r[1][lane] + sm_r[2][lane] + sm_r[3][lane];
+    out[(long long)b * ldo + h * 32 + lane] = A / Ls;
   }
 }
 
@@ -476,6 +505,7 @@ extern "C" int evk_attn_decode(const float* qkv, int64_t batch_stride, int32_t l
                                float* out, int32_t ldo, cudaStream_t st) {
   EVK_REQUIRE(qkv && out && B >= 1 && H >= 1 && n_keys >= 1, EVK_ERR_ARG, "attn_decode: bad arguments");
   EVK_REQUIRE(ld >= 3 * H * 32 && ldo >= H * 32, EVK_ERR_ARG, "attn_decode: row pitch %d / %d too small for %d heads of 32", ld, ldo, H);
+  EVK_REQUIRE(ld % 4 == 0 && batch_stride % 4 == 0 && ((uintptr_t)qkv % 16) == 0, EVK_ERR_ARG, "attn_decode: rows must be 16-byte aligned");
   attn_decode_kernel<<<dim3(H, B), 128, 0, st>>>(qkv, batch_stride, ld, n_keys, nullptr, H, scale, out, ldo);
   return check_launch("attn_decode");
 }
@@ -484,6 +514,7 @@ extern "C" int evk_attn_decode_dev(const float* qkv, int64_t batch_stride, int32
                                    float scale, float* out, int32_t ldo, cudaStream_t st) {
   EVK_REQUIRE(qkv && out && n_prev_dev && B >= 1 && H >= 1, EVK_ERR_ARG, "attn_decode_dev: bad arguments");
   EVK_REQUIRE(ld >= 3 * H * 32 && ldo >= H * 32, EVK_ERR_ARG, "attn_decode_dev: row pitch %d / %d too small for %d heads of 32", ld, ldo, H);
+  EVK_REQUIRE(ld % 4 == 0 && batch_stride % 4 == 0 && ((uintptr_t)qkv % 16) == 0, EVK_ERR_ARG, "attn_decode_dev: rows must be 16-byte aligned");
   attn_decode_kernel<<<dim3(H, B), 128, 0, st>>>(qkv, batch_stride, ld, 0, n_prev_dev, H, scale, out, ldo);
   return check_launch("attn_decode_dev");
 }

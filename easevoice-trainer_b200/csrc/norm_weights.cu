@@ -35,6 +35,42 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, int ldx, const
   if (lane == 0 && stats) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
 }
 
+// A handful of rows (the token step of the KV-cache decode: ONE row of 512): the warp-per-row kernel above keeps 16 values per
+// lane in a run-time indexed array (local memory) and ran 11 us per launch; here a whole 256-thread block takes a row.
+__global__ void __launch_bounds__(256) layernorm_fwd_block_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ res, int ldr,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                                                  float* __restrict__ y, int ldy, float* __restrict__ stats, int C) {
+  __shared__ float red[33];
+  const long long row = blockIdx.x;
+  float v[4];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = threadIdx.x + 256 * i;
+    float t = 0.f;
+    if (c < C) {
+      t = x[row * ldx + c];
+      if (res) t += res[row * ldr + c];
+    }
+    v[i] = t;
+    s += t;
+  }
+  const float mean = block_sum(s, red) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float d = (threadIdx.x + 256 * i < C) ? v[i] - mean : 0.f;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(block_sum(q, red) / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = threadIdx.x + 256 * i;
+    if (c < C) y[row * ldy + c] = (v[i] - mean) * rstd * gamma[c] + beta[c];
+  }
+  if (threadIdx.x == 0 && stats) { stats[row * 2] = mean; stats[row * 2 + 1] = rstd; }
+}
+
 // dx = rstd * (g*dy - mean(g*dy) - xhat * mean(g*dy*xhat)); dgamma += dy*xhat; dbeta += dy
 __global__ void layernorm_bwd_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ res, int ldr,
                                      const float* __restrict__ gamma, const float* __restrict__ stats,
@@ -331,6 +367,10 @@ extern "C" int evk_layernorm_fwd(const float* x, int32_t ldx, const float* res, 
   EVK_REQUIRE(x && gamma && beta && y, EVK_ERR_ARG, "layernorm_fwd: null tensor");
   EVK_REQUIRE(C >= 1 && C <= 32 * LN_MAXV, EVK_ERR_UNSUPPORTED, "layernorm_fwd: C=%d unsupported", C);
   if (rows == 0) return EVK_OK;
+  if (rows <= 8) {
+    layernorm_fwd_block_kernel<<<(int)rows, 256, 0, ST>>>(x, ldx, res, ldr, gamma, beta, eps, y, ldy, stats, C);
+    return check_launch("layernorm_fwd_block");
+  }
   layernorm_fwd_kernel<<<cdiv(rows, 8), 256, 0, ST>>>(x, ldx, res, ldr, gamma, beta, eps, y, ldy, stats, rows, C);
   return check_launch("layernorm_fwd");
 }

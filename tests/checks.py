@@ -1491,8 +1491,8 @@ def check_infer_panel():
     prompts = torch.randint(0, 1024, (1, c["Yp"]), generator=g)
     # ---- the KV-cache attention kernel alone vs torch
     gg = _gen(5)
-    cache = torch.randn(2, 70, 3 * 512, generator=gg).to(DEV)
-    for n in (1, 2, 37, 70):
+    cache = torch.randn(2, 700, 3 * 512, generator=gg).to(DEV)
+    for n in (1, 2, 37, 70, 128, 129, 700):
         a = ops_mod().attn_decode(cache, n, 16)
         q = cache[:, n - 1, :512].view(2, 16, 1, 32).double().cpu()
         k = cache[:, :n, 512:1024].reshape(2, n, 16, 32).permute(0, 2, 1, 3).double().cpu()
@@ -1516,6 +1516,14 @@ def check_infer_panel():
         out.append((f"gemv_rows rows={rows} N={N} C={C} vs the unrounded weight (TF32 weight rounding only)",
                     rel(yv[0], torch.relu(xv[0].double().cpu() @ wv[:, :, 0].double().cpu().t() + bv.double().cpu()) if act == o.ACT_RELU else
                         (lambda r: torch.where(r > 0, r, 0.1 * r) if act == o.ACT_LRELU else r)(xv[0].double().cpu() @ wv[:, :, 0].double().cpu().t() + bv.double().cpu())), TOL_TC))
+    # ---- LayerNorm(x + res) of a handful of rows (block-per-row kernel of the token step) vs float64
+    for rows, C in ((1, 512), (3, 768), (8, 1000)):
+        xv, rv = torch.randn(1, rows, C, generator=gg) * 2 + 0.3, torch.randn(1, rows, C, generator=gg)
+        gm, bt = 1 + 0.1 * torch.randn(C, generator=gg), 0.1 * torch.randn(C, generator=gg)
+        with torch.no_grad():
+            yv = o.layernorm(xv.to(DEV), gm.to(DEV), bt.to(DEV), res=rv.to(DEV))
+        ref = torch.nn.functional.layer_norm((xv + rv).double(), (C,), gm.double(), bt.double(), 1e-5)
+        out.append((f"layernorm rows={rows} C={C} (+res) vs float64", rel(yv, ref), 2e-6))
     # ---- greedy decoding
     tr = []
     y, idx = net.infer_panel(x.to(DEV), torch.tensor([c["X"]], device=DEV), prompts.to(DEV), bert.to(DEV), top_k=c["top_k"], top_p=100,
