@@ -630,6 +630,256 @@ __global__ void __launch_bounds__(FWD2_THREADS, 1) flash_tc_fwd2_kernel(FlashArg
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------
+// Forward, warp-specialised with TWO threads per query row (v3).  The cycle counters of fwd2 (profiles/r2_flash_tc.md) left the
+// softmax thread as the critical path with two softmax warps per scheduler; here a row's 64 scores of a tile are split between
+// two threads (warps w and w + 4 read the same TMEM lane quadrant, different columns; they exchange the row maximum through
+// shared memory and a 64-thread named barrier, keep partial row sums and each accumulate 16 of the 32 output dimensions), the CTA
+// is one 128-row UMMA tile again and two CTAs share an SM, so that 16 softmax warps are resident per SM and one CTA's prologue /
+// drain overlaps the other's steady state.   warps 0-7 softmax, 8-10 producers (one ring stage each), 11 MMA issue.
+constexpr int NS3 = 3;
+constexpr int FWD3_SMEM = P128 + NS3 * STAGE2 + A64;                // 104 448
+constexpr int FWD3_THREADS = 384;
+
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;\n" ::"r"(id) : "memory"); }
+
+__global__ void __launch_bounds__(FWD3_THREADS, 2) flash_tc_fwd3_kernel(FlashArgs a, float comp2) {
+  extern __shared__ __align__(128) uint8_t fsm[];
+  uint8_t* sQ = fsm;
+  uint8_t* ring = sQ + P128;                                        // [NS3][K panels P64 | V^T panels T64]
+  uint8_t* sP = ring + NS3 * STAGE2;
+  __shared__ __align__(8) uint64_t q_full, kv_full[NS3], kv_empty[NS3], s_full[2], p_full, o_full;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float xch[2][2][128], xl[2][128];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.z, h = blockIdx.y, i0 = (int)(gridDim.x - 1 - blockIdx.x) * 128;
+  const int L = a.L, X = a.X;
+  const int xl_ = (int)a.xlen[b], yl = (int)a.ylen[b];
+  const size_t boff = (size_t)b * L * a.ld + (size_t)h * DK;
+  const float *Q = a.q + boff, *K = a.k + boff, *V = a.v + boff;
+
+  if (tid == 0) {
+    mbar_init(&q_full, 96);
+    for (int s = 0; s < NS3; ++s) { mbar_init(&kv_full[s], 32); mbar_init(&kv_empty[s], 1); }
+    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1); mbar_init(&p_full, 256); mbar_init(&o_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 11) tmem_alloc<256>(&tmem_slot);
+  int jend = max(X, min(i0 + 128, L));
+  jend = min(jend, X + yl);
+  jend = max(jend, min(X, L));
+  const int nt = (jend + 63) >> 6;
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp < 8) {
+    // ---------------- softmax: row r, column half hc ----------------
+    const int wq = warp & 3, hc = warp >> 2, r = wq * 32 + lane;
+    const int i = i0 + r;
+    const uint32_t tg = tmem + ((uint32_t)(wq * 32) << 16);         // S0 +0, S1 +64, O_tile +128
+    const DropKey dkey = drop_key(a);
+    const float sl2 = a.scale * LOG2E * comp2;
+    const uint32_t z = (uint32_t)(b * a.H + h);
+    const uint32_t rowh = drop_row(dkey, z * (uint32_t)L + (uint32_t)i);
+    float m = -INFINITY, l = 0.f, corr_prev = 0.f;
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+    FT2_DECL(tid == 0);
+    for (int kt = 0; kt < nt; ++kt) {
+      const int j0 = kt * 64 + hc * 32;                              // first key of this thread's half tile
+      FT2_MARK(14);
+      FT2_INC(13);
+      mbar_wait(&s_full[kt & 1], (uint32_t)((kt >> 1) & 1));
+      fence_after();
+      FT2_MARK(0);
+      float s[32];
+      tmem_ld32(tg + (uint32_t)((kt & 1) * 64 + hc * 32), s);
+      float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+      if (tile_full_tc<64>(i0, kt * 64, X, xl_, yl)) {                // CTA-uniform
+#pragma unroll
+        for (int c = 0; c < 32; ++c) mx4[c & 3] = fmaxf(mx4[c & 3], s[c]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          s[c] = allowed(i, j0 + c, X, xl_, yl) ? s[c] : -INFINITY;
+          mx4[c & 3] = fmaxf(mx4[c & 3], s[c]);
+        }
+      }
+      float rmax = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      xch[kt & 1][hc][r] = rmax;
+      pair_sync(1 + wq);
+      rmax = fmaxf(rmax, xch[kt & 1][hc ^ 1][r]);
+      const float mx = fmaxf(m, rmax * sl2);
+      const float e = (mx == -INFINITY) ? 0.f : mx;
+      const float corr = ex2(m - e);
+      m = mx;
+      float rs4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 32; ++c) {
+        s[c] = ex2(fmaf(s[c], sl2, -e));
+        rs4[c & 3] += s[c];
+      }
+      l = l * corr + ((rs4[0] + rs4[1]) + (rs4[2] + rs4[3]));
+      if (dkey.thr) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          bool k0, k1;
+          drop_pair(dkey, rowh, j0 + c, k0, k1);
+          s[c] = k0 ? s[c] * dkey.inv : 0.f;
+          s[c + 1] = k1 ? s[c + 1] * dkey.inv : 0.f;
+        }
+      }
+      FT2_MARK(1);
+      if (kt > 0) {                                                  // O_tile(kt-1) ready, P buffer free
+        mbar_wait(&o_full, (uint32_t)((kt - 1) & 1));
+        fence_after();
+        FT2_MARK(2);
+        uint32_t rr[16];
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                     : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]), "=r"(rr[8]),
+                       "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
+                     : "r"(tg + 128u + (uint32_t)(16 * hc)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[c] = fmaf(acc[c], corr_prev, __uint_as_float(rr[c]));
+      }
+      FT2_MARK(3);
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4)
+        *reinterpret_cast<float4*>(sP + ((size_t)(hc * 8 + c4) * QP + r) * 16) = make_float4(s[4 * c4], s[4 * c4 + 1], s[4 * c4 + 2], s[4 * c4 + 3]);
+      corr_prev = corr;
+      fence_async_smem();
+      fence_before();
+      mbar_arrive(&p_full);
+      FT2_MARK(4);
+    }
+    FT2_FLUSH(0, 4, 14);
+#ifdef FT_PROFILE
+    if (ft2_on) atomicAdd(&g_ft_prof[13], ft2_acc[13]);
+#endif
+    if (nt > 0) {
+      mbar_wait(&o_full, (uint32_t)((nt - 1) & 1));
+      fence_after();
+      uint32_t rr[16];
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+                   : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]), "=r"(rr[8]),
+                     "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15])
+                   : "r"(tg + 128u + (uint32_t)(16 * hc)));
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc[c] = fmaf(acc[c], corr_prev, __uint_as_float(rr[c]));
+    }
+    xl[hc][r] = l;                                                   // the two partial row sums share every running maximum
+    pair_sync(1 + wq);
+    l += xl[hc ^ 1][r];
+    if (i < L) {
+      const float inv = l > 0.f ? comp2 / l : 0.f;
+      float* O = a.o + ((size_t)b * L + i) * a.ldo + (size_t)h * DK + 16 * hc;
+#pragma unroll
+      for (int c = 0; c < 16; c += 4)
+        *reinterpret_cast<float4*>(O + c) = make_float4(acc[c] * inv, acc[c + 1] * inv, acc[c + 2] * inv, acc[c + 3] * inv);
+      if (hc == 0) a.lse[(size_t)z * L + i] = m + log2f(l);
+    }
+  } else if (warp < 11) {
+    // ---------------- producers: warp pw owns ring stage pw ----------------
+    const int pw = warp - 8, pt = tid - 256;
+    for (int c = pt; c < 128 * 8; c += 96) {
+      const int rr = c >> 3, j = c & 7, row = i0 + rr;
+      cp_async16(sQ + ((size_t)j * QP + rr) * 16, Q + (size_t)(row < L ? row : 0) * a.ld + j * 4, row < L ? 16 : 0);
+    }
+    cp_async_commit();
+    cp_async_wait<0>();
+    fence_async_smem();
+    mbar_arrive(&q_full);
+    const int rot = (lane >> 3) & 3;
+    uint8_t* sKs = ring + (size_t)pw * STAGE2;
+    uint8_t* sVs = sKs + P64;
+    FT2_DECL(tid == 256);
+    for (int kt = pw, n = 0; kt < nt; kt += NS3, ++n) {
+      const int j0 = kt * 64;
+      FT2_MARK(14);
+      FT2_INC(15);
+      if (n > 0) mbar_wait(&kv_empty[pw], (uint32_t)((n - 1) & 1));
+      FT2_MARK(9);
+      float4 v[16];
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const int c = lane + 32 * it, rr = c >> 3, j = c & 7, row = j0 + rr;
+        cp_async16(sKs + ((size_t)j * KP + rr) * 16, K + (size_t)(row < L ? row : 0) * a.ld + j * 4, row < L ? 16 : 0);
+      }
+      cp_async_commit();
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        const int row = j0 + 4 * it + (lane & 3);
+        v[it] = row < L ? __ldg(reinterpret_cast<const float4*>(V + (size_t)row * a.ld + 4 * (lane >> 2))) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      FT2_MARK(10);
+#pragma unroll
+      for (int it = 0; it < 16; ++it) {
+        float x[4] = {v[it].x, v[it].y, v[it].z, v[it].w};
+        rot4(x, rot);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          *reinterpret_cast<float*>(sVs + ((size_t)it * TP + 4 * (lane >> 2) + ((e + rot) & 3)) * 16 + (lane & 3) * 4) = x[e];
+      }
+      FT2_MARK(11);
+      cp_async_wait<0>();
+      fence_async_smem();
+      mbar_arrive(&kv_full[pw]);
+      FT2_MARK(12);
+    }
+    FT2_FLUSH(9, 12, -1);
+#ifdef FT_PROFILE
+    if (ft2_on) atomicAdd(&g_ft_prof[15], ft2_acc[15]);
+#endif
+  } else {
+    // ---------------- MMA issue ----------------
+    const bool leader = elect_one();
+    const uint32_t aQ = smem_u32(sQ), aP = smem_u32(sP), aR = smem_u32(ring);
+    mbar_wait(&q_full, 0);
+    fence_after();
+    FT2_DECL(leader);
+    for (int kt = 0; kt <= nt; ++kt) {
+      FT2_MARK(14);
+      if (kt < nt) {
+        const int st = kt % NS3;
+        mbar_wait(&kv_full[st], (uint32_t)((kt / NS3) & 1));
+        fence_after();
+        FT2_MARK(5);
+        if (leader) {
+          mma_panels(tmem + (uint32_t)((kt & 1) * 64), aQ, QP, aR + (uint32_t)(st * STAGE2), KP, 4, idesc_n(64), false);      // S = Q K^T
+          umma_commit(&s_full[kt & 1]);
+        }
+        __syncwarp();
+        FT2_MARK(6);
+      }
+      if (kt > 0) {
+        const int t = kt - 1, st = t % NS3;
+        mbar_wait(&p_full, (uint32_t)(t & 1));
+        fence_after();
+        FT2_MARK(7);
+        if (leader) {
+          mma_panels(tmem + 128u, aP, QP, aR + (uint32_t)(st * STAGE2 + P64), TP, 8, idesc_n(32), false);                     // O_tile = P V
+          umma_commit(&o_full);
+          umma_commit(&kv_empty[st]);
+        }
+        __syncwarp();
+        FT2_MARK(8);
+      }
+    }
+    FT2_FLUSH(5, 8, -1);
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 11) {
+    fence_after();
+    tmem_free<256>(tmem);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128, 2) flash_tc_dq_kernel(FlashArgs a, float comp2) {
   extern __shared__ __align__(128) uint8_t fsm[];
   uint8_t *sQ = fsm, *sD = sQ + P128, *sK = sD + P128, *sV = sK + P64, *sKT = sV + P64, *sS = sKT + T64;
@@ -939,7 +1189,13 @@ int flash_tc_fwd_try(const FlashArgs& a, cudaStream_t st) {
   if (!attr) {
     if (int rc = set_smem(flash_tc_fwd_kernel, FWD_SMEM)) return rc;
     if (int rc = set_smem(flash_tc_fwd2_kernel, FWD2_SMEM)) return rc;
+    if (int rc = set_smem(flash_tc_fwd3_kernel, FWD3_SMEM)) return rc;
     attr = true;
+  }
+  if (g_flash_tc >= 3) {
+    dim3 grid3(cdiv(a.L, 128), a.H, a.B);
+    flash_tc_fwd3_kernel<<<grid3, FWD3_THREADS, FWD3_SMEM, st>>>(a, comp2_now());
+    return check_launch("flash_tc_fwd3");
   }
   if (g_flash_tc >= 2) {
     dim3 grid2(cdiv(a.L, 256), a.H, a.B);

@@ -1588,7 +1588,7 @@ def check_flash_tc():
                 orf = _sdpa_oracle(qr, H, X, xl, yl)
                 orf.backward(dout.double())
                 ref = (orf.detach(), qr.grad.detach())
-            for tc in (1, 2):
+            for tc in (1, 2, 3):
                 o1, g1 = run(qkv, dout, H, X, xl, yl, p, tc)
                 fin = bool(torch.isfinite(o1).all() and torch.isfinite(g1).all())
                 out.append((f"flash_tc[{tc}] {tag} finite", 0.0 if fin else 1.0, 0.5))

@@ -41,9 +41,9 @@ for p in (0.0, 0.1):
         torch.cuda.synchronize()
         raw.evk_ft_prof_read(buf, 0)
     v = list(buf)
-    if TC == 2:
+    if TC >= 2:
         tiles, ptiles = max(v[13], 1), max(v[15], 1)
-        print(f"== v2 p_drop={p}: {e0.elapsed_time(e1):.3f} ms, {tiles} (256 x 64) tiles, {v[14] / tiles:.0f} cycles per tile per CTA")
+        print(f"== v{TC} p_drop={p}: {e0.elapsed_time(e1):.3f} ms, {tiles} tiles, {v[14] / tiles:.0f} cycles per tile per CTA")
         for i in range(13):
             print(f"   {NAMES2[i]:36s} {v[i] / (ptiles if i >= 9 else tiles):8.0f} cycles/tile")
         continue

@@ -54,7 +54,7 @@ def ref64(qkv, dout, H, X, xl, yl):
     return o.detach(), x.grad.detach()
 
 
-TC = int(os.environ.get("AB_TC", "2"))          # kernel generation under test (1: single-stage, 2: warp-specialised forward)
+TC = int(os.environ.get("AB_TC", "3"))          # kernel generation under test (1: single-stage, 2: warp-specialised forward)
 out = dict(parity=[], timing={}, tc=TC)
 g = torch.Generator().manual_seed(11)
 cases = [  # B, H, X, Y, xlens, ylens, p_drop
@@ -97,7 +97,7 @@ if "--no-time" not in sys.argv:
     xl = torch.full((B,), X, device=dev, dtype=torch.int64)
     yl = torch.full((B,), Y, device=dev, dtype=torch.int64)
     pairs = B * H * (X * L + Y * (Y + 1) // 2)
-    for tc in (0, 1, 2):
+    for tc in (0, 2, 3):
         for p in (0.0, 0.1):
             L_.evk_set_flash_tc(tc, -1.0)
             q = qkv.clone().requires_grad_(True)
