@@ -219,7 +219,28 @@ __global__ void __launch_bounds__(128, 5) flash_fwd_kernel(FlashArgs a) {
   }
 }
 
-// delta[z][i] = sum_d dO[i][d] * O[i][d]      (one warp per row, lane = d)
+// delta[z][i] = sum_d dO[i][d] * O[i][d].  Eight lanes per (position, head) row, heads fastest: a warp reads 4 x 128 contiguous
+// bytes of dO and of O with one float4 per lane (the one-warp-per-row version below spent 48 us per layer on index divisions and
+// five shuffle rounds per row: ncu, profiles/r2_ncu_flash.md).
+__global__ void __launch_bounds__(256) flash_delta8_kernel(FlashArgs a) {
+  const long long t = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long rows = (long long)a.B * a.H * a.L;
+  long long r = t >> 3;
+  const int q = (int)(t & 7);
+  const bool valid = r < rows;
+  if (!valid) r = rows - 1;
+  const int h = (int)(r % a.H);
+  const long long bi = r / a.H;                                        // b * L + i
+  const int b = (int)(bi / a.L), i = (int)(bi - (long long)b * a.L);
+  const float4 d = __ldg(reinterpret_cast<const float4*>(a.dout + bi * a.lddo + h * DK + 4 * q));
+  const float4 o = __ldg(reinterpret_cast<const float4*>(a.o + bi * a.ldo + h * DK + 4 * q));
+  float v = fmaf(d.x, o.x, fmaf(d.y, o.y, fmaf(d.z, o.z, d.w * o.w)));
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  if (valid && q == 0) ((float*)a.delta)[((size_t)b * a.H + h) * a.L + i] = v;
+}
+// general layout (rows not 16-byte aligned): one warp per row, lane = d
 __global__ void flash_delta_kernel(FlashArgs a) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -464,7 +485,8 @@ extern "C" int evk_flash_attn_bwd(const float* q, const float* k, const float* v
   a.delta = delta; a.dq = dq; a.dk = dk_; a.dv = dv; a.lddq = lddq; a.B = B; a.H = H; a.L = L; a.X = X;
   a.xlen = (const long long*)xlen; a.ylen = (const long long*)ylen; a.scale = scale; a.p_drop = p_drop; a.rng = (const unsigned long long*)rng; a.sid = sid;
   const int rows = B * H * L;
-  flash_delta_kernel<<<cdiv(rows, 8), 256, 0, st>>>(a);
+  if (ldo % 4 == 0 && ((uintptr_t)o % 16) == 0) flash_delta8_kernel<<<cdiv((long long)rows * 8, 256), 256, 0, st>>>(a);
+  else flash_delta_kernel<<<cdiv(rows, 8), 256, 0, st>>>(a);
   if (int rc = check_launch("flash_delta")) return rc;
   if (!g_precise) {
     const int rc = flash_tc_bwd_try(a, st);
